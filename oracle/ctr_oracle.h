@@ -1,0 +1,125 @@
+/*
+ * ctr_oracle.h — CPU restatement of go-ctr's CTR hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build, link,
+ * import or execute it — and there only as the checker or the reported CPU baseline, never as the
+ * thing measured or shipped.  The product (go-ctr_b200/libctr_b200.so) contains none of this code
+ * and has no CPU fallback.
+ *
+ * Every function cites the reference file:line (relative to /root/reference) it restates.
+ *
+ * PARITY PINNING:
+ *   pinned by the reference's own known-answer tests (tests/golden/kat.json):
+ *     orc_bce32            model/cost_test.go:12-55   (0.8746, 0.3335 ±1e-4)
+ *     orc_mse32/orc_rms32  model/cost_test.go:58-90
+ *     orc_prelu32          model/activation_test.go:11-24
+ *     orc_euc_distance     model/activation_test.go:26-148
+ *     orc_cosine           model/activation_test.go:150-234
+ *     orc_roc_auc          nn/metrics/ranking_test.go:9-42, utils/util_test.go:25-32 (0.75)
+ *     orc_ub_filter        feature/ubcache/cache_test.go:9-38
+ *   PARITY UNPINNED (no reference test, and gorgonia v0.9.17 / gonum v0.11.0 are third-party Go
+ *   modules absent from /root/reference; no Go toolchain here): full DIN/YouTube forward scores,
+ *   every gradient, the Adam trajectory, dropout, weight init.  For those the oracle restates the
+ *   published algorithm (formulas cited per function) and is cross-checked by finite differences.
+ */
+#ifndef CTR_ORACLE_H
+#define CTR_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_YOUTUBE = 0, ORC_DIN_COS = 1, ORC_DIN_EUC = 2 };
+
+typedef struct {
+    int model;          /* ORC_* */
+    int uP, S, D, cF;   /* uProfileDim, uBehaviorSize, uBehaviorDim(=iFeatureDim), cFeatureDim */
+    int H0, H1;         /* 200, 80 in the reference (din.go:14-19) */
+    float d0, d1;       /* dropout probabilities (din.go:204-205: .005; dnn.go:136-137: .003) */
+} orc_cfg;
+
+/* model.SampleInfo (rcmd.go:132-137): [start,end) column ranges inside a dense X row */
+typedef struct { int up[2], ub[2], it[2], cx[2]; } orc_ranges;
+
+/* ---- small known-answer-test subjects ------------------------------------------------------- */
+float orc_bce32(const float* pred, const float* y, int n);                 /* cost.go:9-17 */
+float orc_mse32(const float* pred, const float* y, int n);                 /* cost.go:20-23 */
+float orc_rms32(const float* pred, const float* y, int n);                 /* cost.go:26-29 */
+void  orc_prelu32(const float* x, float slope, int n, float* out);         /* activation.go:11-16 */
+/* x:[n,sx,d], y:[n,sy,d] with sx==sy or one of them 1 (broadcast); out:[n,max(sx,sy)]; returns 0,
+ * or -1 for unsupported shapes.  activation.go:23-50 / :57-83 */
+int   orc_euc_distance(const float* x, int sx, const float* y, int sy, int n, int d, float* out);
+int   orc_cosine(const float* x, int sx, const float* y, int sy, int n, int d, float* out);
+float orc_sigmoid32(float x);                                              /* gorgonia _sigmoidf32 */
+double orc_roc_auc(const float* pred, const float* y, int n);              /* util.go:131-148, ranking.go:13-150 */
+/* ubcache TimeSeq.Filter (cache.go:71-94): ts desc-sorted; returns count, *start = first index */
+int   orc_ub_filter(const int64_t* ts, int n, int64_t max_ts, int64_t max_len, int* start);
+int   orc_hash_onehot32(const char* s, int size);                          /* feature/multihot.go:26-35 (FNV-1) */
+
+/* ---- counter RNG shared by spec with the engine (dropout masks, weight init) ------------------ */
+uint64_t orc_mix64(uint32_t seed, uint32_t stream, uint64_t ctr);
+float    orc_uniform24(uint32_t seed, uint32_t stream, uint64_t ctr);      /* [0,1), 24 bits */
+void     orc_gaussian_init(float* w, long n, uint32_t seed, uint32_t stream); /* N(0,1), din.go:187-191 */
+
+/* ---- a1: GetSampleVector (rcmd.go:462-536), index form -------------------------------------- */
+/* vec = [user_feat[user_row] | emb[hist[0..S)] (row<0 → zeros) | emb[item_row] | item_feat[item_row]] */
+void orc_gather_rows(const float* user_feat, long ldu, const float* item_feat, long ldi,
+                     const float* item_emb, long lde, int uP, int cF, int S, int D,
+                     const int32_t* user_row, const int32_t* item_row, const int32_t* hist,
+                     long B, float* X /* [B, uP+S*D+D+cF] */);
+
+/* ---- a4–a7: forward ------------------------------------------------------------------------- */
+typedef struct orc_ws orc_ws;   /* saved activations for backward */
+orc_ws* orc_ws_new(const orc_cfg* c, int B);
+void    orc_ws_free(orc_ws* ws);
+
+/* One forward over a batch of B rows of dense X (rows >= nvalid are the zero-padded tail,
+ * model.go:132-184,357-371).  training!=0 applies dropout with masks = orc_uniform24(seed,
+ * step*4+layer, b*H+j) < 1-p, scaled 1/(1-p).  Writes p[B]; optional logit[B] (pre-sigmoid z2). */
+void orc_forward(const orc_cfg* c, const float* W0, const float* W1, const float* W2, const float* att,
+                 const float* X, long ldx, const orc_ranges* r, int B, int nvalid,
+                 int training, uint32_t seed, uint32_t step, orc_ws* ws, float* p, float* logit);
+
+/* ---- a8: backward (analytic reverse of a4-a7; + d/d(ub), d/d(item) = engine extension) ------ */
+/* y[B] (tail rows label 0).  Grads are of cost = BCE mean.  dUb [B,S*D], dIt [B,D] may be NULL.
+ * dIt includes both the MLP-input path and the attention path.  Returns cost (cost.go:9-17). */
+float orc_backward(const orc_cfg* c, const float* W0, const float* W1, const float* W2, const float* att,
+                   const orc_ws* ws, const float* y, int B,
+                   float* dW0, float* dW1, float* dW2, float* datt, float* dUb, float* dIt);
+
+/* ---- a9: gorgonia AdamSolver.Step (model.go:88,192) ----------------------------------------- */
+void orc_adam_step(float* w, float* g, float* m, float* v, long n, int t,
+                   float lr, float l2, float batch, float b1, float b2, float eps);
+
+/* ---- a3/a10: model.Train / model.Predict on dense X ----------------------------------------- */
+typedef struct {
+    float lr, l2, b1, b2, eps;      /* 0.01, 1e-4, .9, .999, 1e-8 (model.go:88) */
+    uint32_t seed;                  /* dropout seed */
+} orc_solver;
+/* weights are updated in place; returns epochs run; *last_cost = cost of last batch of last epoch
+ * (model.go:198). */
+int orc_train_dense(const orc_cfg* c, const orc_solver* s, float* W0, float* W1, float* W2, float* att,
+                    const float* X, const float* Y, long n, int xcols, const orc_ranges* r,
+                    int batch, int epochs, int early_stop, float* last_cost, int nthreads);
+void orc_predict_dense(const orc_cfg* c, const float* W0, const float* W1, const float* W2, const float* att,
+                       const float* X, long n, int xcols, const orc_ranges* r, int batch, float* out);
+
+/* ---- index-form train step (engine fast path): gather → fwd → bwd → Adam(dense) → SGD(rows) --- */
+typedef struct {
+    float *m0, *v0, *m1, *v1, *m2, *v2, *ma, *va; int t;
+} orc_adam_state;
+/* table_lr == 0 → frozen table (reference behaviour, din.go:161-169). Duplicated rows accumulate
+ * in (b, slot) order in double, then row -= table_lr * grad. Returns cost. */
+float orc_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_state* st,
+                         float* W0, float* W1, float* W2, float* att,
+                         const float* user_feat, long ldu, const float* item_feat, long ldi,
+                         float* item_emb, long lde, long n_items,
+                         const int32_t* user_row, const int32_t* item_row, const int32_t* hist,
+                         const float* y, int B, float table_lr, float* p_out, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
