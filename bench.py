@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — one "step" = one pass of the CTR hot path (gather → attention → MLP → BCE → backward →
+scatter-add + SGD(rows) + Adam(dense)) over one batch of synthetic MovieLens-shaped input.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+Prints ONE JSON line (see the task contract).  `value` = whole-job train samples/s with inputs
+resident in HBM; `e2e` = same metric through the C-ABI entry point ctr_train_step_idx with pinned
+HOST buffers (H2D of the indices/labels and D2H of the cost inside the timed region);
+`roofline` = the dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM
+peak; `cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: DIN on synthetic MovieLens-20M-shaped batches (138k users, 27k items, dim 64)
+    "din_ml20m": dict(model="din", U=138493, I=27278, D=64, S=50, uP=52, cF=53, B=65536, zipf=True,
+                      note="BASELINE.json configs[1]; item table 7 MB is L2-resident (reported, not an HBM reading)"),
+    # BASELINE.json configs[2]: YouTube DNN, 10M-item table dim 64, batch 16384
+    "youtube_10m": dict(model="youtube", U=138493, I=10_000_000, D=64, S=50, uP=52, cF=53, B=16384, zipf=False,
+                        note="BASELINE.json configs[2]"),
+    # BASELINE.json configs[3] per-GPU shard: DIN, 100M rows / 8 GPUs = 12.5M rows (3.2 GB), batch 65536, S=50
+    "din_100m_shard": dict(model="din", U=138493, I=12_500_000, D=64, S=50, uP=52, cF=53, B=65536, zipf=False,
+                           note="BASELINE.json configs[3], one GPU's 1/8 row shard; uniform indices (worst case for caches)"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def synth_batch(w, rng, B):
+    from tests.util import make_batch
+    return make_batch(rng, w["U"], w["I"], B, w["S"], pad_frac=0.2, zipf=w["zipf"])
+
+
+def algorithmic_bytes(w, hist, ir):
+    """fp32 table, int32 ids, duplicates counted, caches ignored; only rows that
+    exist (hist >= 0) are counted."""
+    B = hist.shape[0]
+    rows = int((hist >= 0).sum()) + int((ir >= 0).sum())
+    row_bytes = w["D"] * 4
+    gather = rows * row_bytes + B * (w["S"] + 2) * 4 + B * (w["uP"] + w["cF"]) * 4
+    scatter = 2 * rows * row_bytes
+    return gather, scatter, rows
+
+
+def run_reference(args, w, wname):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Go
+    (gorgonia) and cannot be built here (no Go toolchain, deps not vendored), so this times the
+    C port of its semantics (oracle/) with all host threads on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    rng = np.random.default_rng(42)
+    Bc = args.cpu_batch
+    wc = dict(w); wc["I"] = min(w["I"], 2_000_000)            # the port allocates a dense f64 accumulator per step
+    model = orc.DIN_COS if w["model"] == "din" else orc.YOUTUBE
+    ocfg = orc.make_cfg(model, w["uP"], w["S"], w["D"], w["cF"], 200, 80, 0.005, 0.005)
+    uf = rng.random((wc["U"], w["uP"]), dtype=np.float32); itf = rng.random((wc["I"], w["cF"]), dtype=np.float32)
+    emb = (rng.standard_normal((wc["I"], w["D"]), dtype=np.float32) / np.sqrt(w["D"])).astype(np.float32)
+    tr = orc.IdxTrainer(ocfg, orc.default_solver(0), orc.init_weights(ocfg, 0), uf, itf, emb)
+    from tests.util import make_batch
+    batches = [make_batch(rng, wc["U"], wc["I"], Bc, w["S"], zipf=w["zipf"]) for _ in range(2)]
+    cores = os.cpu_count() or 1
+    for i in range(args.warmup):
+        tr.step(*batches[i % 2], table_lr=0.05, nthreads=cores)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        tr.step(*batches[i % 2], table_lr=0.05, nthreads=cores)
+    dt = time.perf_counter() - t0
+    v = Bc * args.steps / dt
+    line = {"impl": "reference", "metric": "ctr_train_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wname, "sample": "each step = %d samples of the workload (bounded CPU sample)" % Bc,
+                       "model": w["model"], "S": w["S"], "D": w["D"], "items": wc["I"]},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": "%d steps x %d samples, OpenMP %d threads, C port of go-ctr semantics (Go reference unbuildable here)" % (args.steps, Bc, cores)},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline(w, seconds=12.0, Bc=4096):
+    from oracle import oracle as orc
+    from tests.util import make_batch
+    rng = np.random.default_rng(43)
+    I = min(w["I"], 1_000_000)
+    model = orc.DIN_COS if w["model"] == "din" else orc.YOUTUBE
+    ocfg = orc.make_cfg(model, w["uP"], w["S"], w["D"], w["cF"], 200, 80, 0.005, 0.005)
+    uf = rng.random((w["U"], w["uP"]), dtype=np.float32); itf = rng.random((I, w["cF"]), dtype=np.float32)
+    emb = (rng.standard_normal((I, w["D"]), dtype=np.float32) / np.sqrt(w["D"])).astype(np.float32)
+    tr = orc.IdxTrainer(ocfg, orc.default_solver(0), orc.init_weights(ocfg, 0), uf, itf, emb)
+    batch = make_batch(rng, w["U"], I, Bc, w["S"], zipf=w["zipf"])
+    cores = os.cpu_count() or 1
+    tr.step(*batch, table_lr=0.05, nthreads=cores)           # warm
+    n = 0; t0 = time.perf_counter()
+    while True:
+        tr.step(*batch, table_lr=0.05, nthreads=cores); n += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds and n >= 2:
+            break
+    return {"value": Bc * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d steps x %d samples of the same workload shape in %.1f s, OpenMP %d threads" % (n, Bc, dt, cores)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="din_ml20m", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=4096)
+    ap.add_argument("--table-opt", default="sgd", choices=["sgd", "det", "frozen"])
+    ap.add_argument("--gemm", default="auto", choices=["auto", "fp32", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-leg", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wname = args.workload
+    w = dict(WORKLOADS[wname])
+    if args.batch:
+        w["B"] = args.batch
+    if args.impl == "reference":
+        return run_reference(args, w, wname)
+
+    import torch
+    import go_ctr_b200 as g
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node N" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: this engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, peak_src = load_peaks()
+
+    def build_engine(w, B):
+        model = g.MODEL_DIN_COS if w["model"] == "din" else g.MODEL_YOUTUBE
+        topt = {"sgd": g.TABLE_SGD, "det": g.TABLE_SGD_DETERMINISTIC, "frozen": g.TABLE_FROZEN}[args.table_opt]
+        gm = {"auto": g.GEMM_AUTO, "fp32": g.GEMM_FP32, "tcgen05": g.GEMM_TCGEN05_3XTF32}[args.gemm]
+        cfg = g.engine.default_config(model, uP=w["uP"], S=w["S"], D=w["D"], cF=w["cF"], batch=B, pred_batch=B,
+                                      table_opt=topt, table_lr=0.05, gemm=gm, device=local, rank=rank, world=world, seed=1)
+        eng = g.Engine(cfg)
+        if world > 1:
+            ids = [None]
+            if rank == 0:
+                ids[0] = eng.comm_unique_id()
+            dist.broadcast_object_list(ids, src=0)
+            eng.comm_init(ids[0])
+        # synthetic MovieLens-shaped tables generated on the device: features U[0,1), embeddings N(0, 1/D)
+        eng.table_fill(g.TABLE_USER_FEAT, w["U"], w["uP"], seed=3, dist=0, scale=1.0)
+        eng.table_fill(g.TABLE_ITEM_FEAT, w["I"], w["cF"], seed=4, dist=0, scale=1.0)
+        eng.table_fill(g.TABLE_ITEM_EMB, w["I"], w["D"], seed=5, dist=1, scale=float(1.0 / np.sqrt(w["D"])))
+        return eng
+
+    def make_batches(w, B, nb, seed):
+        rng = np.random.default_rng(seed + rank)
+        out = []
+        for _ in range(nb):
+            out.append(synth_batch(w, rng, B))
+        return out
+
+    dev = torch.device("cuda", local)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def timed_leg(eng, w, B, steps, warmup, profile=False):
+        """K timed steps, inputs resident in HBM, L2 flushed before every step (outside the events)."""
+        host = make_batches(w, B, 4, 100)
+        devb = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in host]
+        st = torch.cuda.ExternalStream(eng.stream, device=dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        l0 = eng.launch_count()
+
+        def one(i, e=None):
+            ur, ir, hist, y = devb[i % len(devb)]
+            with torch.cuda.stream(st):
+                flush_buf.zero_()                                           # L2 flush (write > L2 capacity)
+                if e: e[0].record(st)
+                eng.train_step_idx_dev(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B)
+                if e: e[1].record(st)
+        for i in range(warmup):
+            one(i)
+        eng.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l1 = eng.launch_count()
+        if profile:
+            eng.profile_reset(); eng.profile(True)
+        sampler = ClockSampler(local) if not profile else None
+        t0 = time.perf_counter()
+        for i in range(steps):
+            one(warmup + i, ev[i])
+        eng.sync(); torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        if profile:
+            eng.profile(False)
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        launches = (eng.launch_count() - l1)
+        cost = eng.last_cost()
+        return dict(ms=ms, wall=wall, clocks=clocks, launches=launches, host=host, cost=cost, prof=eng.profile_dump() if profile else None)
+
+    def e2e_leg(eng, w, B, steps, warmup):
+        """Same metric through the public host-buffer entry point: pinned host indices/labels are
+        copied H2D and the step's cost is read back D2H inside every timed call."""
+        host = make_batches(w, B, 4, 200)
+        pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
+        st = g.StepStats()
+        for i in range(warmup):
+            ur, ir, hist, y = pinned[i % 4]
+            eng.train_step_idx_ptr(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B, st)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            ur, ir, hist, y = pinned[(warmup + i) % 4]
+            eng.train_step_idx_ptr(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B, st)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = sum(a.numel() * a.element_size() for a in pinned[0])
+        return dict(value=B * world * steps / dt, unit="samples/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=8,
+                    ms_per_step=1e3 * dt / steps, last_cost=st.cost)
+
+    def roofline_of(w, leg, prof, B):
+        ur, ir, hist, y = leg["host"][0]
+        gbytes, sbytes, rows = algorithmic_bytes(w, hist, ir)
+        kern = {}
+        for name, (ms, n) in prof.items():
+            kern[name] = {"ms_per_launch": ms / max(n, 1), "launches_per_step": n / max(args.steps, 1)}
+        fwd = next((k for k in kern if k.startswith("attn_fwd")), None)
+        bwd = next((k for k in kern if k.startswith("attn_bwd")), None)
+        if fwd:
+            kern[fwd]["algorithmic_bytes"] = gbytes
+            kern[fwd]["gbs"] = gbytes / (kern[fwd]["ms_per_launch"] * 1e-3) / 1e9
+        if bwd:
+            kern[bwd]["algorithmic_bytes"] = sbytes
+            kern[bwd]["gbs"] = sbytes / (kern[bwd]["ms_per_launch"] * 1e-3) / 1e9
+        cand = [k for k in (fwd, bwd) if k]
+        if not cand:
+            return None, kern
+        dom = max(cand, key=lambda k: kern[k]["ms_per_launch"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(wname, {}).get(dom)
+        pair_ms = sum(kern[k]["ms_per_launch"] for k in cand)
+        rl = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+              "frac": kern[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+              "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"], "ms_per_launch": kern[dom]["ms_per_launch"],
+              "fused_pair": {"kernels": cand, "algorithmic_bytes": gbytes + sbytes, "ms": pair_ms,
+                             "achieved": (gbytes + sbytes) / (pair_ms * 1e-3) / 1e9,
+                             "frac": (gbytes + sbytes) / (pair_ms * 1e-3) / 1e9 / hbm_peak},
+              "rows_per_launch": rows,
+              "how": "second pass of the same %d steps with every launch bracketed by CUDA events on the engine stream" % args.steps}
+        return rl, kern
+
+    B = w["B"]
+    eng = build_engine(w, B)
+    leg = timed_leg(eng, w, B, args.steps, args.warmup)
+    prof_leg = timed_leg(eng, w, B, args.steps, 1, profile=True)
+    rl, kern = roofline_of(w, prof_leg, prof_leg["prof"], B)
+    e2e = e2e_leg(eng, w, B, max(3, args.steps // 2), 2)
+    value = B * world * args.steps / (leg["ms"] * 1e-3)
+    step_ms = sum(v["ms_per_launch"] * v["launches_per_step"] for v in kern.values())
+    for v in kern.values():
+        v["share_of_step"] = v["ms_per_launch"] * v["launches_per_step"] / step_ms if step_ms else None
+    line = {"metric": "ctr_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": leg["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wname, "note": w["note"], "model": w["model"], "users": w["U"], "items": w["I"], "D": w["D"], "S": w["S"],
+                       "uP": w["uP"], "cF": w["cF"], "per_gpu_batch": B, "global_batch": B * world, "table_opt": args.table_opt,
+                       "gemm": args.gemm, "ids": "zipf(1.05)" if w["zipf"] else "uniform", "history_padding": "20% of samples have a -1 padded tail",
+                       "l2": "256 MiB buffer written before every timed step (outside the event pair); per-step event pairs are summed",
+                       "parallelism": "1 process per GPU; ITEM_EMB rows sharded row%%world" if world > 1 else "single GPU"},
+            "clocks": leg["clocks"], "e2e": {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+            "e2e_ms_per_step": e2e["ms_per_step"], "gpu_launches": int(leg["launches"]), "last_cost": leg["cost"],
+            "wall_s_timed_region": leg["wall"], "roofline": rl, "kernels": kern}
+    if rank == 0 and world == 1 and not args.no_hbm_leg and wname != "din_100m_shard":
+        # HBM-fair reading of the same kernels: a table far larger than L2
+        del eng
+        torch.cuda.empty_cache()
+        w2 = dict(WORKLOADS["din_100m_shard"])
+        eng2 = build_engine(w2, w2["B"])
+        leg2 = timed_leg(eng2, w2, w2["B"], max(5, args.steps // 2), 3)
+        p2 = timed_leg(eng2, w2, w2["B"], max(5, args.steps // 2), 1, profile=True)
+        steps_saved = args.steps; args.steps = max(5, args.steps // 2)
+        rl2, kern2 = roofline_of(w2, p2, p2["prof"], w2["B"])
+        args.steps = steps_saved
+        line["hbm_roofline"] = {"workload": "din_100m_shard", "note": w2["note"], "items": w2["I"], "per_gpu_batch": w2["B"],
+                                "samples_per_sec": w2["B"] * max(5, steps_saved // 2) / (leg2["ms"] * 1e-3),
+                                "ms_per_step": leg2["ms"] / max(5, steps_saved // 2), "roofline": rl2,
+                                "kernels": {k: v for k, v in kern2.items() if k.startswith("attn")}}
+        del eng2
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(w)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,117 @@
+// common.cuh — device helpers shared by the engine's kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ctr {
+
+constexpr int kWarp = 32;
+
+// gorgonia v0.9.17 float32 sigmoid semantics (saturates outside [-88, 15]); the product of the
+// reference's model.go / din.go graph nodes `G.Sigmoid` (din.go:273,307,311,315).
+__device__ __forceinline__ float sigmoid32(float x) {
+    if (x < -88.0f) return 0.0f;
+    if (x > 15.0f) return 1.0f;
+    return 1.0f / (1.0f + __expf(-x));
+}
+
+// Counter RNG (spec shared with the test oracle; implemented independently here): dropout masks
+// (G.Dropout, din.go:308,312) and N(0,1) init (din.go:187-191).
+__host__ __device__ __forceinline__ uint64_t mix64(uint32_t seed, uint32_t stream, uint64_t ctr) {
+    uint64_t z = (((uint64_t)seed << 32) | stream) * 0x9E3779B97F4A7C15ull + ctr * 0xD1B54A32D192ED03ull
+                 + 0x632BE59BD9B4E019ull;
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return z;
+}
+__host__ __device__ __forceinline__ float uniform24(uint32_t seed, uint32_t stream, uint64_t ctr) {
+    return (float)(mix64(seed, stream, ctr) >> 40) * (1.0f / 16777216.0f);
+}
+// dropout keep-factor: 0 or 1/(1-p)
+__device__ __forceinline__ float drop_keep(float p, uint32_t seed, uint32_t stream, uint64_t ctr) {
+    if (p <= 0.0f) return 1.0f;
+    return uniform24(seed, stream, ctr) < (1.0f - p) ? 1.0f / (1.0f - p) : 0.0f;
+}
+// derivative factor through dropout+sigmoid given the stored post-dropout activation hd = h*keep:
+// keep * h * (1-h); a dropped (or saturated-to-0) unit has hd == 0 and contributes 0.
+__device__ __forceinline__ float dsigmoid_drop(float hd, float p) {
+    if (hd == 0.0f) return 0.0f;
+    if (p <= 0.0f) return hd * (1.0f - hd);
+    float h = hd * (1.0f - p);
+    return (1.0f / (1.0f - p)) * h * (1.0f - h);
+}
+
+template <int W>
+__device__ __forceinline__ float group_sum(float v) {     // sum over aligned groups of W lanes
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v); }
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming 128-bit load that does not allocate in L1 (rows are used once per kernel)
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+// 128-bit vector reduction into global memory (sm_90+): one L2 atomic transaction per 16 bytes
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float4 fma4(float s, float4 a, float4 c) {
+    return make_float4(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y), fmaf(s, a.z, c.z), fmaf(s, a.w, c.w));
+}
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// Where one sample's rows come from.  index mode: the HBM tables + per-sample row ids
+// (GetSampleVector rcmd.go:462-536 done inside the kernel).  dense mode: a materialised X row and
+// SampleInfo column offsets (model.Train's tensor.Slice calls, model.go:129-171).
+struct RowSrc {
+    const float* emb;   long lde;     // ITEM_EMB  [I, D]
+    const float* ufeat; long ldu;     // USER_FEAT [U, uP]
+    const float* ifeat; long ldi;     // ITEM_FEAT [I, cF]
+    const int* user_row; const int* item_row; const int* hist;   // [B] [B] [B,S]
+    const float* X; long ldx; int up0, ub0, it0, cx0;            // dense mode
+    int dense;
+    int nvalid;          // rows >= nvalid are the zero-padded tail (model.go:357-371)
+};
+
+struct Dims { int uP, S, D, cF, in; };
+
+__device__ __forceinline__ const float* src_ub(const RowSrc& r, const Dims& d, int b, int s) {
+    if (b >= r.nvalid) return nullptr;
+    if (r.dense) return r.X + (long)b * r.ldx + r.ub0 + (long)s * d.D;
+    int idx = r.hist[(long)b * d.S + s];
+    return idx >= 0 ? r.emb + (long)idx * r.lde : nullptr;
+}
+__device__ __forceinline__ const float* src_it(const RowSrc& r, const Dims& d, int b) {
+    if (b >= r.nvalid) return nullptr;
+    if (r.dense) return r.X + (long)b * r.ldx + r.it0;
+    int idx = r.item_row[b];
+    return idx >= 0 ? r.emb + (long)idx * r.lde : nullptr;
+}
+__device__ __forceinline__ const float* src_up(const RowSrc& r, int b) {
+    if (b >= r.nvalid) return nullptr;
+    if (r.dense) return r.X + (long)b * r.ldx + r.up0;
+    int idx = r.user_row[b];
+    return idx >= 0 ? r.ufeat + (long)idx * r.ldu : nullptr;
+}
+__device__ __forceinline__ const float* src_cx(const RowSrc& r, int b) {
+    if (b >= r.nvalid) return nullptr;
+    if (r.dense) return r.X + (long)b * r.ldx + r.cx0;
+    int idx = r.item_row[b];
+    return idx >= 0 ? r.ifeat + (long)idx * r.ldi : nullptr;
+}
+
+}  // namespace ctr

@@ -1,0 +1,793 @@
+// engine.cu — libctr_b200.so: handle, host-side mirror of model.Train / model.Predict
+// (model/model.go:27-353 of auxten/go-ctr) and the C ABI of include/ctr_b200.h.
+// sm_100a only; no CPU fallback: every compute entry point launches CUDA kernels or fails.
+#include "../../include/ctr_b200.h"
+#include "attn.cuh"
+#include "mlp.cuh"
+#include "auc.cuh"
+#include "comm.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace ctr;
+
+namespace {
+
+std::string g_create_error;
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct Prof { double ms = 0; long n = 0; };
+
+}  // namespace
+
+struct ctr_handle {
+    ctr_config cfg{};
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    mutable std::string err;
+    std::mutex mu;                        // Predict may be hit concurrently (gin handlers, api.go:106-131)
+
+    int in = 0, Kp = 0, H0p = 0, H1p = 0, Sp = 0, lddx = 0, Bmax = 0;
+    int num_sms = 148;
+
+    // tables (HBM resident)
+    float* tab[3] = {nullptr, nullptr, nullptr};
+    long tab_ld[3] = {0, 0, 0};
+    int64_t tab_rows[3] = {0, 0, 0};      // logical (global) rows
+    int64_t tab_local_rows[3] = {0, 0, 0};
+    int tab_width[3] = {0, 0, 0};
+
+    // learnables, padded storage: W0 [Kp,H0p] W1 [H0p,H1p] W2 [H1p] att [Sp]; grads / Adam moments alike
+    float *W[4] = {}, *G[4] = {}, *Mo[4] = {}, *Vo[4] = {};
+    size_t wsize[4] = {};
+    uint32_t step = 0;                    // optimiser steps taken (Adam t = step+1; dropout stream = step*4+layer)
+
+    // activations
+    float *X0 = nullptr, *H0d = nullptr, *H1d = nullptr, *P = nullptr, *Z = nullptr;
+    float *dZ1 = nullptr, *dZ0 = nullptr, *dX = nullptr;
+    float *dUb = nullptr, *dIt = nullptr;         // row-gradient buffers (deterministic / debug)
+    size_t dUb_cap = 0;
+    unsigned *keys = nullptr, *keys2 = nullptr, *pos = nullptr, *pos2 = nullptr;
+    void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0; size_t keys_cap = 0;
+    double* d_cost = nullptr;
+    // staging for host-pointer entry points
+    int *s_user = nullptr, *s_item = nullptr, *s_hist = nullptr; float* s_label = nullptr;
+    // dense-X residency
+    float* dXd = nullptr; float* dYd = nullptr; size_t dXd_cap = 0, dYd_cap = 0;
+
+    int64_t launches = 0;
+    bool profiling = false;
+    std::map<std::string, Prof> prof;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    Comm comm;
+};
+
+namespace {
+
+int set_err(const ctr_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return set_err(h, e_ == cudaErrorMemoryAllocation ? CTR_ENOMEM : CTR_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+#define RET(x) do { int r_ = (x); if (r_ != CTR_OK) return r_; } while (0)
+
+// every kernel launch goes through here: counts it and, when profiling, brackets it with events
+template <typename F>
+int launch(ctr_handle* h, const char* name, F&& f) {
+    if (h->profiling) cudaEventRecord(h->ev0, h->stream);
+    f();
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(h, CTR_ECUDA, "launch %s: %s", name, cudaGetErrorString(e));
+    if (h->profiling) {
+        cudaEventRecord(h->ev1, h->stream);
+        cudaEventSynchronize(h->ev1);
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        Prof& p = h->prof[name]; p.ms += ms; p.n++;
+    }
+    return CTR_OK;
+}
+
+template <typename T>
+int dalloc(ctr_handle* h, T** p, size_t n, bool zero = true) {
+    CU(h, cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    if (zero) CU(h, cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+    return CTR_OK;
+}
+
+Dims dims_of(const ctr_handle* h) { return Dims{h->cfg.uP, h->cfg.S, h->cfg.D, h->cfg.cF, h->in}; }
+
+int grid_for_warps(const ctr_handle* h, int B) {
+    int blocks = (B + 7) / 8;
+    return std::max(1, std::min(blocks, h->num_sms * 8));
+}
+
+bool vec_ok(const ctr_handle* h, const RowSrc& r) {
+    int D = h->cfg.D;
+    if (D % 4) return false;
+    int lpr = D / 4;
+    if (lpr > 32 || (lpr & (lpr - 1))) return false;
+    if (r.dense) return (r.ldx % 4 == 0) && (r.ub0 % 4 == 0) && (r.it0 % 4 == 0) && (((uintptr_t)r.X) % 16 == 0);
+    return r.lde % 4 == 0;
+}
+
+template <int LPR>
+void launch_fwd_vec(ctr_handle* h, const RowSrc& r, int B) {
+    size_t smem = (size_t)8 * h->Kp * sizeof(float);
+    k_attn_fwd_vec<LPR><<<grid_for_warps(h, B), 256, smem, h->stream>>>(r, dims_of(h), h->cfg.model, h->W[3], h->X0, h->Kp, h->Kp, B);
+}
+template <int LPR>
+void launch_bwd_vec(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
+    size_t smem = (size_t)std::max(h->cfg.S, 1) * sizeof(float);
+    k_attn_bwd_vec<LPR><<<grid_for_warps(h, B), 256, smem, h->stream>>>(r, dims_of(h), h->cfg.model, h->W[3], h->dX, h->lddx, o, B);
+}
+
+int attn_forward(ctr_handle* h, const RowSrc& r, int B) {
+    if (vec_ok(h, r)) {
+        return launch(h, "attn_fwd_vec", [&] {
+            switch (h->cfg.D / 4) {
+                case 1: launch_fwd_vec<1>(h, r, B); break;   case 2: launch_fwd_vec<2>(h, r, B); break;
+                case 4: launch_fwd_vec<4>(h, r, B); break;   case 8: launch_fwd_vec<8>(h, r, B); break;
+                case 16: launch_fwd_vec<16>(h, r, B); break; default: launch_fwd_vec<32>(h, r, B); break;
+            }
+        });
+    }
+    return launch(h, "attn_fwd_gen", [&] {
+        k_attn_fwd_gen<<<grid_for_warps(h, B), 256, 0, h->stream>>>(r, dims_of(h), h->cfg.model, h->W[3], h->X0, h->Kp, h->Kp, B);
+    });
+}
+
+int attn_backward(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
+    if (vec_ok(h, r)) {
+        return launch(h, "attn_bwd_vec", [&] {
+            switch (h->cfg.D / 4) {
+                case 1: launch_bwd_vec<1>(h, r, o, B); break;   case 2: launch_bwd_vec<2>(h, r, o, B); break;
+                case 4: launch_bwd_vec<4>(h, r, o, B); break;   case 8: launch_bwd_vec<8>(h, r, o, B); break;
+                case 16: launch_bwd_vec<16>(h, r, o, B); break; default: launch_bwd_vec<32>(h, r, o, B); break;
+            }
+        });
+    }
+    return launch(h, "attn_bwd_gen", [&] {
+        size_t smem = (size_t)std::max(h->cfg.S, 1) * sizeof(float);
+        k_attn_bwd_gen<<<grid_for_warps(h, B), 256, smem, h->stream>>>(r, dims_of(h), h->cfg.model, h->W[3], h->dX, h->lddx, o, B);
+    });
+}
+
+// ---- fp32 GEMM launchers ---------------------------------------------------------------------------
+template <bool TA, bool TB, int EPI>
+int gemm_big(ctr_handle* h, const char* name, GemmArgs g) {     // M = batch: 128x64 tiles
+    constexpr int BM = 128, BN = 64;
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, 1);
+    return launch(h, name, [&] { k_sgemm<BM, BN, 16, 8, 4, TA, TB, EPI><<<grid, 256, 0, h->stream>>>(g); });
+}
+int gemm_dw(ctr_handle* h, const char* name, GemmArgs g) {      // K = batch: 64x64 tiles, split-K atomics
+    constexpr int BM = 64, BN = 64;
+    int tiles = ((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM);
+    int want_z = std::max(1, (h->num_sms * 4) / std::max(tiles, 1));
+    int kchunk = round_up(std::max(16, (g.K + want_z - 1) / want_z), 16);
+    g.kchunk = kchunk;
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (g.K + kchunk - 1) / kchunk);
+    return launch(h, name, [&] { k_sgemm<BM, BN, 16, 4, 4, true, false, EPI_ATOMIC><<<grid, 256, 0, h->stream>>>(g); });
+}
+
+// One pass of the hot path over one batch (model.go:107-196 inner loop body).
+//   training: dropout on, backward + optimiser step (update) or gradients only (!update)
+struct StepOpts {
+    bool training = false, update = false;
+    bool want_rows = false;              // fill h->dUb / h->dIt
+    const float* d_label = nullptr;
+};
+
+int ensure_rowgrad_buffers(ctr_handle* h, int B) {
+    size_t need = (size_t)B * h->cfg.S * h->cfg.D;
+    if (h->dUb_cap >= need && h->dUb) return CTR_OK;
+    if (h->dUb) cudaFree(h->dUb);
+    if (h->dIt) cudaFree(h->dIt);
+    h->dUb = h->dIt = nullptr;
+    RET(dalloc(h, &h->dUb, need));
+    RET(dalloc(h, &h->dIt, (size_t)B * h->cfg.D));
+    h->dUb_cap = need;
+    return CTR_OK;
+}
+
+int deterministic_table_update(ctr_handle* h, const RowSrc& r, int B) {
+    const int S = h->cfg.S, D = h->cfg.D;
+    size_t n = (size_t)B * (S + 1);
+    if (h->keys_cap < n) {
+        for (void* p : {(void*)h->keys, (void*)h->keys2, (void*)h->pos, (void*)h->pos2, h->sort_tmp}) if (p) cudaFree(p);
+        h->keys = h->keys2 = h->pos = h->pos2 = nullptr; h->sort_tmp = nullptr;
+        RET(dalloc(h, &h->keys, n, false)); RET(dalloc(h, &h->keys2, n, false));
+        RET(dalloc(h, &h->pos, n, false)); RET(dalloc(h, &h->pos2, n, false));
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->keys, h->keys2, h->pos, h->pos2, (int)n, 0, 32, h->stream);
+        CU(h, cudaMalloc(&h->sort_tmp, bytes));
+        h->sort_tmp_bytes = bytes; h->keys_cap = n;
+    }
+    RET(launch(h, "scatter_keys", [&] {
+        k_scatter_keys<<<std::min<int>((int)((n + 255) / 256), h->num_sms * 8), 256, 0, h->stream>>>(r.hist, r.item_row, S, B, h->keys, h->pos);
+    }));
+    RET(launch(h, "cub_radix_sort_pairs", [&] {
+        cub::DeviceRadixSort::SortPairs(h->sort_tmp, h->sort_tmp_bytes, h->keys, h->keys2, h->pos, h->pos2, (int)n, 0, 32, h->stream);
+    }));
+    RET(launch(h, "segment_sgd", [&] {
+        k_segment_sgd<<<std::min<int>((int)((n * 32 + 255) / 256), h->num_sms * 16), 256, 0, h->stream>>>(
+            h->keys2, h->pos2, (long)n, h->dUb, h->dIt, S, D, h->tab[CTR_TABLE_ITEM_EMB], h->tab_ld[CTR_TABLE_ITEM_EMB], h->cfg.table_lr);
+    }));
+    return CTR_OK;
+}
+
+int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
+    const ctr_config& c = h->cfg;
+    if (B <= 0 || B > h->Bmax) return set_err(h, CTR_EINVAL, "batch %d outside (0, %d]", B, h->Bmax);
+    const float d0 = o.training ? c.dropout0 : 0.0f, d1 = o.training ? c.dropout1 : 0.0f;
+
+    RET(attn_forward(h, r, B));
+    {   // h0 = dropout(sigmoid(x·W0))   din.go:307-308
+        GemmArgs g{}; g.A = h->X0; g.lda = h->Kp; g.B = h->W[0]; g.ldb = h->H0p; g.C = h->H0d; g.ldc = h->H0p;
+        g.M = B; g.N = c.H0; g.K = h->in; g.Nz = h->H0p; g.drop_p = d0; g.seed = c.seed; g.stream = h->step * 4u + 0u;
+        RET((gemm_big<false, false, EPI_SIGMOID_DROP>(h, "sgemm_fwd0_sigmoid", g)));
+    }
+    {   // h1 = dropout(sigmoid(h0·W1))  din.go:311-312
+        GemmArgs g{}; g.A = h->H0d; g.lda = h->H0p; g.B = h->W[1]; g.ldb = h->H1p; g.C = h->H1d; g.ldc = h->H1p;
+        g.M = B; g.N = c.H1; g.K = c.H0; g.Nz = h->H1p; g.drop_p = d1; g.seed = c.seed; g.stream = h->step * 4u + 1u;
+        RET((gemm_big<false, false, EPI_SIGMOID_DROP>(h, "sgemm_fwd1_sigmoid", g)));
+    }
+    const bool bwd = o.training;
+    if (bwd) CU(h, cudaMemsetAsync(h->d_cost, 0, sizeof(double), h->stream));
+    {
+        HeadArgs a{}; a.H1d = h->H1d; a.ldh = h->H1p; a.H1 = c.H1; a.H1p = h->H1p; a.w2 = h->W[2];
+        a.y = bwd ? o.d_label : nullptr; a.B = B; a.nvalid = r.nvalid; a.drop_p = d1;
+        a.p = h->P; a.logit = h->Z; a.dZ1 = bwd ? h->dZ1 : nullptr; a.lddz = h->H1p; a.dW2 = h->G[2]; a.cost_sum = h->d_cost;
+        RET(launch(h, bwd ? "head_fwd_bwd" : "head_fwd", [&] { k_head<<<grid_for_warps(h, B), 256, 0, h->stream>>>(a); }));
+    }
+    if (!bwd) return CTR_OK;
+
+    {   // dW1 += h0dᵀ · dZ1
+        GemmArgs g{}; g.A = h->H0d; g.lda = h->H0p; g.B = h->dZ1; g.ldb = h->H1p; g.C = h->G[1]; g.ldc = h->H1p;
+        g.M = c.H0; g.N = c.H1; g.K = B;
+        RET(gemm_dw(h, "sgemm_dW1_splitk", g));
+    }
+    {   // dZ0 = (dZ1 · W1ᵀ) ⊙ dsigmoid(h0d)
+        GemmArgs g{}; g.A = h->dZ1; g.lda = h->H1p; g.B = h->W[1]; g.ldb = h->H1p; g.C = h->dZ0; g.ldc = h->H0p;
+        g.M = B; g.N = c.H0; g.K = c.H1; g.Nz = h->H0p; g.H = h->H0d; g.ldh = h->H0p; g.drop_p = d0;
+        RET((gemm_big<false, true, EPI_DSIGMOID>(h, "sgemm_dZ0_dsigmoid", g)));
+    }
+    {   // dW0 += x0ᵀ · dZ0
+        GemmArgs g{}; g.A = h->X0; g.lda = h->Kp; g.B = h->dZ0; g.ldb = h->H0p; g.C = h->G[0]; g.ldc = h->H0p;
+        g.M = h->in; g.N = c.H0; g.K = B;
+        RET(gemm_dw(h, "sgemm_dW0_splitk", g));
+    }
+    const bool learn_rows = o.update && c.table_opt != CTR_TABLE_FROZEN && !r.dense;
+    const bool need_attn_bwd = c.model != CTR_MODEL_YOUTUBE || learn_rows || o.want_rows;
+    if (need_attn_bwd) {
+        {   // d concat[:, uP:uP+2D] = dZ0 · W0[uP:uP+2D, :]ᵀ
+            GemmArgs g{}; g.A = h->dZ0; g.lda = h->H0p; g.B = h->W[0] + (long)c.uP * h->H0p; g.ldb = h->H0p;
+            g.C = h->dX; g.ldc = h->lddx; g.M = B; g.N = 2 * c.D; g.K = c.H0; g.Nz = h->lddx;
+            RET((gemm_big<false, true, EPI_STORE>(h, "sgemm_dX", g)));
+        }
+        const bool buffers = o.want_rows || (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC);
+        if (buffers) RET(ensure_rowgrad_buffers(h, B));
+        BwdOut bo{}; bo.datt = h->G[3]; bo.dUb = buffers ? h->dUb : nullptr; bo.dIt = buffers ? h->dIt : nullptr;
+        bo.sgd = (learn_rows && c.table_opt == CTR_TABLE_SGD) ? 1 : 0; bo.neg_lr = -c.table_lr;
+        RET(attn_backward(h, r, bo, B));
+        if (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC) RET(deterministic_table_update(h, r, B));
+    }
+    if (o.update) {
+        if (h->comm.world > 1) RET(comm_allreduce_grads(h));
+        AdamArgs a{};
+        const int in = h->in;
+        a.t[0] = AdamTensor{h->W[0], h->G[0], h->Mo[0], h->Vo[0], in, c.H0, h->H0p};
+        a.t[1] = AdamTensor{h->W[1], h->G[1], h->Mo[1], h->Vo[1], c.H0, c.H1, h->H1p};
+        a.t[2] = AdamTensor{h->W[2], h->G[2], h->Mo[2], h->Vo[2], 1, c.H1, h->H1p};
+        a.t[3] = AdamTensor{h->W[3], h->G[3], h->Mo[3], h->Vo[3], 1, c.S, h->Sp};
+        a.nt = c.model == CTR_MODEL_YOUTUBE ? 3 : 4;       // Learnable(): dnn.go:153 vs din.go:161-169
+        const int t = (int)h->step + 1;
+        a.lr = c.lr; a.l2 = c.l2; a.inv_batch = B > 1 ? 1.0f / (float)B : 1.0f; a.b1 = c.beta1; a.b2 = c.beta2; a.eps = c.eps;
+        a.c1 = (float)(1.0 - std::pow((double)c.beta1, (double)t));
+        a.c2 = (float)(1.0 - std::pow((double)c.beta2, (double)t));
+        RET(launch(h, "adam_dense", [&] { k_adam<<<h->num_sms, 256, 0, h->stream>>>(a); }));
+        h->step++;
+    }
+    return CTR_OK;
+}
+
+int zero_grads(ctr_handle* h) {
+    for (int i = 0; i < 4; i++) CU(h, cudaMemsetAsync(h->G[i], 0, h->wsize[i] * sizeof(float), h->stream));
+    return CTR_OK;
+}
+
+RowSrc idx_src(const ctr_handle* h, const int* d_user, const int* d_item, const int* d_hist, int B) {
+    RowSrc r{};
+    r.emb = h->tab[CTR_TABLE_ITEM_EMB]; r.lde = h->tab_ld[CTR_TABLE_ITEM_EMB];
+    r.ufeat = h->tab[CTR_TABLE_USER_FEAT]; r.ldu = h->tab_ld[CTR_TABLE_USER_FEAT];
+    r.ifeat = h->tab[CTR_TABLE_ITEM_FEAT]; r.ldi = h->tab_ld[CTR_TABLE_ITEM_FEAT];
+    r.user_row = d_user; r.item_row = d_item; r.hist = d_hist;
+    r.dense = 0; r.nvalid = B;
+    return r;
+}
+
+int check_tables(const ctr_handle* h) {
+    const ctr_config& c = h->cfg;
+    if (!h->tab[CTR_TABLE_ITEM_EMB] || h->tab_width[CTR_TABLE_ITEM_EMB] != c.D)
+        return set_err(h, CTR_ESTATE, "ITEM_EMB table not uploaded with width D=%d", c.D);
+    if (c.uP > 0 && (!h->tab[CTR_TABLE_USER_FEAT] || h->tab_width[CTR_TABLE_USER_FEAT] != c.uP))
+        return set_err(h, CTR_ESTATE, "USER_FEAT table not uploaded with width uP=%d", c.uP);
+    if (c.cF > 0 && (!h->tab[CTR_TABLE_ITEM_FEAT] || h->tab_width[CTR_TABLE_ITEM_FEAT] != c.cF))
+        return set_err(h, CTR_ESTATE, "ITEM_FEAT table not uploaded with width cF=%d", c.cF);
+    if (h->comm.world > 1) return set_err(h, CTR_ESTATE, "sharded tables: use the comm step path");
+    return CTR_OK;
+}
+
+int stage_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row, const int32_t* hist, const float* label, int B) {
+    const int S = h->cfg.S;
+    CU(h, cudaMemcpyAsync(h->s_user, user_row, sizeof(int) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->s_item, item_row, sizeof(int) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+    if (S > 0) CU(h, cudaMemcpyAsync(h->s_hist, hist, sizeof(int) * (size_t)B * S, cudaMemcpyHostToDevice, h->stream));
+    if (label) CU(h, cudaMemcpyAsync(h->s_label, label, sizeof(float) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+    return CTR_OK;
+}
+
+int read_cost(ctr_handle* h, int B, float* cost) {
+    double s = 0;
+    CU(h, cudaMemcpyAsync(&s, h->d_cost, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    *cost = -(float)(s / (double)B);         // -mean, cost.go:15
+    return CTR_OK;
+}
+
+int dense_src(ctr_handle* h, const int32_t ranges[8], int32_t xcols, RowSrc* out) {
+    const ctr_config& c = h->cfg;
+    const int up0 = ranges[0], up1 = ranges[1], ub0 = ranges[2], ub1 = ranges[3], it0 = ranges[4], it1 = ranges[5], cx0 = ranges[6], cx1 = ranges[7];
+    if (up1 - up0 != c.uP || ub1 - ub0 != c.S * c.D || it1 - it0 != c.D || cx1 - cx0 != c.cF)
+        return set_err(h, CTR_EINVAL, "SampleInfo ranges do not match the model dims (uP=%d S*D=%d D=%d cF=%d)", c.uP, c.S * c.D, c.D, c.cF);
+    for (int i = 0; i < 8; i++) if (ranges[i] < 0 || ranges[i] > xcols) return set_err(h, CTR_EINVAL, "SampleInfo range outside [0, xcols=%d]", xcols);
+    RowSrc r{}; r.dense = 1; r.ldx = xcols; r.up0 = up0; r.ub0 = ub0; r.it0 = it0; r.cx0 = cx0;
+    *out = r;
+    return CTR_OK;
+}
+
+int upload_dense(ctr_handle* h, const float* X, const float* Y, int64_t n, int32_t xcols) {
+    size_t need = (size_t)n * xcols;
+    if (h->dXd_cap < need) { if (h->dXd) cudaFree(h->dXd); h->dXd = nullptr; CU(h, cudaMalloc(&h->dXd, need * sizeof(float))); h->dXd_cap = need; }
+    CU(h, cudaMemcpyAsync(h->dXd, X, need * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (Y) {
+        if (h->dYd_cap < (size_t)n) { if (h->dYd) cudaFree(h->dYd); h->dYd = nullptr; CU(h, cudaMalloc(&h->dYd, (size_t)n * sizeof(float))); h->dYd_cap = (size_t)n; }
+        CU(h, cudaMemcpyAsync(h->dYd, Y, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    }
+    return CTR_OK;
+}
+
+void gaussian_fill(std::vector<float>& w, uint32_t seed, uint32_t stream) {
+    for (size_t i = 0; i < w.size(); i++) {       // Box–Muller on the counter RNG
+        uint64_t z = mix64(seed, stream, (uint64_t)i);
+        double u1 = ((double)(z >> 40) + 1.0) * (1.0 / 16777217.0);
+        double u2 = (double)((z >> 8) & 0xFFFFFFull) * (1.0 / 16777216.0);
+        w[i] = (float)(std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2));
+    }
+}
+
+}  // namespace
+
+#include "comm_impl.cuh"
+
+// =====================================================================================================
+extern "C" {
+
+int ctr_abi_version(void) { return CTR_B200_ABI_VERSION; }
+
+void ctr_config_default(ctr_config* c, int model) {
+    memset(c, 0, sizeof *c);
+    c->model = model;
+    c->uP = 52; c->S = 10; c->D = 16; c->cF = 53;          // example/movielens: feature.go:87-196, rcmd.go:22-24
+    c->H0 = 200; c->H1 = 80;                                // din.go:17-18
+    c->batch = 200; c->pred_batch = 100;                    // model_test.go:22, dinimpl_test.go
+    c->lr = 0.01f; c->l2 = 1e-4f; c->beta1 = 0.9f; c->beta2 = 0.999f; c->eps = 1e-8f;   // model.go:88
+    c->dropout0 = c->dropout1 = (model == CTR_MODEL_YOUTUBE) ? 0.003f : 0.005f;           // dnn.go:136-137, din.go:204-205
+    c->seed = 0; c->table_opt = CTR_TABLE_FROZEN; c->table_lr = 0.0f; c->gemm = CTR_GEMM_AUTO;
+    c->device = 0; c->rank = 0; c->world = 1;
+}
+
+const char* ctr_last_error(const ctr_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ctr_create(const ctr_config* cfg, ctr_handle** out) {
+    if (!cfg || !out) return set_err(nullptr, CTR_EINVAL, "null argument");
+    *out = nullptr;
+    const ctr_config& c = *cfg;
+    if (c.model < 0 || c.model > 2) return set_err(nullptr, CTR_EINVAL, "unknown model %d", c.model);
+    if (c.uP < 0 || c.cF < 0 || c.S < 1 || c.D < 1 || c.H0 < 1 || c.H1 < 1 || c.batch < 1 || c.pred_batch < 1)
+        return set_err(nullptr, CTR_EINVAL, "bad dims");
+    if (c.D > 32 * kGenAcc) return set_err(nullptr, CTR_EINVAL, "D=%d > %d unsupported", c.D, 32 * kGenAcc);
+    if (c.H1 > 128) return set_err(nullptr, CTR_EINVAL, "H1=%d > 128 unsupported", c.H1);
+    if (c.world < 1 || c.rank < 0 || c.rank >= c.world) return set_err(nullptr, CTR_EINVAL, "bad rank/world");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_err(nullptr, CTR_ENODEV, "no CUDA device: this engine has no CPU fallback"); }
+    if (c.device < 0 || c.device >= ndev) return set_err(nullptr, CTR_ENODEV, "device %d of %d", c.device, ndev);
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, c.device);
+    if (prop.major != 10) return set_err(nullptr, CTR_ENODEV, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+
+    ctr_handle* h = new ctr_handle();
+    h->cfg = c; h->dev = c.device; h->num_sms = prop.multiProcessorCount;
+    h->comm.rank = c.rank; h->comm.world = c.world;
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(nullptr, CTR_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); ctr_destroy(h); return CTR_ECUDA; } } while (0)
+#define RC(x) do { int r_ = (x); if (r_ != CTR_OK) { g_create_error = h->err; ctr_destroy(h); return r_; } } while (0)
+    CUC(cudaSetDevice(h->dev));
+    CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true;
+    CUC(cudaEventCreate(&h->ev0)); CUC(cudaEventCreate(&h->ev1));
+    h->in = c.uP + 2 * c.D + c.cF;                      // din.go:187
+    h->Kp = round_up(h->in, 32); h->H0p = round_up(c.H0, 32); h->H1p = round_up(c.H1, 32); h->Sp = round_up(c.S, 4);
+    h->lddx = round_up(2 * c.D, 4);
+    h->Bmax = std::max(c.batch, c.pred_batch);
+    h->wsize[0] = (size_t)h->Kp * h->H0p; h->wsize[1] = (size_t)h->H0p * h->H1p; h->wsize[2] = h->H1p; h->wsize[3] = h->Sp;
+    for (int i = 0; i < 4; i++) { RC(dalloc(h, &h->W[i], h->wsize[i])); RC(dalloc(h, &h->G[i], h->wsize[i])); RC(dalloc(h, &h->Mo[i], h->wsize[i])); RC(dalloc(h, &h->Vo[i], h->wsize[i])); }
+    const size_t B = h->Bmax;
+    RC(dalloc(h, &h->X0, B * h->Kp)); RC(dalloc(h, &h->H0d, B * h->H0p)); RC(dalloc(h, &h->H1d, B * h->H1p));
+    RC(dalloc(h, &h->P, B)); RC(dalloc(h, &h->Z, B));
+    RC(dalloc(h, &h->dZ1, B * h->H1p)); RC(dalloc(h, &h->dZ0, B * h->H0p)); RC(dalloc(h, &h->dX, B * h->lddx));
+    RC(dalloc(h, &h->d_cost, 1));
+    RC(dalloc(h, &h->s_user, B)); RC(dalloc(h, &h->s_item, B)); RC(dalloc(h, &h->s_hist, B * c.S)); RC(dalloc(h, &h->s_label, B));
+    RC(ctr_init_weights(h, c.seed));
+    CUC(cudaStreamSynchronize(h->stream));
+#undef CUC
+#undef RC
+    *out = h;
+    return CTR_OK;
+}
+
+void ctr_destroy(ctr_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    comm_destroy(h);
+    for (int i = 0; i < 3; i++) if (h->tab[i]) cudaFree(h->tab[i]);
+    for (int i = 0; i < 4; i++) for (float* p : {h->W[i], h->G[i], h->Mo[i], h->Vo[i]}) if (p) cudaFree(p);
+    for (void* p : {(void*)h->X0, (void*)h->H0d, (void*)h->H1d, (void*)h->P, (void*)h->Z, (void*)h->dZ1, (void*)h->dZ0, (void*)h->dX,
+                    (void*)h->dUb, (void*)h->dIt, (void*)h->keys, (void*)h->keys2, (void*)h->pos, (void*)h->pos2, h->sort_tmp,
+                    (void*)h->d_cost, (void*)h->s_user, (void*)h->s_item, (void*)h->s_hist, (void*)h->s_label, (void*)h->dXd, (void*)h->dYd})
+        if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int ctr_set_weights(ctr_handle* h, const float* mlp0, const float* mlp1, const float* mlp2, const float* att0) {
+    if (!h || !mlp0 || !mlp1 || !mlp2) return set_err(h, CTR_EINVAL, "null weights");
+    std::lock_guard<std::mutex> lk(h->mu);
+    const ctr_config& c = h->cfg;
+    CU(h, cudaSetDevice(h->dev));
+    for (int i = 0; i < 4; i++) {
+        CU(h, cudaMemsetAsync(h->W[i], 0, h->wsize[i] * sizeof(float), h->stream));
+        CU(h, cudaMemsetAsync(h->G[i], 0, h->wsize[i] * sizeof(float), h->stream));
+        CU(h, cudaMemsetAsync(h->Mo[i], 0, h->wsize[i] * sizeof(float), h->stream));
+        CU(h, cudaMemsetAsync(h->Vo[i], 0, h->wsize[i] * sizeof(float), h->stream));
+    }
+    CU(h, cudaMemcpy2DAsync(h->W[0], h->H0p * sizeof(float), mlp0, c.H0 * sizeof(float), c.H0 * sizeof(float), h->in, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpy2DAsync(h->W[1], h->H1p * sizeof(float), mlp1, c.H1 * sizeof(float), c.H1 * sizeof(float), c.H0, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->W[2], mlp2, c.H1 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (att0) CU(h, cudaMemcpyAsync(h->W[3], att0, c.S * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    else { std::vector<float> ones(c.S, 1.0f); CU(h, cudaMemcpyAsync(h->W[3], ones.data(), c.S * sizeof(float), cudaMemcpyHostToDevice, h->stream)); CU(h, cudaStreamSynchronize(h->stream)); }
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->step = 0;
+    return CTR_OK;
+}
+
+int ctr_init_weights(ctr_handle* h, uint32_t seed) {
+    if (!h) return CTR_EINVAL;
+    const ctr_config& c = h->cfg;
+    std::vector<float> w0((size_t)h->in * c.H0), w1((size_t)c.H0 * c.H1), w2(c.H1), a(c.S, 1.0f);   // att0 = 1: din.go:181
+    gaussian_fill(w0, seed, 0); gaussian_fill(w1, seed, 1); gaussian_fill(w2, seed, 2);
+    return ctr_set_weights(h, w0.data(), w1.data(), w2.data(), a.data());
+}
+
+int ctr_get_weights(ctr_handle* h, float* mlp0, float* mlp1, float* mlp2, float* att0) {
+    if (!h) return CTR_EINVAL;
+    std::lock_guard<std::mutex> lk(h->mu);
+    const ctr_config& c = h->cfg;
+    CU(h, cudaSetDevice(h->dev));
+    if (mlp0) CU(h, cudaMemcpy2DAsync(mlp0, c.H0 * sizeof(float), h->W[0], h->H0p * sizeof(float), c.H0 * sizeof(float), h->in, cudaMemcpyDeviceToHost, h->stream));
+    if (mlp1) CU(h, cudaMemcpy2DAsync(mlp1, c.H1 * sizeof(float), h->W[1], h->H1p * sizeof(float), c.H1 * sizeof(float), c.H0, cudaMemcpyDeviceToHost, h->stream));
+    if (mlp2) CU(h, cudaMemcpyAsync(mlp2, h->W[2], c.H1 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (att0) CU(h, cudaMemcpyAsync(att0, h->W[3], c.S * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return CTR_OK;
+}
+
+int ctr_table_upload(ctr_handle* h, int which, const float* rows, int64_t nrows, int32_t width) {
+    if (!h || !rows || which < 0 || which > 2 || nrows < 1 || width < 1) return set_err(h, CTR_EINVAL, "bad table upload arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    const ctr_config& c = h->cfg;
+    const int want = which == CTR_TABLE_USER_FEAT ? c.uP : which == CTR_TABLE_ITEM_FEAT ? c.cF : c.D;
+    if (width != want) return set_err(h, CTR_EINVAL, "table %d width %d != model dim %d", which, width, want);
+    CU(h, cudaSetDevice(h->dev));
+    if (h->tab[which]) { cudaFree(h->tab[which]); h->tab[which] = nullptr; }
+    const long ld = round_up(width, 4);                       // 16-byte aligned rows for 128-bit loads
+    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1;
+    const int64_t local = shard ? (nrows - h->comm.rank + h->comm.world - 1) / h->comm.world : nrows;
+    CU(h, cudaMalloc(&h->tab[which], (size_t)std::max<int64_t>(local, 1) * ld * sizeof(float)));
+    CU(h, cudaMemsetAsync(h->tab[which], 0, (size_t)std::max<int64_t>(local, 1) * ld * sizeof(float), h->stream));
+    if (!shard) {
+        CU(h, cudaMemcpy2DAsync(h->tab[which], ld * sizeof(float), rows, (size_t)width * sizeof(float), (size_t)width * sizeof(float), (size_t)nrows, cudaMemcpyHostToDevice, h->stream));
+    } else if (local > 0) {   // owner(row) = row % world; local row = row / world
+        CU(h, cudaMemcpy2DAsync(h->tab[which], ld * sizeof(float), rows + (size_t)h->comm.rank * width, (size_t)width * h->comm.world * sizeof(float),
+                                (size_t)width * sizeof(float), (size_t)local, cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->tab_ld[which] = ld; h->tab_rows[which] = nrows; h->tab_local_rows[which] = local; h->tab_width[which] = width;
+    return CTR_OK;
+}
+
+int ctr_table_fill(ctr_handle* h, int which, int64_t nrows, int32_t width, uint32_t seed, int32_t dist, float scale) {
+    if (!h || which < 0 || which > 2 || nrows < 1 || width < 1) return set_err(h, CTR_EINVAL, "bad table fill arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    const ctr_config& c = h->cfg;
+    const int want = which == CTR_TABLE_USER_FEAT ? c.uP : which == CTR_TABLE_ITEM_FEAT ? c.cF : c.D;
+    if (width != want) return set_err(h, CTR_EINVAL, "table %d width %d != model dim %d", which, width, want);
+    CU(h, cudaSetDevice(h->dev));
+    if (h->tab[which]) { cudaFree(h->tab[which]); h->tab[which] = nullptr; }
+    const long ld = round_up(width, 4);
+    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1;
+    const int64_t local = shard ? (nrows - h->comm.rank + h->comm.world - 1) / h->comm.world : nrows;
+    const size_t bytes = (size_t)std::max<int64_t>(local, 1) * ld * sizeof(float);
+    CU(h, cudaMalloc(&h->tab[which], bytes));
+    CU(h, cudaMemsetAsync(h->tab[which], 0, bytes, h->stream));
+    RET(launch(h, "table_fill", [&] {
+        k_table_fill<<<h->num_sms * 8, 256, 0, h->stream>>>(h->tab[which], ld, (long)local, width, shard ? h->comm.world : 1, shard ? h->comm.rank : 0,
+                                                           seed, (uint32_t)which, dist, scale);
+    }));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->tab_ld[which] = ld; h->tab_rows[which] = nrows; h->tab_local_rows[which] = local; h->tab_width[which] = width;
+    return CTR_OK;
+}
+
+int ctr_table_download(ctr_handle* h, int which, float* rows, int64_t nrows, int32_t width) {
+    if (!h || !rows || which < 0 || which > 2) return set_err(h, CTR_EINVAL, "bad table download arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->tab[which] || nrows != h->tab_rows[which] || width != h->tab_width[which]) return set_err(h, CTR_EINVAL, "table %d shape mismatch", which);
+    CU(h, cudaSetDevice(h->dev));
+    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1;
+    if (!shard) {
+        CU(h, cudaMemcpy2DAsync(rows, (size_t)width * sizeof(float), h->tab[which], h->tab_ld[which] * sizeof(float), (size_t)width * sizeof(float), (size_t)nrows, cudaMemcpyDeviceToHost, h->stream));
+    } else if (h->tab_local_rows[which] > 0) {   // fills only this rank's rows (row % world == rank)
+        CU(h, cudaMemcpy2DAsync(rows + (size_t)h->comm.rank * width, (size_t)width * h->comm.world * sizeof(float), h->tab[which], h->tab_ld[which] * sizeof(float),
+                                (size_t)width * sizeof(float), (size_t)h->tab_local_rows[which], cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    return CTR_OK;
+}
+
+int ctr_gather_rows(ctr_handle* h, const int32_t* user_row, const int32_t* item_row, const int32_t* hist, int64_t B, float* X) {
+    if (!h || !user_row || !item_row || !hist || !X || B < 1) return set_err(h, CTR_EINVAL, "bad gather arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    RET(check_tables(h));
+    CU(h, cudaSetDevice(h->dev));
+    const ctr_config& c = h->cfg;
+    const long xc = (long)c.uP + (long)c.S * c.D + c.D + c.cF;
+    float* dout = nullptr;
+    const int chunk = h->Bmax;
+    CU(h, cudaMalloc(&dout, (size_t)chunk * xc * sizeof(float)));
+    int rc = CTR_OK;
+    for (int64_t s = 0; s < B && rc == CTR_OK; s += chunk) {
+        int nb = (int)std::min<int64_t>(chunk, B - s);
+        rc = stage_idx(h, user_row + s, item_row + s, hist + s * c.S, nullptr, nb);
+        if (rc != CTR_OK) break;
+        RowSrc r = idx_src(h, h->s_user, h->s_item, h->s_hist, nb);
+        rc = launch(h, "gather_rows", [&] { k_gather_rows<<<grid_for_warps(h, nb), 256, 0, h->stream>>>(r, dims_of(h), dout, xc, nb); });
+        if (rc != CTR_OK) break;
+        if (cudaMemcpyAsync(X + s * xc, dout, (size_t)nb * xc * sizeof(float), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) rc = set_err(h, CTR_ECUDA, "gather D2H: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(dout);
+    return rc;
+}
+
+int ctr_train_dense(ctr_handle* h, const float* X, const float* Y, int64_t n, int32_t xcols, const int32_t ranges[8],
+                    int32_t epochs, int32_t early_stop, float* last_cost, int32_t* epochs_run) {
+    if (!h || !X || !Y || !ranges || n < 1 || xcols < 1 || epochs < 0) return set_err(h, CTR_EINVAL, "bad train arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    RowSrc base{};
+    RET(dense_src(h, ranges, xcols, &base));
+    RET(upload_dense(h, X, Y, n, xcols));
+    const int B = h->cfg.batch;
+    const int64_t batches = n / B + (n % B != 0);           // model.go:96-99
+    float best = INFINITY, cost = 0.0f; int no_improve = 0, ep = 0;
+    for (ep = 0; ep < epochs; ep++) {
+        for (int64_t b = 0; b < batches; b++) {
+            const int64_t start = b * B; int64_t end = start + B;
+            if (start >= n) break;
+            if (end > n) end = n;
+            RowSrc r = base; r.X = h->dXd + start * xcols; r.nvalid = (int)(end - start);   // tail rows → zeros, label 0 (model.go:357-371)
+            StepOpts o; o.training = true; o.update = true; o.d_label = h->dYd + start;
+            RET(step_core(h, r, B, o));
+        }
+        RET(read_cost(h, B, &cost));                        // cost of the epoch's last batch, model.go:198
+        if (cost < best) { best = cost; no_improve = 0; } else no_improve++;
+        if (early_stop != 0 && no_improve >= early_stop) { ep++; break; }   // model.go:206-209
+    }
+    if (last_cost) *last_cost = cost;
+    if (epochs_run) *epochs_run = ep;
+    return CTR_OK;
+}
+
+int ctr_predict_dense(ctr_handle* h, const float* X, int64_t n, int32_t xcols, const int32_t ranges[8], float* out) {
+    if (!h || !X || !ranges || !out || n < 1 || xcols < 1) return set_err(h, CTR_EINVAL, "bad predict arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    RowSrc base{};
+    RET(dense_src(h, ranges, xcols, &base));
+    RET(upload_dense(h, X, nullptr, n, xcols));
+    const int B = h->cfg.pred_batch;
+    const int64_t batches = n / B + (n % B != 0);
+    for (int64_t b = 0; b < batches; b++) {
+        const int64_t start = b * B; int64_t end = start + B;
+        if (start >= n) break;
+        if (end > n) end = n;
+        RowSrc r = base; r.X = h->dXd + start * xcols; r.nvalid = (int)(end - start);
+        StepOpts o;                                          // dropout off: din.go:133-145
+        RET(step_core(h, r, B, o));
+        CU(h, cudaMemcpyAsync(out + start, h->P, (size_t)(end - start) * sizeof(float), cudaMemcpyDeviceToHost, h->stream));   // model.go:344-347
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    return CTR_OK;
+}
+
+int ctr_train_step_idx_dev(ctr_handle* h, const int32_t* d_user, const int32_t* d_item, const int32_t* d_hist, const float* d_label, int32_t B) {
+    if (!h || !d_user || !d_item || !d_hist || !d_label) return set_err(h, CTR_EINVAL, "null argument");
+    if (B != h->cfg.batch) return set_err(h, CTR_EINVAL, "B=%d != configured batch %d", B, h->cfg.batch);
+    if (h->comm.world > 1) return comm_train_step(h, d_user, d_item, d_hist, d_label, B);
+    RET(check_tables(h));
+    RowSrc r = idx_src(h, d_user, d_item, d_hist, B);
+    StepOpts o; o.training = true; o.update = true; o.d_label = d_label;
+    return step_core(h, r, B, o);
+}
+
+int ctr_train_step_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row, const int32_t* hist, const float* label, int32_t B, ctr_step_stats* stats) {
+    if (!h || !user_row || !item_row || !hist || !label) return set_err(h, CTR_EINVAL, "null argument");
+    if (B != h->cfg.batch) return set_err(h, CTR_EINVAL, "B=%d != configured batch %d", B, h->cfg.batch);
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    const int64_t l0 = h->launches;
+    RET(stage_idx(h, user_row, item_row, hist, label, B));
+    RET(ctr_train_step_idx_dev(h, h->s_user, h->s_item, h->s_hist, h->s_label, B));
+    float cost = 0;
+    RET(read_cost(h, B * std::max(1, h->comm.world > 1 ? 1 : 1), &cost));
+    if (stats) { stats->cost = cost; stats->ms_device = 0; stats->launches = (int32_t)(h->launches - l0); stats->reserved = 0; }
+    return CTR_OK;
+}
+
+int ctr_predict_idx_dev(ctr_handle* h, const int32_t* d_user, const int32_t* d_item, const int32_t* d_hist, int32_t B, float* d_out) {
+    if (!h || !d_user || !d_item || !d_hist) return set_err(h, CTR_EINVAL, "null argument");
+    if (h->comm.world > 1) return comm_predict(h, d_user, d_item, d_hist, B, d_out);
+    RET(check_tables(h));
+    RowSrc r = idx_src(h, d_user, d_item, d_hist, B);
+    StepOpts o;
+    RET(step_core(h, r, B, o));
+    if (d_out) CU(h, cudaMemcpyAsync(d_out, h->P, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    return CTR_OK;
+}
+
+int ctr_predict_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row, const int32_t* hist, int64_t n, float* out) {
+    if (!h || !user_row || !item_row || !hist || !out || n < 1) return set_err(h, CTR_EINVAL, "bad predict arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    const int B = h->cfg.pred_batch, S = h->cfg.S;
+    for (int64_t s = 0; s < n; s += B) {
+        const int nb = (int)std::min<int64_t>(B, n - s);
+        RET(stage_idx(h, user_row + s, item_row + s, hist + s * S, nullptr, nb));
+        RET(ctr_predict_idx_dev(h, h->s_user, h->s_item, h->s_hist, nb, nullptr));
+        CU(h, cudaMemcpyAsync(out + s, h->P, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));    // staging buffers are reused by the next chunk
+    }
+    return CTR_OK;
+}
+
+int ctr_last_cost(ctr_handle* h, float* cost) {
+    if (!h || !cost) return CTR_EINVAL;
+    CU(h, cudaSetDevice(h->dev));
+    return read_cost(h, h->cfg.batch, cost);
+}
+
+int ctr_sync(ctr_handle* h) {
+    if (!h) return CTR_EINVAL;
+    CU(h, cudaSetDevice(h->dev));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return CTR_OK;
+}
+
+void* ctr_get_stream(ctr_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int ctr_set_stream(ctr_handle* h, void* s) {
+    if (!h) return CTR_EINVAL;
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    h->stream = (cudaStream_t)s;
+    return CTR_OK;
+}
+
+int64_t ctr_launch_count(const ctr_handle* h) { return h ? h->launches : 0; }
+
+int ctr_profile_enable(ctr_handle* h, int on) { if (!h) return CTR_EINVAL; h->profiling = on != 0; return CTR_OK; }
+int ctr_profile_reset(ctr_handle* h) { if (!h) return CTR_EINVAL; h->prof.clear(); return CTR_OK; }
+int ctr_profile_get(ctr_handle* h, const char* kernel, double* ms, int64_t* n) {
+    if (!h || !kernel) return CTR_EINVAL;
+    auto it = h->prof.find(kernel);
+    if (it == h->prof.end()) { if (ms) *ms = 0; if (n) *n = 0; return CTR_OK; }
+    if (ms) *ms = it->second.ms; if (n) *n = it->second.n;
+    return CTR_OK;
+}
+int ctr_profile_dump(ctr_handle* h, char* buf, int64_t len) {
+    if (!h || !buf || len < 1) return CTR_EINVAL;
+    std::string s;
+    for (auto& kv : h->prof) { char line[256]; snprintf(line, sizeof line, "%s %.6f %ld\n", kv.first.c_str(), kv.second.ms, kv.second.n); s += line; }
+    snprintf(buf, (size_t)len, "%s", s.c_str());
+    return CTR_OK;
+}
+
+int ctr_debug_grads_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row, const int32_t* hist, const float* label,
+                        int32_t B, int32_t training, float* dmlp0, float* dmlp1, float* dmlp2, float* datt0,
+                        float* dUb, float* dIt, float* p, float* logit, float* cost) {
+    if (!h || !user_row || !item_row || !hist || !label) return set_err(h, CTR_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    RET(check_tables(h));
+    const ctr_config& c = h->cfg;
+    RET(stage_idx(h, user_row, item_row, hist, label, B));
+    RET(zero_grads(h));
+    RowSrc r = idx_src(h, h->s_user, h->s_item, h->s_hist, B);
+    StepOpts o; o.training = true; o.update = false; o.want_rows = true; o.d_label = h->s_label;
+    ctr_config saved = h->cfg;
+    if (!training) { h->cfg.dropout0 = 0; h->cfg.dropout1 = 0; }
+    int rc = step_core(h, r, B, o);
+    h->cfg = saved;
+    RET(rc);
+    if (dmlp0) CU(h, cudaMemcpy2DAsync(dmlp0, c.H0 * sizeof(float), h->G[0], h->H0p * sizeof(float), c.H0 * sizeof(float), h->in, cudaMemcpyDeviceToHost, h->stream));
+    if (dmlp1) CU(h, cudaMemcpy2DAsync(dmlp1, c.H1 * sizeof(float), h->G[1], h->H1p * sizeof(float), c.H1 * sizeof(float), c.H0, cudaMemcpyDeviceToHost, h->stream));
+    if (dmlp2) CU(h, cudaMemcpyAsync(dmlp2, h->G[2], c.H1 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (datt0) CU(h, cudaMemcpyAsync(datt0, h->G[3], c.S * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (dUb) CU(h, cudaMemcpyAsync(dUb, h->dUb, (size_t)B * c.S * c.D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (dIt) CU(h, cudaMemcpyAsync(dIt, h->dIt, (size_t)B * c.D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (p) CU(h, cudaMemcpyAsync(p, h->P, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (logit) CU(h, cudaMemcpyAsync(logit, h->Z, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    float cst = 0;
+    RET(read_cost(h, B, &cst));
+    if (cost) *cost = cst;
+    RET(zero_grads(h));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return CTR_OK;
+}
+
+int ctr_roc_auc(ctr_handle* h, const float* pred, const float* y, int64_t n, double* auc) {
+    if (!h || !pred || !y || !auc || n < 1) return set_err(h, CTR_EINVAL, "bad auc arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    { cudaError_t e = auc_run(h->stream, pred, y, (long)n, auc); if (e != cudaSuccess) return set_err(h, CTR_ECUDA, "auc: %s", cudaGetErrorString(e)); return CTR_OK; }
+}
+
+int ctr_comm_unique_id(void* id_out, int32_t* id_bytes) { return comm_unique_id(id_out, id_bytes); }
+int ctr_comm_init(ctr_handle* h, const void* id, int32_t id_bytes) {
+    if (!h || !id) return set_err(h, CTR_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    return comm_init(h, id, id_bytes);
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+// mlp.cuh — the dense half of the hot path: the no-bias sigmoid MLP (din.go:307-315,
+// dnn.go:172-177), BCE (cost.go:9-17), their backward (what G.Grad builds, model.go:56) and
+// gorgonia's AdamSolver.Step (model.go:88,192).  This file is the exact-fp32 engine
+// (CTR_GEMM_FP32): a register-tiled FFMA SGEMM with fused epilogues.  The tcgen05 engine
+// (umma_gemm.cuh) replaces the two forward GEMMs and the dX/dH GEMMs when enabled and is validated
+// against this one.
+#pragma once
+#include "common.cuh"
+
+namespace ctr {
+
+enum { EPI_STORE = 0, EPI_SIGMOID_DROP = 1, EPI_DSIGMOID = 2, EPI_ATOMIC = 3 };
+
+struct GemmArgs {
+    const float* A; long lda;     // TA=false: A[M,K] row-major ; TA=true: stored [K,M]
+    const float* B; long ldb;     // TB=false: B[K,N] row-major ; TB=true: stored [N,K]
+    float* C; long ldc;           // C[M,N]
+    int M, N, K;
+    int Nz;                       // columns [N, Nz) of C are written as zeros (keeps K-padding of the next layer clean)
+    int kchunk;                   // split-K: each blockIdx.z handles kchunk of K (EPI_ATOMIC)
+    // epilogue parameters
+    const float* H; long ldh;     // EPI_DSIGMOID: stored post-dropout activation
+    float drop_p; uint32_t seed, stream;
+};
+
+template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB, int EPI>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+k_sgemm(GemmArgs g) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    static_assert(BK % 4 == 0 && BM % 4 == 0 && BN % 4 == 0 && TM % 4 == 0 && TN % 4 == 0, "tile");
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    int kbeg = 0, kend = g.K;
+    if (EPI == EPI_ATOMIC) { kbeg = blockIdx.z * g.kchunk; kend = min(g.K, kbeg + g.kchunk); }
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = 0.0f;
+
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        // ---- A tile → As[k][m]
+        if (!TA) {
+            constexpr int KQ = BK / 4;
+            for (int e = tid; e < BM * KQ; e += NT) {
+                int m = e / KQ, kq = e % KQ;
+                int gm = m0 + m, gk = k0 + kq * 4;
+                float4 v = zero4();
+                if (gm < g.M) {
+                    const float* p = g.A + (long)gm * g.lda + gk;
+                    if (gk + 3 < kend) v = ldg4(p);
+                    else { if (gk < kend) v.x = __ldg(p); if (gk + 1 < kend) v.y = __ldg(p + 1); if (gk + 2 < kend) v.z = __ldg(p + 2); }
+                }
+                As[kq * 4 + 0][m] = v.x; As[kq * 4 + 1][m] = v.y; As[kq * 4 + 2][m] = v.z; As[kq * 4 + 3][m] = v.w;
+            }
+        } else {
+            constexpr int MQ = BM / 4;
+            for (int e = tid; e < BK * MQ; e += NT) {
+                int k = e / MQ, mq = e % MQ;
+                int gk = k0 + k, gm = m0 + mq * 4;
+                float4 v = zero4();
+                if (gk < kend) {
+                    const float* p = g.A + (long)gk * g.lda + gm;
+                    if (gm + 3 < g.M) v = ldg4(p);
+                    else { if (gm < g.M) v.x = __ldg(p); if (gm + 1 < g.M) v.y = __ldg(p + 1); if (gm + 2 < g.M) v.z = __ldg(p + 2); }
+                }
+                *reinterpret_cast<float4*>(&As[k][mq * 4]) = v;
+            }
+        }
+        // ---- B tile → Bs[k][n]
+        if (!TB) {
+            constexpr int NQ = BN / 4;
+            for (int e = tid; e < BK * NQ; e += NT) {
+                int k = e / NQ, nq = e % NQ;
+                int gk = k0 + k, gn = n0 + nq * 4;
+                float4 v = zero4();
+                if (gk < kend) {
+                    const float* p = g.B + (long)gk * g.ldb + gn;
+                    if (gn + 3 < g.N) v = ldg4(p);
+                    else { if (gn < g.N) v.x = __ldg(p); if (gn + 1 < g.N) v.y = __ldg(p + 1); if (gn + 2 < g.N) v.z = __ldg(p + 2); }
+                }
+                *reinterpret_cast<float4*>(&Bs[k][nq * 4]) = v;
+            }
+        } else {
+            constexpr int KQ = BK / 4;
+            for (int e = tid; e < BN * KQ; e += NT) {
+                int n = e / KQ, kq = e % KQ;
+                int gn = n0 + n, gk = k0 + kq * 4;
+                float4 v = zero4();
+                if (gn < g.N) {
+                    const float* p = g.B + (long)gn * g.ldb + gk;
+                    if (gk + 3 < kend) v = ldg4(p);
+                    else { if (gk < kend) v.x = __ldg(p); if (gk + 1 < kend) v.y = __ldg(p + 1); if (gk + 2 < kend) v.z = __ldg(p + 2); }
+                }
+                Bs[kq * 4 + 0][n] = v.x; Bs[kq * 4 + 1][n] = v.y; Bs[kq * 4 + 2][n] = v.z; Bs[kq * 4 + 3][n] = v.w;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                float4 t = *reinterpret_cast<const float4*>(&As[k][ty * TM + i]);
+                a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+            }
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) {
+                float4 t = *reinterpret_cast<const float4*>(&Bs[k][tx * TN + j]);
+                b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue
+#pragma unroll
+    for (int i = 0; i < TM; i++) {
+        int gm = m0 + ty * TM + i;
+        if (gm >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+            int gn = n0 + tx * TN + j;
+            float* c = g.C + (long)gm * g.ldc + gn;
+            if (gn < g.N) {
+                float v = acc[i][j];
+                if (EPI == EPI_SIGMOID_DROP) {
+                    v = sigmoid32(v) * drop_keep(g.drop_p, g.seed, g.stream, (uint64_t)gm * (uint64_t)g.N + gn);
+                    *c = v;
+                } else if (EPI == EPI_DSIGMOID) {
+                    *c = v * dsigmoid_drop(__ldg(g.H + (long)gm * g.ldh + gn), g.drop_p);
+                } else if (EPI == EPI_ATOMIC) {
+                    atomicAdd(c, v);
+                } else {
+                    *c = v;
+                }
+            } else if (gn < g.Nz && EPI != EPI_ATOMIC) {
+                *c = 0.0f;
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Output layer + loss + first backward step, one warp per sample (din.go:315, cost.go:9-17):
+//   z2 = h1d·w2 ; p = sigmoid(z2) ; cost += y ln p + (1-y) ln(1-p)
+//   dz2 = (p - y)/B ; dZ1 = dz2 w2ᵀ ⊙ dsigmoid(h1d) ; dW2 += h1dᵀ dz2
+// -------------------------------------------------------------------------------------------------
+struct HeadArgs {
+    const float* H1d; long ldh; int H1; int H1p;     // [B, ldh], true width H1, zero-fill to H1p
+    const float* w2;                                  // [H1]
+    const float* y;                                   // [B] labels (null: predict only); rows >= nvalid use label 0
+    int B, nvalid;
+    float drop_p;
+    float* p; float* logit;                           // [B] (logit may be null)
+    float* dZ1; long lddz;                            // [B, lddz] (null: predict only)
+    float* dW2;                                       // [H1] atomics
+    double* cost_sum;                                 // scalar atomic: sum of y ln p + (1-y) ln(1-p)
+};
+
+__global__ void __launch_bounds__(256) k_head(HeadArgs a) {
+    __shared__ float s_dw2[8][128];     // per-warp partials, H1 <= 128
+    __shared__ double s_cost[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const bool train = a.dZ1 != nullptr;
+    float w2r[4], dw2r[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { int k = lane + 32 * j; w2r[j] = k < a.H1 ? __ldg(a.w2 + k) : 0.0f; dw2r[j] = 0.0f; }
+    double cost = 0.0;
+    const float invB = 1.0f / (float)a.B;
+    for (int b = blockIdx.x * (blockDim.x >> 5) + wib; b < a.B; b += nwarps) {
+        float h[4]; float z = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { int k = lane + 32 * j; h[j] = k < a.H1 ? __ldg(a.H1d + (long)b * a.ldh + k) : 0.0f; z = fmaf(h[j], w2r[j], z); }
+        z = warp_sum(z);
+        const float p = sigmoid32(z);
+        if (lane == 0) { a.p[b] = p; if (a.logit) a.logit[b] = z; }
+        if (!train) continue;
+        const float y = (b < a.nvalid) ? __ldg(a.y + b) : 0.0f;
+        if (lane == 0) cost += (double)(logf(p) * y + logf(1.0f - p) * (1.0f - y));
+        const float dz2 = (p - y) * invB;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int k = lane + 32 * j;
+            if (k < a.H1) a.dZ1[(long)b * a.lddz + k] = dz2 * w2r[j] * dsigmoid_drop(h[j], a.drop_p);
+            else if (k < a.H1p) a.dZ1[(long)b * a.lddz + k] = 0.0f;
+            dw2r[j] = fmaf(h[j], dz2, dw2r[j]);
+        }
+    }
+    if (!train) return;
+#pragma unroll
+    for (int j = 0; j < 4; j++) s_dw2[wib][lane + 32 * j] = dw2r[j];
+    if (lane == 0) s_cost[wib] = cost;
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int k = threadIdx.x; k < a.H1; k += blockDim.x) {
+        float s = 0.0f;
+        for (int w = 0; w < nw; w++) s += s_dw2[w][k];
+        atomicAdd(a.dW2 + k, s);
+    }
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < nw; w++) s += s_cost[w];
+        atomicAdd(a.cost_sum, s);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// gorgonia AdamSolver.Step over the learnables (model.go:88,192): g += l2 w ; g *= 1/batch ;
+// m,v update ; w -= lr (m/c1)/(sqrt(v/c2)+eps) ; g = 0.  c1,c2 = 1-β^t computed on the host.
+// One launch covers all four tensors (logical [rows, cols] inside padded storage with stride ld).
+// -------------------------------------------------------------------------------------------------
+struct AdamTensor { float* w; float* g; float* m; float* v; int rows, cols; long ld; };
+struct AdamArgs {
+    AdamTensor t[4]; int nt;
+    float lr, l2, inv_batch, b1, b2, eps, c1, c2;
+};
+
+__global__ void __launch_bounds__(256) k_adam(AdamArgs a) {
+    for (int ti = 0; ti < a.nt; ti++) {
+        const AdamTensor& t = a.t[ti];
+        long n = (long)t.rows * t.cols;
+        for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+            long off = (i / t.cols) * t.ld + (i % t.cols);
+            float w = t.w[off];
+            float g = t.g[off];
+            if (a.l2 != 0.0f) g = g + a.l2 * w;
+            g = g * a.inv_batch;
+            float m = a.b1 * t.m[off] + (1.0f - a.b1) * g;
+            float v = a.b2 * t.v[off] + (1.0f - a.b2) * (g * g);
+            t.m[off] = m; t.v[off] = v;
+            t.w[off] = w - a.lr * (m / a.c1) / (sqrtf(v / a.c2) + a.eps);
+            t.g[off] = 0.0f;
+        }
+    }
+}
+
+}  // namespace ctr

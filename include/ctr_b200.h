@@ -1,0 +1,174 @@
+/*
+ * ctr_b200.h — C ABI of libctr_b200.so: the B200 (sm_100a) engine behind go-ctr's CTR hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one Go-side interface of the reference
+ * (auxten/go-ctr @ c181363c; file:line relative to the repository root) and is exactly what a cgo
+ * shim binds (see INTEGRATION.md and go/ctrb200/ctrb200.go).  Plain pointers and sizes only — no
+ * torch / C++ types.  The caller owns every host buffer; the library copies and never retains a
+ * caller pointer after return (cgo pointer-passing rule).  Every function returns 0 on success or a
+ * CTR_E* code; the message is available from ctr_last_error().  Nothing aborts or exits.
+ * There is no CPU fallback: without a CUDA device ctr_create fails with CTR_ENODEV.
+ *
+ * Layouts: all matrices row-major float32; indices int32 dense row ids (the id→row map stays on
+ * the Go side where the reference keeps it, rcmd.go:472-505); -1 = missing row → zeros
+ * (rcmd.go:502-505,519).
+ */
+#ifndef CTR_B200_H
+#define CTR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTR_B200_ABI_VERSION 1
+
+enum { CTR_OK = 0, CTR_EINVAL = 1, CTR_ENODEV = 2, CTR_ECUDA = 3, CTR_ENOMEM = 4, CTR_ESTATE = 5, CTR_ECOMM = 6 };
+
+/* which graph: model/youtube/dnn.go:162-184 | model/din/din.go:219-323 (cosine, live) |
+ * din.go:230 + model/activation.go:23-50 (euclidean ActivationUnit variant) */
+enum { CTR_MODEL_YOUTUBE = 0, CTR_MODEL_DIN_COS = 1, CTR_MODEL_DIN_EUC = 2 };
+
+enum { CTR_TABLE_USER_FEAT = 0, CTR_TABLE_ITEM_FEAT = 1, CTR_TABLE_ITEM_EMB = 2 };
+
+/* embedding-table optimiser.  FROZEN is the reference's behaviour (embeddings are inputs, not
+ * learnables: din.go:161-169).  SGD fuses gradient scatter-add + update into the backward kernel
+ * with red.global.add.v4.f32 (order-nondeterministic, Hogwild within a batch like the reference's
+ * own item2vec trainer).  SGD_DETERMINISTIC sorts (row, sample, slot) keys and reduces each row's
+ * segment in a fixed order — the parity-test mode. */
+enum { CTR_TABLE_FROZEN = 0, CTR_TABLE_SGD = 1, CTR_TABLE_SGD_DETERMINISTIC = 2 };
+
+/* dense-layer GEMM engine: exact fp32 FFMA, or tcgen05 3xTF32 (error-compensated, fp32 accumulate
+ * in TMEM).  AUTO = tcgen05 when the shape qualifies. */
+enum { CTR_GEMM_AUTO = 0, CTR_GEMM_FP32 = 1, CTR_GEMM_TCGEN05_3XTF32 = 2 };
+
+typedef struct ctr_handle ctr_handle;
+
+/* Hyper-parameters the reference hard-codes, as runtime fields (SURVEY.md §5 "Config / flags").
+ * ctr_config_default() fills the reference's values. */
+typedef struct {
+    int32_t model;            /* CTR_MODEL_* */
+    int32_t uP;               /* uProfileDim            model.go:27 */
+    int32_t S;                /* uBehaviorSize          rcmd.go:24  (10) */
+    int32_t D;                /* uBehaviorDim == iFeatureDim (din.go:176-178)  rcmd.go:22 (16) */
+    int32_t cF;               /* cFeatureDim */
+    int32_t H0, H1;           /* din.go:17-18 (200, 80) */
+    int32_t batch;            /* model.Train batchSize */
+    int32_t pred_batch;       /* model.InitForwardOnlyVm batchSize (model.go:215) */
+    float   lr, l2, beta1, beta2, eps;   /* model.go:88: 0.01, 1e-4; gorgonia Adam defaults .9 .999 1e-8 */
+    float   dropout0, dropout1;          /* din.go:204-205 (.005) / dnn.go:136-137 (.003) */
+    uint32_t seed;            /* dropout-mask / weight-init counter RNG seed */
+    int32_t table_opt;        /* CTR_TABLE_* */
+    float   table_lr;         /* SGD step for embedding rows (engine extension) */
+    int32_t gemm;             /* CTR_GEMM_* */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t rank, world;      /* row-sharding of ITEM_EMB across `world` GPUs: owner(row) = row % world */
+    int32_t reserved[8];
+} ctr_config;
+
+typedef struct {
+    float   cost;             /* BCE mean of this batch (model/cost.go:9-17) */
+    float   ms_device;        /* device time of the step (CUDA events on the engine stream); 0 if not measured */
+    int32_t launches;         /* kernels launched by the step */
+    int32_t reserved;
+} ctr_step_stats;
+
+int  ctr_abi_version(void);
+void ctr_config_default(ctr_config* cfg, int model);
+
+/* din.NewDinNet / youtube.NewYoutubeDnn (din.go:171, dnn.go:119) — allocates device state. */
+int  ctr_create(const ctr_config* cfg, ctr_handle** out);
+void ctr_destroy(ctr_handle* h);
+/* last error message of this handle (or of the last failed ctr_create when h == NULL) */
+const char* ctr_last_error(const ctr_handle* h);
+
+/* G.WithInit(G.Gaussian(0,1)) for mlp0/1/2 and ValuesOf(1) for att0 (din.go:181-191) with the
+ * engine's counter RNG (streams 0,1,2) — the reference's draws are time-seeded, never reproducible. */
+int ctr_init_weights(ctr_handle* h, uint32_t seed);
+/* DinNet.Marshal / NewDinNetFromJson field layout (din.go:41-52, dnn.go:38-47): mlp0 [in,H0],
+ * mlp1 [H0,H1], mlp2 [H1,1], att0 [1,S] row-major; att0 may be NULL for YouTube.  set also resets
+ * the Adam moments and step counter (a fresh solver is built per model.Train call, model.go:88). */
+int ctr_set_weights(ctr_handle* h, const float* mlp0, const float* mlp1, const float* mlp2, const float* att0);
+int ctr_get_weights(ctr_handle* h, float* mlp0, float* mlp1, float* mlp2, float* att0);
+
+/* Feature / embedding tables resident in HBM: replaces UserFeatureCache / ItemFeatureCache /
+ * itemEmbeddingMap (rcmd.go:30-36, 473-505).  rows is [nrows, width] row-major.  With world > 1,
+ * ITEM_EMB upload takes the FULL table on every rank and keeps rows r % world == rank. */
+int ctr_table_upload(ctr_handle* h, int which, const float* rows, int64_t nrows, int32_t width);
+int ctr_table_download(ctr_handle* h, int which, float* rows, int64_t nrows, int32_t width);
+/* Synthetic table generated on the device with the counter RNG (benchmarks with 10M-100M rows,
+ * BASELINE.json configs[2..3]): element (r, c) of the FULL table = scale * draw(seed, stream=which,
+ * ctr=r*width+c), dist 0 = U[0,1), 1 = N(0,1) (Box-Muller) — identical on every rank / shard. */
+int ctr_table_fill(ctr_handle* h, int which, int64_t nrows, int32_t width, uint32_t seed, int32_t dist, float scale);
+
+/* recommend.GetSampleVector for a batch (rcmd.go:462-536): X[b] = [user_feat | emb[hist[b,0..S)] |
+ * emb[item] | item_feat], bit-exact copies.  X is [B, uP + S*D + D + cF]. */
+int ctr_gather_rows(ctr_handle* h, const int32_t* user_row, const int32_t* item_row,
+                    const int32_t* hist_rows, int64_t B, float* X);
+
+/* model.Train (model.go:27-213) on the dense X / Y that recommend.GetSample built
+ * (rcmd.go:339-460).  ranges = SampleInfo {UserProfile, UserBehavior, ItemFeature, CtxFeature} as
+ * 4 [start,end) pairs (rcmd.go:132-137).  Zero-pads the ragged last batch and trains on it with
+ * label 0 (model.go:132-184,357-371); *last_cost = cost of the last batch (model.go:198);
+ * early_stop = no-improvement epochs (0 = off, model.go:199-209). */
+int ctr_train_dense(ctr_handle* h, const float* X, const float* Y, int64_t n, int32_t xcols,
+                    const int32_t ranges[8], int32_t epochs, int32_t early_stop,
+                    float* last_cost, int32_t* epochs_run);
+/* model.Predict (model.go:242-353): batches of pred_batch, zero-padded tail, dropout off
+ * (din.go:133-145).  out is [n]. */
+int ctr_predict_dense(ctr_handle* h, const float* X, int64_t n, int32_t xcols,
+                      const int32_t ranges[8], float* out);
+
+/* The B200-native fast path: one model.Train inner-loop iteration (model.go:107-196) fed by row
+ * indices instead of a materialised X; gathers from the HBM tables inside the kernels.
+ * hist_rows is [B,S], most-recent-first, -1 padded (prepare.go:49-51, rcmd.go:517-522).
+ * B must equal cfg.batch.  Host buffers: copied H2D inside the call. */
+int ctr_train_step_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row,
+                       const int32_t* hist_rows, const float* label, int32_t B, ctr_step_stats* stats);
+/* recommend.BatchPredict → model.Predict (rcmd.go:277-337) fed by indices. out is [n]. */
+int ctr_predict_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row,
+                    const int32_t* hist_rows, int64_t n, float* out);
+
+/* Same step with DEVICE-resident index / label buffers; asynchronous on the engine stream, no host
+ * sync (stats->cost is not filled; read it with ctr_last_cost after ctr_sync).  Used when the caller
+ * keeps the sample stream in HBM (bench.py's `value` leg; the device-side ubcache row f2). */
+int ctr_train_step_idx_dev(ctr_handle* h, const int32_t* d_user_row, const int32_t* d_item_row,
+                           const int32_t* d_hist_rows, const float* d_label, int32_t B);
+int ctr_predict_idx_dev(ctr_handle* h, const int32_t* d_user_row, const int32_t* d_item_row,
+                        const int32_t* d_hist_rows, int32_t B, float* d_out);
+int ctr_last_cost(ctr_handle* h, float* cost);
+int ctr_sync(ctr_handle* h);
+/* the cudaStream_t the engine launches on (so a harness can record its own events on it), and a
+ * way to adopt the caller's stream instead */
+void* ctr_get_stream(ctr_handle* h);
+int   ctr_set_stream(ctr_handle* h, void* cuda_stream);
+/* number of kernels the engine has launched since creation */
+int64_t ctr_launch_count(const ctr_handle* h);
+/* per-kernel device-time profile: enable → every launch is bracketed by events (slow; for bench's
+ * roofline leg).  ctr_profile_get returns accumulated ms and launch count for a kernel name. */
+int ctr_profile_enable(ctr_handle* h, int on);
+int ctr_profile_get(ctr_handle* h, const char* kernel, double* ms_total, int64_t* launches);
+int ctr_profile_reset(ctr_handle* h);
+int ctr_profile_dump(ctr_handle* h, char* buf, int64_t buflen);   /* "name ms launches\n" lines */
+
+/* Test hook: forward+backward of one index batch WITHOUT any update; returns what G.Grad would
+ * (model.go:56) plus the engine's row gradients.  Any output pointer may be NULL.
+ * dUb [B,S,D], dIt [B,D], p [B], logit [B]. */
+int ctr_debug_grads_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row,
+                        const int32_t* hist_rows, const float* label, int32_t B, int32_t training,
+                        float* dmlp0, float* dmlp1, float* dmlp2, float* datt0,
+                        float* dUb, float* dIt, float* p, float* logit, float* cost);
+
+/* utils.RocAuc32 (util.go:131-148 → nn/metrics/ranking.go:144): labels binarised at 0.5, tied
+ * scores grouped, trapezoid. Sorted on the device. */
+int ctr_roc_auc(ctr_handle* h, const float* pred, const float* y, int64_t n, double* auc);
+
+/* Multi-GPU (world > 1): one handle per rank/process.  The id is ncclUniqueId bytes produced on
+ * rank 0 by ctr_comm_unique_id and distributed by the host (torch.distributed / Go). */
+int ctr_comm_unique_id(void* id_out, int32_t* id_bytes /* in: capacity, out: used */);
+int ctr_comm_init(ctr_handle* h, const void* id, int32_t id_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
