@@ -1,0 +1,221 @@
+// Package ctrb200 is the cgo shim that maps go-ctr's unchanged plugin surface —
+// recommend.Fitter / recommend.PredictAbstract (recommend/rcmd.go:87-97) and the
+// model.Train / model.Predict call shape (model/model.go:27, 242) — onto libctr_b200.so.
+//
+// NOT BUILT IN THIS REPOSITORY'S CI: the build image has no Go toolchain (SURVEY.md §8b "Compile
+// reality").  It is the binding a go-ctr maintainer adds; every C entry point it calls is covered
+// by the Python ctypes tests in tests/, which drive the identical C ABI.
+//
+// Build (on a machine with Go, CUDA 12.9 and a B200):
+//
+//	CGO_CFLAGS="-I${CTR_B200}/include" CGO_LDFLAGS="-L${CTR_B200}/go-ctr_b200 -lctr_b200" go build ./...
+package ctrb200
+
+/*
+#include <stdlib.h>
+#include "ctr_b200.h"
+*/
+import "C"
+
+import (
+	"encoding/json"
+	"fmt"
+	"runtime"
+	"unsafe"
+
+	rcmd "github.com/auxten/go-ctr/recommend"
+	"gorgonia.org/tensor"
+)
+
+// Kind selects the graph the engine evaluates.
+type Kind int
+
+const (
+	YoutubeDnn Kind = C.CTR_MODEL_YOUTUBE // model/youtube/dnn.go
+	DinCosine  Kind = C.CTR_MODEL_DIN_COS // model/din/din.go (live variant)
+	DinEuclid  Kind = C.CTR_MODEL_DIN_EUC // din.go:230
+)
+
+// Engine owns one device handle (weights + HBM tables).
+type Engine struct {
+	h   *C.ctr_handle
+	cfg C.ctr_config
+}
+
+func (e *Engine) err(rc C.int) error {
+	if rc == C.CTR_OK {
+		return nil
+	}
+	return fmt.Errorf("ctr_b200 error %d: %s", int(rc), C.GoString(C.ctr_last_error(e.h)))
+}
+
+// NewEngine mirrors din.NewDinNet / youtube.NewYoutubeDnn (din.go:171, dnn.go:119).
+func NewEngine(kind Kind, uProfileDim, uBehaviorSize, uBehaviorDim, iFeatureDim, cFeatureDim, batchSize, predBatchSize int) (*Engine, error) {
+	if uBehaviorDim != iFeatureDim { // din.go:176-178
+		return nil, fmt.Errorf("uBehaviorDim %d != iFeatureDim %d", uBehaviorDim, iFeatureDim)
+	}
+	e := &Engine{}
+	C.ctr_config_default(&e.cfg, C.int(kind))
+	e.cfg.uP, e.cfg.S, e.cfg.D, e.cfg.cF = C.int32_t(uProfileDim), C.int32_t(uBehaviorSize), C.int32_t(uBehaviorDim), C.int32_t(cFeatureDim)
+	e.cfg.batch, e.cfg.pred_batch = C.int32_t(batchSize), C.int32_t(predBatchSize)
+	if rc := C.ctr_create(&e.cfg, &e.h); rc != C.CTR_OK {
+		return nil, fmt.Errorf("ctr_create: %d: %s", int(rc), C.GoString(C.ctr_last_error(nil)))
+	}
+	runtime.SetFinalizer(e, func(e *Engine) { e.Close() })
+	return e, nil
+}
+
+func (e *Engine) Close() {
+	if e.h != nil {
+		C.ctr_destroy(e.h)
+		e.h = nil
+	}
+}
+
+func f32(p []float32) *C.float { return (*C.float)(unsafe.Pointer(&p[0])) }
+func i32(p []int32) *C.int32_t { return (*C.int32_t)(unsafe.Pointer(&p[0])) }
+
+func ranges(si *rcmd.SampleInfo) [8]C.int32_t {
+	return [8]C.int32_t{
+		C.int32_t(si.UserProfileRange[0]), C.int32_t(si.UserProfileRange[1]),
+		C.int32_t(si.UserBehaviorRange[0]), C.int32_t(si.UserBehaviorRange[1]),
+		C.int32_t(si.ItemFeatureRange[0]), C.int32_t(si.ItemFeatureRange[1]),
+		C.int32_t(si.CtxFeatureRange[0]), C.int32_t(si.CtxFeatureRange[1]),
+	}
+}
+
+// Train has model.Train's meaning (model.go:27-213) for the engine's model.
+func (e *Engine) Train(numExamples, epochs, earlyStop int, si *rcmd.SampleInfo, inputs, targets []float32, xcols int) (lastCost float32, err error) {
+	r := ranges(si)
+	var cost C.float
+	var ran C.int32_t
+	rc := C.ctr_train_dense(e.h, f32(inputs), f32(targets), C.int64_t(numExamples), C.int32_t(xcols), &r[0],
+		C.int32_t(epochs), C.int32_t(earlyStop), &cost, &ran)
+	return float32(cost), e.err(rc)
+}
+
+// Predict has model.Predict's meaning (model.go:242-353).
+func (e *Engine) Predict(numExamples int, si *rcmd.SampleInfo, inputs []float32, xcols int) ([]float32, error) {
+	r := ranges(si)
+	y := make([]float32, numExamples)
+	rc := C.ctr_predict_dense(e.h, f32(inputs), C.int64_t(numExamples), C.int32_t(xcols), &r[0], f32(y))
+	return y, e.err(rc)
+}
+
+// UploadTable puts a feature / embedding table in HBM (replaces UserFeatureCache /
+// ItemFeatureCache / itemEmbeddingMap, rcmd.go:30-36).
+func (e *Engine) UploadTable(which int, rows []float32, nrows, width int) error {
+	return e.err(C.ctr_table_upload(e.h, C.int(which), f32(rows), C.int64_t(nrows), C.int32_t(width)))
+}
+
+// TrainStepIdx is one inner-loop iteration of model.Train (model.go:107-196) fed by row ids.
+func (e *Engine) TrainStepIdx(userRow, itemRow, histRows []int32, label []float32) (cost float32, err error) {
+	var st C.ctr_step_stats
+	rc := C.ctr_train_step_idx(e.h, i32(userRow), i32(itemRow), i32(histRows), f32(label), C.int32_t(len(userRow)), &st)
+	return float32(st.cost), e.err(rc)
+}
+
+// PredictIdx is recommend.BatchPredict → model.Predict (rcmd.go:277-337) fed by row ids.
+func (e *Engine) PredictIdx(userRow, itemRow, histRows []int32) ([]float32, error) {
+	y := make([]float32, len(userRow))
+	rc := C.ctr_predict_idx(e.h, i32(userRow), i32(itemRow), i32(histRows), C.int64_t(len(userRow)), f32(y))
+	return y, e.err(rc)
+}
+
+// dinModel is the reference's JSON schema (din.go:41-52; dnn.go:38-47 without att0).
+type dinModel struct {
+	UProfileDim   int       `json:"uProfileDim"`
+	UBehaviorSize int       `json:"uBehaviorSize"`
+	UBehaviorDim  int       `json:"uBehaviorDim"`
+	IFeatureDim   int       `json:"iFeatureDim"`
+	CFeatureDim   int       `json:"cFeatureDim"`
+	Mlp0          []float32 `json:"mlp0"`
+	Mlp1          []float32 `json:"mlp1"`
+	Mlp2          []float32 `json:"mlp2"`
+	Att0          []float32 `json:"att0,omitempty"`
+}
+
+// Marshal emits exactly what DinNet.Marshal / YoutubeDnn.Marshal emit (din.go:62, dnn.go:49), so
+// din.NewDinNetFromJson can load an engine-trained model and vice versa.
+func (e *Engine) Marshal() ([]byte, error) {
+	in := int(e.cfg.uP + 2*e.cfg.D + e.cfg.cF)
+	m := dinModel{UProfileDim: int(e.cfg.uP), UBehaviorSize: int(e.cfg.S), UBehaviorDim: int(e.cfg.D),
+		IFeatureDim: int(e.cfg.D), CFeatureDim: int(e.cfg.cF),
+		Mlp0: make([]float32, in*int(e.cfg.H0)), Mlp1: make([]float32, int(e.cfg.H0*e.cfg.H1)),
+		Mlp2: make([]float32, int(e.cfg.H1)), Att0: make([]float32, int(e.cfg.S))}
+	if err := e.err(C.ctr_get_weights(e.h, f32(m.Mlp0), f32(m.Mlp1), f32(m.Mlp2), f32(m.Att0))); err != nil {
+		return nil, err
+	}
+	if Kind(e.cfg.model) == YoutubeDnn {
+		m.Att0 = nil
+	}
+	return json.Marshal(m)
+}
+
+// LoadJSON is NewDinNetFromJson / NewYoutubeDnnFromJson for the engine (din.go:82, dnn.go:63).
+func (e *Engine) LoadJSON(data []byte) error {
+	var m dinModel
+	if err := json.Unmarshal(data, &m); err != nil {
+		return err
+	}
+	var att *C.float
+	if len(m.Att0) > 0 {
+		att = f32(m.Att0)
+	}
+	return e.err(C.ctr_set_weights(e.h, f32(m.Mlp0), f32(m.Mlp1), f32(m.Mlp2), att))
+}
+
+// Impl is the drop-in for example/movielens dinImpl / YoutubeDnnImpl (dinimpl.go:13-92,
+// youtube.go:13-91): it satisfies recommend.Fitter and recommend.PredictAbstract, so
+// recommend.Train(ctx, recSys, &ctrb200.Impl{...}) (rcmd.go:196,229) works unchanged.
+type Impl struct {
+	Kind                               Kind
+	PredBatchSize, BatchSize, Epochs   int
+	EarlyStop                          int
+	UBehaviorSize, UBehaviorDim        int // rcmd.UserBehaviorLen, rcmd.ItemEmbDim
+	sampleInfo                         *rcmd.SampleInfo
+	xcols                              int
+	pred                               *Engine
+}
+
+// Fit implements recommend.Fitter (rcmd.go:95-97); body follows dinImpl.Fit (dinimpl.go:44-92).
+func (d *Impl) Fit(trainSample *rcmd.TrainSample) (rcmd.PredictAbstract, error) {
+	uP := trainSample.Info.UserProfileRange[1] - trainSample.Info.UserProfileRange[0]
+	cF := trainSample.Info.CtxFeatureRange[1] - trainSample.Info.CtxFeatureRange[0]
+	d.sampleInfo, d.xcols = &trainSample.Info, trainSample.XCols
+	if trainSample.Rows != len(trainSample.Y) {
+		return nil, fmt.Errorf("number of examples %d and labels %d do not match", trainSample.Rows, len(trainSample.Y))
+	}
+	learner, err := NewEngine(d.Kind, uP, d.UBehaviorSize, d.UBehaviorDim, d.UBehaviorDim, cF, d.BatchSize, d.BatchSize)
+	if err != nil {
+		return nil, err
+	}
+	defer learner.Close()
+	if _, err = learner.Train(trainSample.Rows, d.Epochs, d.EarlyStop, d.sampleInfo, trainSample.X, trainSample.Y, trainSample.XCols); err != nil {
+		return nil, err
+	}
+	js, err := learner.Marshal() // learner → JSON → predictor, dinimpl.go:73-89
+	if err != nil {
+		return nil, err
+	}
+	pred, err := NewEngine(d.Kind, uP, d.UBehaviorSize, d.UBehaviorDim, d.UBehaviorDim, cF, d.PredBatchSize, d.PredBatchSize)
+	if err != nil {
+		return nil, err
+	}
+	if err = pred.LoadJSON(js); err != nil {
+		return nil, err
+	}
+	d.pred = pred
+	return d, nil
+}
+
+// Predict implements recommend.PredictAbstract (rcmd.go:87-89); body follows dinImpl.Predict
+// (dinimpl.go:32-42), including returning nil on failure.
+func (d *Impl) Predict(X tensor.Tensor) tensor.Tensor {
+	numPred := X.Shape()[0]
+	y, err := d.pred.Predict(numPred, d.sampleInfo, X.Data().([]float32), d.xcols)
+	if err != nil {
+		return nil
+	}
+	return tensor.NewDense(tensor.Float32, tensor.Shape{numPred, 1}, tensor.WithBacking(y))
+}
