@@ -8,8 +8,9 @@
 // pass backward (+ the L2-side red.add that writes each touched row back once).
 //
 // Mapping: one warp per sample.  Vector kernels: a row of D=4*LPR floats is covered by LPR lanes
-// with one 128-bit load each, so a warp issues 32/LPR rows per load instruction; the dot products
-// reduce inside the LPR-lane group with __shfl_xor.  Generic kernels: any D<=256, scalar loads.
+// with one 128-bit load each, so a warp issues 32/LPR rows per load instruction, UNR of them back
+// to back (UNR*32/LPR rows in flight per warp) before any arithmetic; the dot products reduce
+// inside the LPR-lane group with __shfl_xor.  Generic kernels: any D<=256, scalar loads.
 #pragma once
 #include "common.cuh"
 
@@ -36,20 +37,49 @@ struct HistIdx {
     }
 };
 
-__device__ __forceinline__ const float* ub_ptr(const RowSrc& r, const Dims& d, const HistIdx& hi,
-                                               bool use_hi, int b, int s) {
+// one history slot: pointer to the row (nullptr = zeros) and its table row id (-1 in dense mode)
+struct RowRef { const float* p; int idx; };
+
+__device__ __forceinline__ RowRef ub_ref(const RowSrc& r, const Dims& d, const HistIdx& hi,
+                                         bool use_hi, int b, int s) {
     // every lane of the warp reaches the shuffle inside hi.get()
     int sidx = use_hi ? hi.get(s < d.S ? s : 0) : -1;
-    if (s >= d.S || b >= r.nvalid) return nullptr;
-    if (r.dense) return r.X + (long)b * r.ldx + r.ub0 + (long)s * d.D;
+    RowRef o; o.p = nullptr; o.idx = -1;
+    if (s >= d.S || b >= r.nvalid) return o;
+    if (r.dense) { o.p = r.X + (long)b * r.ldx + r.ub0 + (long)s * d.D; return o; }
     int idx = use_hi ? sidx : __ldg(r.hist + (long)b * d.S + s);
-    return idx >= 0 ? r.emb + (long)idx * r.lde : nullptr;
+    if (idx >= 0) { o.p = r.emb + (long)idx * r.lde; o.idx = idx; }
+    return o;
+}
+__device__ __forceinline__ const float* ub_ptr(const RowSrc& r, const Dims& d, const HistIdx& hi,
+                                               bool use_hi, int b, int s) {
+    return ub_ref(r, d, hi, use_hi, b, s).p;
+}
+
+// fast reciprocal / sigmoid for the attention gate (MUFU.RCP / MUFU.EX2; relative error ~1e-6,
+// two orders below the 1e-4 parity bar)
+__device__ __forceinline__ float frcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    if (x < -88.0f) return 0.0f;
+    if (x > 15.0f) return 1.0f;
+    return frcp(1.0f + __expf(-x));
+}
+// sqrt(x) for x >= 0 through MUFU.RSQ
+__device__ __forceinline__ float fsqrt_pos(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
+
+// attention gate of one row given the group-reduced dot products (generic kernels)
+__device__ __forceinline__ float gate_cos(float dot, float nx2, float ny, float att_s) {
+    return sigmoid32((dot / (sqrtf(nx2) * ny + 1e-8f) + 1.0f) * 0.5f * att_s);
 }
 
 // -------------------------------------------------------------------------------------------------
 // forward, vector path.  Writes the MLP input row X0[b] = [uProfile | pooled | item | ctx | 0-pad].
+// A row of D = 4*LPR*VPL floats is covered by LPR lanes holding VPL float4 each (column block q of
+// lane l = (q*LPR + l)*4, so every load instruction of the group is one contiguous LPR*16-byte
+// segment); a warp therefore carries 32/LPR rows per instruction group and the scalar gate math is
+// amortised over them.
 // -------------------------------------------------------------------------------------------------
-template <int LPR>
+template <int LPR, int VPL, int UNR>
 __global__ void __launch_bounds__(256)
 k_attn_fwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
                float* __restrict__ X0, long ldx0, int Kp, int B) {
@@ -65,54 +95,72 @@ k_attn_fwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
     for (int b = blockIdx.x * (blockDim.x >> 5) + wib; b < B; b += nwarps) {
         HistIdx hi; hi.load(r, d, b, lane);
         const float* ip = src_it(r, d, b);
-        const float4 v = ip ? ldg4(ip + lir * 4) : zero4();
-        const float ny = sqrtf(group_sum<LPR>(dot4(v, v)));
-        float4 acc = zero4();
-        for (int s0 = 0; s0 < d.S; s0 += 2 * RPW) {
-            // two independent row loads in flight per lane
-            const int sA = s0 + sub, sB = s0 + RPW + sub;
-            const float* pA = ub_ptr(r, d, hi, use_hi, b, sA);
-            const float* pB = ub_ptr(r, d, hi, use_hi, b, sB);
-            const float4 uA = pA ? ldg4_stream(pA + lir * 4) : zero4();
-            const float4 uB = pB ? ldg4_stream(pB + lir * 4) : zero4();
-            float aA = 1.0f, aB = 1.0f;
-            if (model == MODEL_DIN_COS) {
-                float dA = group_sum<LPR>(dot4(uA, v)), nA = group_sum<LPR>(dot4(uA, uA));
-                float dB = group_sum<LPR>(dot4(uB, v)), nB = group_sum<LPR>(dot4(uB, uB));
-                float wA = (dA / (sqrtf(nA) * ny + 1e-8f) + 1.0f) * 0.5f;
-                float wB = (dB / (sqrtf(nB) * ny + 1e-8f) + 1.0f) * 0.5f;
-                aA = sigmoid32(wA * (sA < d.S ? __ldg(att + sA) : 0.0f));
-                aB = sigmoid32(wB * (sB < d.S ? __ldg(att + sB) : 0.0f));
-            } else if (model == MODEL_DIN_EUC) {
-                float4 eA = make_float4(uA.x - v.x, uA.y - v.y, uA.z - v.z, uA.w - v.w);
-                float4 eB = make_float4(uB.x - v.x, uB.y - v.y, uB.z - v.z, uB.w - v.w);
-                float wA = 1.0f - sqrtf(group_sum<LPR>(dot4(eA, eA)));
-                float wB = 1.0f - sqrtf(group_sum<LPR>(dot4(eB, eB)));
-                aA = sigmoid32(wA * (sA < d.S ? __ldg(att + sA) : 0.0f));
-                aB = sigmoid32(wB * (sB < d.S ? __ldg(att + sB) : 0.0f));
-            }
-            acc = fma4(aA, uA, acc);     // slots beyond S and missing rows carry u == 0
-            acc = fma4(aB, uB, acc);
-        }
+        float4 v[VPL];
+        float ny2 = 0.0f;
 #pragma unroll
-        for (int o = LPR; o < 32; o <<= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-        }
-        // assemble the concat row in shared memory, then one coalesced 128-bit store pass
+        for (int q = 0; q < VPL; q++) { v[q] = ip ? ldg4(ip + (q * LPR + lir) * 4) : zero4(); ny2 += dot4(v[q], v[q]); }
+        // dense per-sample features: issued before the row loop so they overlap it
         const float* pu = src_up(r, b);
-        for (int j = lane; j < d.uP; j += 32) row[j] = pu ? __ldg(pu + j) : 0.0f;
-        if (sub == 0) {
-            float* q = row + d.uP + lir * 4;
-            q[0] = acc.x * invS; q[1] = acc.y * invS; q[2] = acc.z * invS; q[3] = acc.w * invS;
-            float* q2 = row + d.uP + d.D + lir * 4;
-            q2[0] = v.x; q2[1] = v.y; q2[2] = v.z; q2[3] = v.w;
-        }
         const float* pc = src_cx(r, b);
+        for (int j = lane; j < d.uP; j += 32) row[j] = pu ? __ldg(pu + j) : 0.0f;
         for (int j = lane; j < d.cF; j += 32) row[d.uP + 2 * d.D + j] = pc ? __ldg(pc + j) : 0.0f;
         for (int j = d.in + lane; j < Kp; j += 32) row[j] = 0.0f;
+        const float ny = fsqrt_pos(group_sum<LPR>(ny2));
+        float4 acc[VPL];
+#pragma unroll
+        for (int q = 0; q < VPL; q++) acc[q] = zero4();
+        for (int s0 = 0; s0 < d.S; s0 += UNR * RPW) {
+            float4 u[UNR][VPL];
+#pragma unroll
+            for (int j = 0; j < UNR; j++) {               // UNR*VPL independent 128-bit loads in flight
+                const float* p = ub_ptr(r, d, hi, use_hi, b, s0 + j * RPW + sub);
+#pragma unroll
+                for (int q = 0; q < VPL; q++) u[j][q] = p ? ldg4_stream(p + (q * LPR + lir) * 4) : zero4();
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; j++) {
+                const int s = s0 + j * RPW + sub;
+                float a = 1.0f;
+                if (model == MODEL_DIN_COS) {
+                    float dot = 0.0f, nx2 = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < VPL; q++) { dot += dot4(u[j][q], v[q]); nx2 += dot4(u[j][q], u[j][q]); }
+                    dot = group_sum<LPR>(dot); nx2 = group_sum<LPR>(nx2);
+                    const float cs = dot * frcp(fsqrt_pos(nx2) * ny + 1e-8f);
+                    a = sigmoid_fast((cs + 1.0f) * 0.5f * (s < d.S ? __ldg(att + s) : 0.0f));
+                } else if (model == MODEL_DIN_EUC) {
+                    float d2 = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < VPL; q++) {
+                        const float4 e = make_float4(u[j][q].x - v[q].x, u[j][q].y - v[q].y, u[j][q].z - v[q].z, u[j][q].w - v[q].w);
+                        d2 += dot4(e, e);
+                    }
+                    a = sigmoid_fast((1.0f - fsqrt_pos(group_sum<LPR>(d2))) * (s < d.S ? __ldg(att + s) : 0.0f));
+                }
+#pragma unroll
+                for (int q = 0; q < VPL; q++) acc[q] = fma4(a, u[j][q], acc[q]);   // slots beyond S / missing rows carry u == 0
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < VPL; q++) {
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+                acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+                acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+                acc[q].z += __shfl_xor_sync(0xffffffffu, acc[q].z, o);
+                acc[q].w += __shfl_xor_sync(0xffffffffu, acc[q].w, o);
+            }
+        }
+        // assemble the concat row in shared memory, then one coalesced 128-bit store pass
+        if (sub == 0) {
+#pragma unroll
+            for (int q = 0; q < VPL; q++) {
+                float* p1 = row + d.uP + (q * LPR + lir) * 4;
+                p1[0] = acc[q].x * invS; p1[1] = acc[q].y * invS; p1[2] = acc[q].z * invS; p1[3] = acc[q].w * invS;
+                float* p2 = p1 + d.D;
+                p2[0] = v[q].x; p2[1] = v[q].y; p2[2] = v[q].z; p2[3] = v[q].w;
+            }
+        }
         __syncwarp();
         float4* dst = reinterpret_cast<float4*>(X0 + (long)b * ldx0);
         const float4* src4 = reinterpret_cast<const float4*>(row);
@@ -158,8 +206,7 @@ k_attn_fwd_gen(RowSrc r, Dims d, int model, const float* __restrict__ att,
             float a = 1.0f;
             if (model == MODEL_DIN_COS) {
                 dot = warp_sum(dot); nx2 = warp_sum(nx2);
-                float w = (dot / (sqrtf(nx2) * ny + 1e-8f) + 1.0f) * 0.5f;
-                a = sigmoid32(w * __ldg(att + s));
+                a = gate_cos(dot, nx2, ny, __ldg(att + s));
             } else if (model == MODEL_DIN_EUC) {
                 d2 = warp_sum(d2);
                 a = sigmoid32((1.0f - sqrtf(d2)) * __ldg(att + s));
@@ -184,7 +231,11 @@ k_attn_fwd_gen(RowSrc r, Dims d, int model, const float* __restrict__ att,
 // -------------------------------------------------------------------------------------------------
 // backward.  dX[b] = [g (d cost/d pooled) | gi (d cost/d item through the MLP input)].
 // Emits d cost/d att0 (sum over batch), and for every gathered row either
-//   * sgd != 0: table_row += -lr * grad with red.global.add.v4.f32 (fused scatter-add + SGD), or
+//   * sgd != 0: fused scatter-add + SGD with red.global.add.v4.f32:
+//       rows >= hot_rows : table_row += -lr * grad directly;
+//       rows <  hot_rows : grad accumulates in one of hot_reps replica accumulators (contention on
+//                          popular rows is spread over the replicas; k_hot_apply folds them into
+//                          the table after the kernel), or
 //   * dUb/dIt buffers (deterministic update path, debug hook, multi-GPU return leg).
 // Analytic reverse of din.go:231-298 (see DESIGN.md §kernels for the derivation):
 //   da_s = g·u_s / S ; dz_s = da_s a_s (1-a_s) ; datt_s += dz_s w_s ; dw_s = dz_s att_s
@@ -199,9 +250,21 @@ struct BwdOut {
     float* dIt;         // [B,D]   or null
     int    sgd;         // fused scatter-add + SGD into r.emb
     float  neg_lr;      // -table_lr
+    float* hot_acc;     // [hot_reps, hot_rows, D] replica accumulators (unscaled gradient sums)
+    int    hot_rows, hot_reps;
 };
 
-template <int LPR>
+__device__ __forceinline__ void scatter_row(const RowSrc& r, const Dims& d, const BwdOut& o, int idx, int rep,
+                                            int col, float4 g) {
+    if (idx < o.hot_rows) {
+        red_add4(o.hot_acc + ((long)rep * o.hot_rows + idx) * d.D + col, g);
+    } else {
+        red_add4(const_cast<float*>(r.emb) + (long)idx * r.lde + col,
+                 make_float4(o.neg_lr * g.x, o.neg_lr * g.y, o.neg_lr * g.z, o.neg_lr * g.w));
+    }
+}
+
+template <int LPR, int VPL, int UNR>
 __global__ void __launch_bounds__(256)
 k_attn_bwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
                const float* __restrict__ dX, long lddx, BwdOut o, int B) {
@@ -209,88 +272,151 @@ k_attn_bwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int lir = lane % LPR, sub = lane / LPR;
+    const int gwarp = blockIdx.x * (blockDim.x >> 5) + wib;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const int rep = o.hot_reps > 0 ? gwarp % o.hot_reps : 0;
     const float invS = 1.0f / (float)d.S;
     const bool use_hi = (!r.dense) && d.S <= 64;
     for (int j = threadIdx.x; j < d.S; j += blockDim.x) smem[j] = 0.0f;
     __syncthreads();
 
-    for (int b = blockIdx.x * (blockDim.x >> 5) + wib; b < B; b += nwarps) {
+    for (int b = gwarp; b < B; b += nwarps) {
         HistIdx hi; hi.load(r, d, b, lane);
-        const float4 g = ldg4(dX + (long)b * lddx + lir * 4);
-        const float4 gi = ldg4(dX + (long)b * lddx + d.D + lir * 4);
         const float* ip = src_it(r, d, b);
-        // the table is written by this kernel (sgd mode): coherent loads, no .nc
-        const float4 v = ip ? *reinterpret_cast<const float4*>(ip + lir * 4) : zero4();
-        const float ny = sqrtf(group_sum<LPR>(dot4(v, v)));
-        float4 dv = sub == 0 ? gi : zero4();
-        for (int s0 = 0; s0 < d.S; s0 += RPW) {
-            const int s = s0 + sub;
-            const float* up = ub_ptr(r, d, hi, use_hi, b, s);
-            const float4 u = up ? *reinterpret_cast<const float4*>(up + lir * 4) : zero4();
-            float4 du;
-            if (model == MODEL_YOUTUBE) {
-                du = make_float4(g.x * invS, g.y * invS, g.z * invS, g.w * invS);
-            } else {
-                const float att_s = s < d.S ? __ldg(att + s) : 0.0f;
-                const float gu = group_sum<LPR>(dot4(g, u));
-                if (model == MODEL_DIN_COS) {
-                    const float dot = group_sum<LPR>(dot4(u, v));
-                    const float nx = sqrtf(group_sum<LPR>(dot4(u, u)));
-                    const float den = nx * ny + 1e-8f;
-                    const float cs = dot / den;
-                    const float w = (cs + 1.0f) * 0.5f;
-                    const float a = sigmoid32(w * att_s);
-                    const float dz = gu * invS * a * (1.0f - a);
-                    if (lir == 0 && s < d.S) atomicAdd(&smem[s], dz * w);
-                    const float cc = 0.5f * dz * att_s;
-                    const float iden = 1.0f / den;
-                    const float ku = nx > 0.0f ? cs * ny / (nx * den) : 0.0f;
-                    const float kv = ny > 0.0f ? cs * nx / (ny * den) : 0.0f;
-                    const float ag = a * invS;
-                    du = make_float4(ag * g.x + cc * (v.x * iden - ku * u.x), ag * g.y + cc * (v.y * iden - ku * u.y),
-                                     ag * g.z + cc * (v.z * iden - ku * u.z), ag * g.w + cc * (v.w * iden - ku * u.w));
-                    dv.x += cc * (u.x * iden - kv * v.x); dv.y += cc * (u.y * iden - kv * v.y);
-                    dv.z += cc * (u.z * iden - kv * v.z); dv.w += cc * (u.w * iden - kv * v.w);
-                } else {
-                    const float4 e = make_float4(u.x - v.x, u.y - v.y, u.z - v.z, u.w - v.w);
-                    const float dist = sqrtf(group_sum<LPR>(dot4(e, e)));
-                    const float w = 1.0f - dist;
-                    const float a = sigmoid32(w * att_s);
-                    const float dz = gu * invS * a * (1.0f - a);
-                    if (lir == 0 && s < d.S) atomicAdd(&smem[s], dz * w);
-                    const float dw = dz * att_s;
-                    const float k = dist > 0.0f ? dw / dist : 0.0f;
-                    const float ag = a * invS;
-                    du = make_float4(ag * g.x - k * e.x, ag * g.y - k * e.y, ag * g.z - k * e.z, ag * g.w - k * e.w);
-                    if (s < d.S) { dv.x += k * e.x; dv.y += k * e.y; dv.z += k * e.z; dv.w += k * e.w; }
+        float4 g[VPL], v[VPL], dvu[VPL];
+        float ny2 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < VPL; q++) {
+            g[q] = ldg4(dX + (long)b * lddx + (q * LPR + lir) * 4);
+            // the table is written by this kernel (sgd mode): coherent loads, no .nc
+            v[q] = ip ? *reinterpret_cast<const float4*>(ip + (q * LPR + lir) * 4) : zero4();
+            ny2 += dot4(v[q], v[q]); dvu[q] = zero4();
+        }
+        ny2 = group_sum<LPR>(ny2);
+        const float ny = fsqrt_pos(ny2);
+        const float rny = ny2 > 0.0f ? rsqrtf(ny2) : 0.0f;
+        float kvsum = 0.0f;                               // coefficient of -v in dv (cosine)
+        for (int s0 = 0; s0 < d.S; s0 += UNR * RPW) {
+            float4 u[UNR][VPL]; int idx[UNR]; bool have[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; j++) {
+                const RowRef rr = ub_ref(r, d, hi, use_hi, b, s0 + j * RPW + sub);
+                idx[j] = rr.idx; have[j] = rr.p != nullptr;
+#pragma unroll
+                for (int q = 0; q < VPL; q++) u[j][q] = rr.p ? *reinterpret_cast<const float4*>(rr.p + (q * LPR + lir) * 4) : zero4();
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; j++) {
+                const int s = s0 + j * RPW + sub;
+                // du = c1*g + c2*v + c3*u ; dv += c4*u (+ c5*v accumulated as a scalar)
+                float c1 = invS, c2 = 0.0f, c3 = 0.0f, c4 = 0.0f;
+                if (model != MODEL_YOUTUBE) {
+                    const float att_s = s < d.S ? __ldg(att + s) : 0.0f;
+                    float gu = 0.0f, dot = 0.0f, nx2 = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < VPL; q++) {
+                        gu += dot4(g[q], u[j][q]);
+                        if (model == MODEL_DIN_COS) { dot += dot4(u[j][q], v[q]); nx2 += dot4(u[j][q], u[j][q]); }
+                        else {
+                            const float4 e = make_float4(u[j][q].x - v[q].x, u[j][q].y - v[q].y, u[j][q].z - v[q].z, u[j][q].w - v[q].w);
+                            nx2 += dot4(e, e);
+                        }
+                    }
+                    gu = group_sum<LPR>(gu); nx2 = group_sum<LPR>(nx2);
+                    if (model == MODEL_DIN_COS) {
+                        dot = group_sum<LPR>(dot);
+                        const float nx = fsqrt_pos(nx2);
+                        const float iden = frcp(nx * ny + 1e-8f);
+                        const float cs = dot * iden;
+                        const float w = (cs + 1.0f) * 0.5f;
+                        const float a = sigmoid_fast(w * att_s);
+                        const float dz = gu * invS * a * (1.0f - a);
+                        if (lir == 0 && s < d.S) atomicAdd(&smem[s], dz * w);
+                        const float cc = 0.5f * dz * att_s;
+                        c1 = a * invS; c2 = cc * iden; c4 = c2;
+                        c3 = nx2 > 0.0f ? -cc * cs * ny * iden * rsqrtf(nx2) : 0.0f;     // -cc*cos*|v|/(|u| den)
+                        kvsum += cc * cs * nx * iden * rny;                               //  cc*cos*|u|/(|v| den)
+                    } else {
+                        const float dist = fsqrt_pos(nx2);
+                        const float w = 1.0f - dist;
+                        const float a = sigmoid_fast(w * att_s);
+                        const float dz = gu * invS * a * (1.0f - a);
+                        if (lir == 0 && s < d.S) atomicAdd(&smem[s], dz * w);
+                        const float k = nx2 > 0.0f ? dz * att_s * rsqrtf(nx2) : 0.0f;    // dw/dist
+                        c1 = a * invS; c3 = -k; c2 = k;      // du = c1 g - k (u - v)
+                        c4 = s < d.S ? k : 0.0f;             // dv += k (u - v)
+                        kvsum += c4;
+                    }
+                }
+                if (s < d.S) {
+#pragma unroll
+                    for (int q = 0; q < VPL; q++) {
+                        const float4 uu = u[j][q];
+                        float4 du;
+                        du.x = fmaf(c3, uu.x, fmaf(c2, v[q].x, c1 * g[q].x)); du.y = fmaf(c3, uu.y, fmaf(c2, v[q].y, c1 * g[q].y));
+                        du.z = fmaf(c3, uu.z, fmaf(c2, v[q].z, c1 * g[q].z)); du.w = fmaf(c3, uu.w, fmaf(c2, v[q].w, c1 * g[q].w));
+                        dvu[q] = fma4(c4, uu, dvu[q]);
+                        if (o.dUb) *reinterpret_cast<float4*>(o.dUb + ((long)b * d.S + s) * d.D + (q * LPR + lir) * 4) = du;
+                        if (o.sgd && have[j]) scatter_row(r, d, o, idx[j], rep, (q * LPR + lir) * 4, du);
+                    }
                 }
             }
-            if (s < d.S) {
-                if (o.dUb) *reinterpret_cast<float4*>(o.dUb + ((long)b * d.S + s) * d.D + lir * 4) = du;
-                if (o.sgd && up)
-                    red_add4(const_cast<float*>(up) + lir * 4,
-                             make_float4(o.neg_lr * du.x, o.neg_lr * du.y, o.neg_lr * du.z, o.neg_lr * du.w));
+        }
+        // dv = gi + sum_subgroups(dvu) - (sum kv) * v
+#pragma unroll
+        for (int of = LPR; of < 32; of <<= 1) kvsum += __shfl_xor_sync(0xffffffffu, kvsum, of);
+#pragma unroll
+        for (int q = 0; q < VPL; q++) {
+#pragma unroll
+            for (int of = LPR; of < 32; of <<= 1) {
+                dvu[q].x += __shfl_xor_sync(0xffffffffu, dvu[q].x, of);
+                dvu[q].y += __shfl_xor_sync(0xffffffffu, dvu[q].y, of);
+                dvu[q].z += __shfl_xor_sync(0xffffffffu, dvu[q].z, of);
+                dvu[q].w += __shfl_xor_sync(0xffffffffu, dvu[q].w, of);
             }
         }
-#pragma unroll
-        for (int of = LPR; of < 32; of <<= 1) {
-            dv.x += __shfl_xor_sync(0xffffffffu, dv.x, of);
-            dv.y += __shfl_xor_sync(0xffffffffu, dv.y, of);
-            dv.z += __shfl_xor_sync(0xffffffffu, dv.z, of);
-            dv.w += __shfl_xor_sync(0xffffffffu, dv.w, of);
-        }
         if (sub == 0) {
-            if (o.dIt) *reinterpret_cast<float4*>(o.dIt + (long)b * d.D + lir * 4) = dv;
-            if (o.sgd && ip)
-                red_add4(const_cast<float*>(ip) + lir * 4,
-                         make_float4(o.neg_lr * dv.x, o.neg_lr * dv.y, o.neg_lr * dv.z, o.neg_lr * dv.w));
+            const int irow = (o.sgd && ip) ? r.item_row[b] : -1;
+#pragma unroll
+            for (int q = 0; q < VPL; q++) {
+                const float4 gi = ldg4(dX + (long)b * lddx + d.D + (q * LPR + lir) * 4);
+                float4 dv;
+                dv.x = gi.x + dvu[q].x - kvsum * v[q].x; dv.y = gi.y + dvu[q].y - kvsum * v[q].y;
+                dv.z = gi.z + dvu[q].z - kvsum * v[q].z; dv.w = gi.w + dvu[q].w - kvsum * v[q].w;
+                if (o.dIt) *reinterpret_cast<float4*>(o.dIt + (long)b * d.D + (q * LPR + lir) * 4) = dv;
+                if (irow >= 0) scatter_row(r, d, o, irow, rep, (q * LPR + lir) * 4, dv);
+            }
         }
     }
     __syncthreads();
     if (model != MODEL_YOUTUBE && o.datt)
         for (int j = threadIdx.x; j < d.S; j += blockDim.x)
             if (smem[j] != 0.0f) atomicAdd(o.datt + j, smem[j]);
+}
+
+// folds the hot-row replica accumulators into the table: row -= lr * sum_rep acc ; acc = 0
+__global__ void __launch_bounds__(256)
+k_hot_apply(float* __restrict__ emb, long lde, float* __restrict__ hot_acc, int hot_rows, int hot_reps,
+            int D, float neg_lr) {
+    const long n4 = (long)hot_rows * (D / 4);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const long row = i / (D / 4); const int c = (int)(i % (D / 4)) * 4;
+        float4 s = zero4();
+        for (int rep = 0; rep < hot_reps; rep++) {
+            float4* p = reinterpret_cast<float4*>(hot_acc + ((long)rep * hot_rows + row) * D + c);
+            const float4 t = *p;
+            if (t.x != 0.0f || t.y != 0.0f || t.z != 0.0f || t.w != 0.0f) {
+                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+                *p = zero4();
+            }
+        }
+        if (s.x != 0.0f || s.y != 0.0f || s.z != 0.0f || s.w != 0.0f) {
+            float4* e = reinterpret_cast<float4*>(emb + row * lde + c);
+            float4 t = *e;
+            t.x = fmaf(neg_lr, s.x, t.x); t.y = fmaf(neg_lr, s.y, t.y); t.z = fmaf(neg_lr, s.z, t.z); t.w = fmaf(neg_lr, s.w, t.w);
+            *e = t;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)

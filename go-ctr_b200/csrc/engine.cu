@@ -62,6 +62,7 @@ struct ctr_handle {
     unsigned *keys = nullptr, *keys2 = nullptr, *pos = nullptr, *pos2 = nullptr;
     void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0; size_t keys_cap = 0;
     double* d_cost = nullptr;
+    float* hot_acc = nullptr; int hot_rows = 0, hot_reps = 0;
     // staging for host-pointer entry points
     int *s_user = nullptr, *s_item = nullptr, *s_hist = nullptr; float* s_label = nullptr;
     // dense-X residency
@@ -124,29 +125,32 @@ bool vec_ok(const ctr_handle* h, const RowSrc& r) {
     int D = h->cfg.D;
     if (D % 4) return false;
     int lpr = D / 4;
-    if (lpr > 32 || (lpr & (lpr - 1))) return false;
+    if (lpr > 32 || (lpr & (lpr - 1))) return false;      // D in {4,8,16,32,64,128}
     if (r.dense) return (r.ldx % 4 == 0) && (r.ub0 % 4 == 0) && (r.it0 % 4 == 0) && (((uintptr_t)r.X) % 16 == 0);
     return r.lde % 4 == 0;
 }
 
-template <int LPR>
+// Lane mapping of the vector attention kernels for a row of D floats: LPR lanes x VPL float4 each.
+// Forward keeps 16 floats per lane when it can (8 rows per load-instruction group at D=64), backward
+// 8 (it also holds g, v and the item gradient); UNR groups are in flight before any arithmetic.
+template <int LPR, int VPL, int UNR>
 void launch_fwd_vec(ctr_handle* h, const RowSrc& r, int B) {
     size_t smem = (size_t)8 * h->Kp * sizeof(float);
-    k_attn_fwd_vec<LPR><<<grid_for_warps(h, B), 256, smem, h->stream>>>(r, dims_of(h), h->cfg.model, h->W[3], h->X0, h->Kp, h->Kp, B);
+    k_attn_fwd_vec<LPR, VPL, UNR><<<grid_for_warps(h, B), 256, smem, h->stream>>>(r, dims_of(h), h->cfg.model, h->W[3], h->X0, h->Kp, h->Kp, B);
 }
-template <int LPR>
+template <int LPR, int VPL, int UNR>
 void launch_bwd_vec(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
     size_t smem = (size_t)std::max(h->cfg.S, 1) * sizeof(float);
-    k_attn_bwd_vec<LPR><<<grid_for_warps(h, B), 256, smem, h->stream>>>(r, dims_of(h), h->cfg.model, h->W[3], h->dX, h->lddx, o, B);
+    k_attn_bwd_vec<LPR, VPL, UNR><<<grid_for_warps(h, B), 256, smem, h->stream>>>(r, dims_of(h), h->cfg.model, h->W[3], h->dX, h->lddx, o, B);
 }
 
 int attn_forward(ctr_handle* h, const RowSrc& r, int B) {
     if (vec_ok(h, r)) {
         return launch(h, "attn_fwd_vec", [&] {
-            switch (h->cfg.D / 4) {
-                case 1: launch_fwd_vec<1>(h, r, B); break;   case 2: launch_fwd_vec<2>(h, r, B); break;
-                case 4: launch_fwd_vec<4>(h, r, B); break;   case 8: launch_fwd_vec<8>(h, r, B); break;
-                case 16: launch_fwd_vec<16>(h, r, B); break; default: launch_fwd_vec<32>(h, r, B); break;
+            switch (h->cfg.D / 4) {           // float4 per row
+                case 1: launch_fwd_vec<1, 1, 2>(h, r, B); break;   case 2: launch_fwd_vec<2, 1, 2>(h, r, B); break;
+                case 4: launch_fwd_vec<4, 1, 2>(h, r, B); break;   case 8: launch_fwd_vec<4, 2, 2>(h, r, B); break;
+                case 16: launch_fwd_vec<4, 4, 2>(h, r, B); break;  default: launch_fwd_vec<8, 4, 2>(h, r, B); break;
             }
         });
     }
@@ -159,9 +163,9 @@ int attn_backward(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
     if (vec_ok(h, r)) {
         return launch(h, "attn_bwd_vec", [&] {
             switch (h->cfg.D / 4) {
-                case 1: launch_bwd_vec<1>(h, r, o, B); break;   case 2: launch_bwd_vec<2>(h, r, o, B); break;
-                case 4: launch_bwd_vec<4>(h, r, o, B); break;   case 8: launch_bwd_vec<8>(h, r, o, B); break;
-                case 16: launch_bwd_vec<16>(h, r, o, B); break; default: launch_bwd_vec<32>(h, r, o, B); break;
+                case 1: launch_bwd_vec<1, 1, 2>(h, r, o, B); break;   case 2: launch_bwd_vec<2, 1, 2>(h, r, o, B); break;
+                case 4: launch_bwd_vec<4, 1, 2>(h, r, o, B); break;   case 8: launch_bwd_vec<4, 2, 2>(h, r, o, B); break;
+                case 16: launch_bwd_vec<8, 2, 2>(h, r, o, B); break;  default: launch_bwd_vec<16, 2, 2>(h, r, o, B); break;
             }
         });
     }
@@ -206,6 +210,25 @@ int ensure_rowgrad_buffers(ctr_handle* h, int B) {
     RET(dalloc(h, &h->dIt, (size_t)B * h->cfg.D));
     h->dUb_cap = need;
     return CTR_OK;
+}
+
+// Replica accumulators for the popular rows of ITEM_EMB (rows [0, hot_rows), see k_attn_bwd_vec).
+// cfg.reserved[0]: 0 = auto (all rows of a small table / the first 32768 of a large one — keep rows
+// ordered by popularity, as word2vec-style vocabularies are), >0 = that many rows, <0 = off.
+int ensure_hot(ctr_handle* h) {
+    const int64_t rows = h->tab_local_rows[CTR_TABLE_ITEM_EMB];
+    int want = h->cfg.reserved[0];
+    if (want == 0) want = (int)std::min<int64_t>(rows, 32768);
+    if (want < 0) want = 0;
+    want = (int)std::min<int64_t>(want, rows);
+    if (h->hot_acc && h->hot_rows == want) return CTR_OK;
+    if (h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; }
+    h->hot_rows = want; h->hot_reps = 0;
+    if (want == 0) return CTR_OK;
+    const size_t row_bytes = (size_t)h->cfg.D * sizeof(float);
+    int reps = (int)std::min<size_t>(32, std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)want * row_bytes)));
+    h->hot_reps = reps;
+    return dalloc(h, &h->hot_acc, (size_t)reps * want * h->cfg.D);
 }
 
 int deterministic_table_update(ctr_handle* h, const RowSrc& r, int B) {
@@ -287,7 +310,14 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         if (buffers) RET(ensure_rowgrad_buffers(h, B));
         BwdOut bo{}; bo.datt = h->G[3]; bo.dUb = buffers ? h->dUb : nullptr; bo.dIt = buffers ? h->dIt : nullptr;
         bo.sgd = (learn_rows && c.table_opt == CTR_TABLE_SGD) ? 1 : 0; bo.neg_lr = -c.table_lr;
+        const bool hot = bo.sgd && vec_ok(h, r);
+        if (hot) { RET(ensure_hot(h)); bo.hot_acc = h->hot_acc; bo.hot_rows = h->hot_rows; bo.hot_reps = h->hot_reps; }
         RET(attn_backward(h, r, bo, B));
+        if (hot && h->hot_rows > 0)
+            RET(launch(h, "hot_rows_apply", [&] {
+                k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(h->tab[CTR_TABLE_ITEM_EMB], h->tab_ld[CTR_TABLE_ITEM_EMB], h->hot_acc,
+                                                                h->hot_rows, h->hot_reps, c.D, -c.table_lr);
+            }));
         if (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC) RET(deterministic_table_update(h, r, B));
     }
     if (o.update) {
@@ -461,7 +491,7 @@ void ctr_destroy(ctr_handle* h) {
     for (int i = 0; i < 4; i++) for (float* p : {h->W[i], h->G[i], h->Mo[i], h->Vo[i]}) if (p) cudaFree(p);
     for (void* p : {(void*)h->X0, (void*)h->H0d, (void*)h->H1d, (void*)h->P, (void*)h->Z, (void*)h->dZ1, (void*)h->dZ0, (void*)h->dX,
                     (void*)h->dUb, (void*)h->dIt, (void*)h->keys, (void*)h->keys2, (void*)h->pos, (void*)h->pos2, h->sort_tmp,
-                    (void*)h->d_cost, (void*)h->s_user, (void*)h->s_item, (void*)h->s_hist, (void*)h->s_label, (void*)h->dXd, (void*)h->dYd})
+                    (void*)h->d_cost, (void*)h->s_user, (void*)h->s_item, (void*)h->s_hist, (void*)h->s_label, (void*)h->dXd, (void*)h->dYd, (void*)h->hot_acc})
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -532,6 +562,7 @@ int ctr_table_upload(ctr_handle* h, int which, const float* rows, int64_t nrows,
     }
     CU(h, cudaStreamSynchronize(h->stream));
     h->tab_ld[which] = ld; h->tab_rows[which] = nrows; h->tab_local_rows[which] = local; h->tab_width[which] = width;
+    if (which == CTR_TABLE_ITEM_EMB && h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; h->hot_rows = 0; }
     return CTR_OK;
 }
 
@@ -555,6 +586,7 @@ int ctr_table_fill(ctr_handle* h, int which, int64_t nrows, int32_t width, uint3
     }));
     CU(h, cudaStreamSynchronize(h->stream));
     h->tab_ld[which] = ld; h->tab_rows[which] = nrows; h->tab_local_rows[which] = local; h->tab_width[which] = width;
+    if (which == CTR_TABLE_ITEM_EMB && h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; h->hot_rows = 0; }
     return CTR_OK;
 }
 

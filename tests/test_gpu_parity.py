@@ -227,7 +227,7 @@ def test_full_size_properties_at_north_star_batch():
       * prediction is per-sample: any 1000-row slice scores the same alone as inside the batch."""
     uP, S, D, cF, B, U, I = 52, 50, 64, 53, 65536, 5000, 40000
     rng = np.random.default_rng(12)
-    cfg = g.engine.default_config(g.MODEL_DIN_COS, uP=uP, S=S, D=D, cF=cF, batch=B, pred_batch=B, table_opt=g.TABLE_SGD, table_lr=1.0,
+    cfg = g.engine.default_config(g.MODEL_DIN_COS, uP=uP, S=S, D=D, cF=cF, batch=B, pred_batch=B, table_opt=g.TABLE_SGD, table_lr=100.0,
                                   dropout0=0.0, dropout1=0.0)
     eng = g.Engine(cfg)
     uf, itf, emb = make_tables(rng, U, I, uP, cF, D)
@@ -256,5 +256,5 @@ def test_full_size_properties_at_north_star_batch():
     got = (eng.table_download(g.TABLE_ITEM_EMB, I, D).astype(np.float64) - emb).sum(1)
     scale = np.abs(want).max()
     assert scale > 0
-    np.testing.assert_allclose(got, -want, rtol=2e-2, atol=2e-2 * scale)
-    assert abs(got.sum() + want.sum()) <= 2e-3 * np.abs(want).sum()
+    np.testing.assert_allclose(got, -100.0 * want, rtol=2e-2, atol=2e-2 * 100.0 * scale)
+    assert abs(got.sum() + 100.0 * want.sum()) <= 2e-3 * 100.0 * np.abs(want).sum()
