@@ -4,6 +4,7 @@
 #include "../../include/ctr_b200.h"
 #include "attn.cuh"
 #include "mlp.cuh"
+#include "umma_gemm.cuh"
 #include "auc.cuh"
 #include "comm.cuh"
 
@@ -72,6 +73,17 @@ struct ctr_handle {
     bool profiling = false;
     std::map<std::string, Prof> prof;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // tcgen05 GEMM engine (umma_gemm.cuh): pre-split K-major weight operands + TMA descriptors
+    struct Umma {
+        bool ready = false;
+        bool dirty = true;                 // weights changed since the last split
+        int stages_fwd0 = 0, stages_fwd1 = 0, stages_dz0 = 0, stages_dx = 0;
+        int bn_fwd0 = 0, bn_fwd1 = 0, bn_dx = 0;
+        float *Wt0[2] = {}, *Wt1[2] = {}, *W1s[2] = {}, *W0s[2] = {};     // [hi, lo]
+        CUtensorMap mA_X0, mA_H0d, mA_dZ1, mA_dZ0;
+        CUtensorMap mB_Wt0[2], mB_Wt1[2], mB_W1s[2], mB_W0s[2];
+    } um;
 
     Comm comm;
 };
@@ -192,6 +204,97 @@ int gemm_dw(ctr_handle* h, const char* name, GemmArgs g) {      // K = batch: 64
     return launch(h, name, [&] { k_sgemm<BM, BN, 16, 4, 4, true, false, EPI_ATOMIC><<<grid, 256, 0, h->stream>>>(g); });
 }
 
+
+// ---- tcgen05 GEMM launchers --------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(ctr_handle* h, CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q;
+        void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+            return set_err(h, CTR_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+        fn = (PFN_encodeTiled)p;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)umma::kBlockK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(h, CTR_ECUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return CTR_OK;
+}
+
+int umma_stages(int bn) {
+    size_t st = (size_t)umma::kABytes * 2 + (size_t)bn * 128 * 2;
+    return (int)std::min<size_t>(4, ((size_t)227 * 1024 - 2048) / st);
+}
+size_t umma_smem(int bn, int stages) {
+    return (size_t)stages * ((size_t)umma::kABytes * 2 + (size_t)bn * 128 * 2) + 8 * (3 * stages + 4) + 16 + 1024;
+}
+
+bool umma_supported(const ctr_handle* h) {
+    return h->H0p <= 256 && h->H1p <= 256 && round_up(2 * h->cfg.D, 16) <= 256 && h->H0p % 16 == 0 && h->H1p % 16 == 0;
+}
+
+int umma_init(ctr_handle* h) {
+    if (h->um.ready) return CTR_OK;
+    const ctr_config& c = h->cfg;
+    auto& u = h->um;
+    u.bn_fwd0 = h->H0p; u.bn_fwd1 = h->H1p; u.bn_dx = round_up(2 * c.D, 16);
+    u.stages_fwd0 = umma_stages(u.bn_fwd0); u.stages_fwd1 = umma_stages(u.bn_fwd1);
+    u.stages_dz0 = umma_stages(u.bn_fwd0); u.stages_dx = umma_stages(u.bn_dx);
+    if (u.stages_fwd0 < 2) return set_err(h, CTR_EINVAL, "tcgen05 GEMM: tile does not fit shared memory");
+    for (int i = 0; i < 2; i++) {
+        RET(dalloc(h, &u.Wt0[i], (size_t)h->H0p * h->Kp)); RET(dalloc(h, &u.Wt1[i], (size_t)h->H1p * h->H0p));
+        RET(dalloc(h, &u.W1s[i], (size_t)h->H0p * h->H1p)); RET(dalloc(h, &u.W0s[i], (size_t)u.bn_dx * h->H0p));
+        RET(make_map(h, &u.mB_Wt0[i], u.Wt0[i], h->H0p, h->Kp, h->Kp, u.bn_fwd0));
+        RET(make_map(h, &u.mB_Wt1[i], u.Wt1[i], h->H1p, h->H0p, h->H0p, u.bn_fwd1));
+        RET(make_map(h, &u.mB_W1s[i], u.W1s[i], h->H0p, h->H1p, h->H1p, u.bn_fwd0));
+        RET(make_map(h, &u.mB_W0s[i], u.W0s[i], u.bn_dx, h->H0p, h->H0p, u.bn_dx));
+    }
+    RET(make_map(h, &u.mA_X0, h->X0, h->Bmax, h->Kp, h->Kp, umma::kBlockM));
+    RET(make_map(h, &u.mA_H0d, h->H0d, h->Bmax, h->H0p, h->H0p, umma::kBlockM));
+    RET(make_map(h, &u.mA_dZ1, h->dZ1, h->Bmax, h->H1p, h->H1p, umma::kBlockM));
+    RET(make_map(h, &u.mA_dZ0, h->dZ0, h->Bmax, h->H0p, h->H0p, umma::kBlockM));
+    const size_t smax = umma_smem(256, 2);
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    u.ready = true; u.dirty = true;
+    return CTR_OK;
+}
+
+int umma_split_weights(ctr_handle* h) {
+    auto& u = h->um;
+    if (!u.dirty) return CTR_OK;
+    const ctr_config& c = h->cfg;
+    RET(launch(h, "split_weights_tf32", [&] {
+        umma::k_split_weights<<<64, 256, 0, h->stream>>>(h->W[0], h->H0p, h->in, c.H0, 1, u.Wt0[0], u.Wt0[1], h->Kp);          // W0ᵀ [H0, in]
+        umma::k_split_weights<<<32, 256, 0, h->stream>>>(h->W[1], h->H1p, c.H0, c.H1, 1, u.Wt1[0], u.Wt1[1], h->H0p);        // W1ᵀ [H1, H0]
+        umma::k_split_weights<<<32, 256, 0, h->stream>>>(h->W[1], h->H1p, c.H0, c.H1, 0, u.W1s[0], u.W1s[1], h->H1p);        // W1  [H0, H1]
+        umma::k_split_weights<<<64, 256, 0, h->stream>>>(h->W[0] + (long)c.uP * h->H0p, h->H0p, 2 * c.D, c.H0, 0, u.W0s[0], u.W0s[1], h->H0p);   // W0[uP:uP+2D, :]
+    }));
+    u.dirty = false;
+    return CTR_OK;
+}
+
+template <int EPI>
+int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtensorMap* mB, umma::Args a) {
+    const int tiles = (a.M + umma::kBlockM - 1) / umma::kBlockM;
+    const int grid = std::min(tiles, h->num_sms);
+    const size_t smem = umma_smem(a.bn, a.stages);
+    return launch(h, name, [&] { umma::k_umma_gemm<EPI, true><<<grid, 256, smem, h->stream>>>(mA, mB[0], mB[1], a); });
+}
+
+bool use_umma(const ctr_handle* h) {
+    return h->cfg.gemm == CTR_GEMM_TCGEN05_3XTF32 && umma_supported(h);
+}
+
 // One pass of the hot path over one batch (model.go:107-196 inner loop body).
 //   training: dropout on, backward + optimiser step (update) or gradients only (!update)
 struct StepOpts {
@@ -263,6 +366,17 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
     const float d0 = o.training ? c.dropout0 : 0.0f, d1 = o.training ? c.dropout1 : 0.0f;
 
     RET(attn_forward(h, r, B));
+    const bool um = use_umma(h);
+    if (um) {
+        RET(umma_init(h));
+        RET(umma_split_weights(h));
+        umma::Args a{}; a.M = B; a.N = c.H0; a.Nz = h->H0p; a.K = h->Kp; a.bn = h->um.bn_fwd0; a.C = h->H0d; a.ldc = h->H0p;
+        a.drop_p = d0; a.seed = c.seed; a.stream = h->step * 4u + 0u; a.stages = h->um.stages_fwd0;
+        RET(umma_gemm<umma::UEPI_SIGMOID_DROP>(h, "umma_fwd0_sigmoid", h->um.mA_X0, h->um.mB_Wt0, a));
+        umma::Args b{}; b.M = B; b.N = c.H1; b.Nz = h->H1p; b.K = h->H0p; b.bn = h->um.bn_fwd1; b.C = h->H1d; b.ldc = h->H1p;
+        b.drop_p = d1; b.seed = c.seed; b.stream = h->step * 4u + 1u; b.stages = h->um.stages_fwd1;
+        RET(umma_gemm<umma::UEPI_SIGMOID_DROP>(h, "umma_fwd1_sigmoid", h->um.mA_H0d, h->um.mB_Wt1, b));
+    } else {
     {   // h0 = dropout(sigmoid(x·W0))   din.go:307-308
         GemmArgs g{}; g.A = h->X0; g.lda = h->Kp; g.B = h->W[0]; g.ldb = h->H0p; g.C = h->H0d; g.ldc = h->H0p;
         g.M = B; g.N = c.H0; g.K = h->in; g.Nz = h->H0p; g.drop_p = d0; g.seed = c.seed; g.stream = h->step * 4u + 0u;
@@ -272,6 +386,7 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         GemmArgs g{}; g.A = h->H0d; g.lda = h->H0p; g.B = h->W[1]; g.ldb = h->H1p; g.C = h->H1d; g.ldc = h->H1p;
         g.M = B; g.N = c.H1; g.K = c.H0; g.Nz = h->H1p; g.drop_p = d1; g.seed = c.seed; g.stream = h->step * 4u + 1u;
         RET((gemm_big<false, false, EPI_SIGMOID_DROP>(h, "sgemm_fwd1_sigmoid", g)));
+    }
     }
     const bool bwd = o.training;
     if (bwd) CU(h, cudaMemsetAsync(h->d_cost, 0, sizeof(double), h->stream));
@@ -288,7 +403,11 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         g.M = c.H0; g.N = c.H1; g.K = B;
         RET(gemm_dw(h, "sgemm_dW1_splitk", g));
     }
-    {   // dZ0 = (dZ1 · W1ᵀ) ⊙ dsigmoid(h0d)
+    if (um) {
+        umma::Args a{}; a.M = B; a.N = c.H0; a.Nz = h->H0p; a.K = h->H1p; a.bn = h->um.bn_fwd0; a.C = h->dZ0; a.ldc = h->H0p;
+        a.H = h->H0d; a.ldh = h->H0p; a.drop_p = d0; a.stages = h->um.stages_dz0;
+        RET(umma_gemm<umma::UEPI_DSIGMOID>(h, "umma_dZ0_dsigmoid", h->um.mA_dZ1, h->um.mB_W1s, a));
+    } else {   // dZ0 = (dZ1 · W1ᵀ) ⊙ dsigmoid(h0d)
         GemmArgs g{}; g.A = h->dZ1; g.lda = h->H1p; g.B = h->W[1]; g.ldb = h->H1p; g.C = h->dZ0; g.ldc = h->H0p;
         g.M = B; g.N = c.H0; g.K = c.H1; g.Nz = h->H0p; g.H = h->H0d; g.ldh = h->H0p; g.drop_p = d0;
         RET((gemm_big<false, true, EPI_DSIGMOID>(h, "sgemm_dZ0_dsigmoid", g)));
@@ -301,7 +420,11 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
     const bool learn_rows = o.update && c.table_opt != CTR_TABLE_FROZEN && !r.dense;
     const bool need_attn_bwd = c.model != CTR_MODEL_YOUTUBE || learn_rows || o.want_rows;
     if (need_attn_bwd) {
-        {   // d concat[:, uP:uP+2D] = dZ0 · W0[uP:uP+2D, :]ᵀ
+        if (um) {
+            umma::Args a{}; a.M = B; a.N = 2 * c.D; a.Nz = h->lddx; a.K = h->H0p; a.bn = h->um.bn_dx; a.C = h->dX; a.ldc = h->lddx;
+            a.stages = h->um.stages_dx;
+            RET(umma_gemm<umma::UEPI_STORE>(h, "umma_dX", h->um.mA_dZ0, h->um.mB_W0s, a));
+        } else {   // d concat[:, uP:uP+2D] = dZ0 · W0[uP:uP+2D, :]ᵀ
             GemmArgs g{}; g.A = h->dZ0; g.lda = h->H0p; g.B = h->W[0] + (long)c.uP * h->H0p; g.ldb = h->H0p;
             g.C = h->dX; g.ldc = h->lddx; g.M = B; g.N = 2 * c.D; g.K = c.H0; g.Nz = h->lddx;
             RET((gemm_big<false, true, EPI_STORE>(h, "sgemm_dX", g)));
@@ -334,6 +457,7 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         a.c1 = (float)(1.0 - std::pow((double)c.beta1, (double)t));
         a.c2 = (float)(1.0 - std::pow((double)c.beta2, (double)t));
         RET(launch(h, "adam_dense", [&] { k_adam<<<h->num_sms, 256, 0, h->stream>>>(a); }));
+        h->um.dirty = true;
         h->step++;
     }
     return CTR_OK;
@@ -488,6 +612,7 @@ void ctr_destroy(ctr_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     comm_destroy(h);
     for (int i = 0; i < 3; i++) if (h->tab[i]) cudaFree(h->tab[i]);
+    for (int i = 0; i < 2; i++) for (float* p : {h->um.Wt0[i], h->um.Wt1[i], h->um.W1s[i], h->um.W0s[i]}) if (p) cudaFree(p);
     for (int i = 0; i < 4; i++) for (float* p : {h->W[i], h->G[i], h->Mo[i], h->Vo[i]}) if (p) cudaFree(p);
     for (void* p : {(void*)h->X0, (void*)h->H0d, (void*)h->H1d, (void*)h->P, (void*)h->Z, (void*)h->dZ1, (void*)h->dZ0, (void*)h->dX,
                     (void*)h->dUb, (void*)h->dIt, (void*)h->keys, (void*)h->keys2, (void*)h->pos, (void*)h->pos2, h->sort_tmp,
@@ -517,6 +642,7 @@ int ctr_set_weights(ctr_handle* h, const float* mlp0, const float* mlp1, const f
     else { std::vector<float> ones(c.S, 1.0f); CU(h, cudaMemcpyAsync(h->W[3], ones.data(), c.S * sizeof(float), cudaMemcpyHostToDevice, h->stream)); CU(h, cudaStreamSynchronize(h->stream)); }
     CU(h, cudaStreamSynchronize(h->stream));
     h->step = 0;
+    h->um.dirty = true;
     return CTR_OK;
 }
 

@@ -1,0 +1,295 @@
+// umma_gemm.cuh — the dense MLP GEMMs on Blackwell's 5th-gen tensor cores (tcgen05 + TMEM + TMA),
+// hand-written for sm_100a.  C[M,N] = epilogue(A[M,K] · B[N,K]ᵀ), fp32 in / fp32 out.
+//
+// Precision: the reference's MLP is float32 (gonum Sgemm under gorgonia, din.go:307-315) and the
+// parity bar is 1e-4 relative on scores, which single-pass TF32 (10-bit mantissa) cannot hold.  So
+// each product is error-compensated "3xTF32": x = hi + lo with hi = x & 0xFFFFE000 (exactly
+// representable in TF32) and lo = x - hi (exact in fp32), and
+//     A·B ≈ A_hi·B_hi + A_hi·B_lo + A_lo·B_hi            (fp32 accumulation in TMEM).
+// B (weights, tiny) is pre-split once per step by k_split_weights; A (activations, streamed from
+// HBM exactly once) is split inside the kernel by two converter warps, tile by tile in shared
+// memory — the operation is elementwise, so it is oblivious to the 128-byte swizzle TMA applied.
+//
+// One persistent CTA per SM, 8 warps, warp-specialised:
+//   warp 0   TMA producer: cp.async.bulk.tensor 2D, SWIZZLE_128B, {32 fp32 x 128 rows} A boxes and
+//            {32 x BLOCK_N} B_hi/B_lo boxes into a STAGES-deep smem ring (mbarrier complete_tx)
+//   warp 1   MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BLOCK_N,
+//            K=8 per instruction; 4 k-steps x 3 products per 32-wide k-block; tcgen05.commit frees
+//            the smem stage and, after the last k-block, publishes the TMEM accumulator
+//   warps 2-3 converters (warp 2 also owns tcgen05.alloc/dealloc)
+//   warps 4-7 epilogue: tcgen05.ld 32x32b.x16 (TMEM lane = tile row), fused sigmoid+dropout /
+//            dsigmoid / plain store, 64-byte row segments to global
+// Two TMEM accumulators (double buffering) overlap tile i's epilogue with tile i+1's MMAs.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace ctr {
+namespace umma {
+
+enum { UEPI_STORE = 0, UEPI_SIGMOID_DROP = 1, UEPI_DSIGMOID = 2 };
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;                    // fp32 elements = 128 bytes = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 4; // 16 KB
+
+struct Args {
+    int M, N, Nz, K;            // K multiple of 32; columns [N, Nz) of C written as zeros
+    int bn;                     // BLOCK_N (multiple of 16, <= 256) >= Nz
+    float* C; long ldc;
+    const float* H; long ldh;   // UEPI_DSIGMOID: stored post-dropout activation
+    float drop_p; uint32_t seed, stream;
+    int stages;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B: rows of 128 bytes, 8-row groups
+// 1024 bytes apart (SBO), LBO unused (=1); version 1 (sm_100); layout type 2.
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ size_t stage_bytes(int bn, bool split3) {
+    return (size_t)kABytes * (split3 ? 2 : 1) + (size_t)bn * 128 * (split3 ? 2 : 1);
+}
+
+template <int EPI, bool SPLIT3>
+__global__ void __launch_bounds__(256, 1)
+k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+            const __grid_constant__ CUtensorMap tmBlo, Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int bn = a.bn, stages = a.stages;
+    const uint32_t bBytes = (uint32_t)bn * 128u;
+    const uint32_t stBytes = (uint32_t)kABytes * (SPLIT3 ? 2u : 1u) + bBytes * (SPLIT3 ? 2u : 1u);
+    // stage s: [A | (Alo) | Bhi | (Blo)]
+    auto sA = [&](int s) { return base + (uint32_t)s * stBytes; };
+    auto sAlo = [&](int s) { return sA(s) + kABytes; };
+    auto sBhi = [&](int s) { return sA(s) + kABytes * (SPLIT3 ? 2u : 1u); };
+    auto sBlo = [&](int s) { return sBhi(s) + bBytes; };
+    const uint32_t bars = base + (uint32_t)stages * stBytes;          // 8-byte barriers
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto conv = [&](int s) { return bars + 8u * (stages + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * stages + s); };
+    auto tfull = [&](int i) { return bars + 8u * (3 * stages + i); };
+    auto tempty = [&](int i) { return bars + 8u * (3 * stages + 2 + i); };
+    const uint32_t tmem_slot = bars + 8u * (3 * stages + 4);
+    const int acc_stride = bn <= 128 ? 128 : 256;
+    const uint32_t ncols = 2u * acc_stride;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++) { mbar_init(full(s), 1); mbar_init(conv(s), 64); mbar_init(empty(s), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int num_k = a.K / kBlockK;
+    const int num_tiles = (a.M + kBlockM - 1) / kBlockM;
+
+    if (warp == 0) {
+        if (lane == 0) {                                            // ---------------- TMA producer
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < num_k; kb++, it++) {
+                    const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
+                    mbar_wait(empty(s), ph ^ 1u);
+                    mbar_expect_tx(full(s), (uint32_t)kABytes + bBytes * (SPLIT3 ? 2u : 1u));
+                    tma_load_2d(sA(s), &tmA, full(s), kb * kBlockK, tile * kBlockM);
+                    tma_load_2d(sBhi(s), &tmBhi, full(s), kb * kBlockK, 0);
+                    if (SPLIT3) tma_load_2d(sBlo(s), &tmBlo, full(s), kb * kBlockK, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                            // ---------------- MMA issuer
+            const uint32_t idesc = idesc_tf32(kBlockM, bn);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+                const int acc = tcount & 1; const uint32_t aph = (tcount >> 1) & 1u;
+                mbar_wait(tempty(acc), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+                for (int kb = 0; kb < num_k; kb++, it++) {
+                    const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
+                    mbar_wait(SPLIT3 ? conv(s) : full(s), ph);
+                    tc_fence_after();
+                    const uint64_t dAhi = desc_k_sw128(sA(s)), dBhi = desc_k_sw128(sBhi(s));
+                    const uint64_t dAlo = SPLIT3 ? desc_k_sw128(sAlo(s)) : 0, dBlo = SPLIT3 ? desc_k_sw128(sBlo(s)) : 0;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 8; k++) {         // UMMA_K = 8 tf32 = 32 bytes = +2 in the address field
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        umma_tf32(d_tmem, dAhi + ko, dBhi + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (SPLIT3) {
+                            umma_tf32(d_tmem, dAhi + ko, dBlo + ko, idesc, 1u);
+                            umma_tf32(d_tmem, dAlo + ko, dBhi + ko, idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty(s));                          // smem stage reusable once these MMAs retire
+                }
+                umma_commit(tfull(acc));                            // accumulator complete
+            }
+        }
+    } else if (warp < 4) {
+        if (SPLIT3) {                                               // ---------------- converters (64 threads)
+            const int c = threadIdx.x - 64;
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < num_k; kb++, it++) {
+                    const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
+                    mbar_wait(full(s), ph);
+                    const uint32_t pa = sA(s), pl = sAlo(s);
+#pragma unroll 4
+                    for (int i = c; i < kABytes / 16; i += 64) {
+                        float4 x;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(pa + 16u * i));
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+                        h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pa + 16u * i), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pl + 16u * i), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                    }
+                    fence_proxy_async();                            // generic-proxy writes → visible to tcgen05.mma
+                    mbar_arrive(conv(s));
+                }
+            }
+        }
+    } else {                                                        // ---------------- epilogue (warps 4..7)
+        const int q = warp & 3;                                     // TMEM lane quadrant this warp may read
+        const int row_in_tile = q * 32 + lane;
+        const float inv_keep = a.drop_p > 0.0f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
+            const int acc = tcount & 1; const uint32_t aph = (tcount >> 1) & 1u;
+            mbar_wait(tfull(acc), aph);
+            tc_fence_after();
+            const long gm = (long)tile * kBlockM + row_in_tile;
+            const uint32_t trow = tmem_base + (uint32_t)(acc * acc_stride) + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < bn; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+                if (gm < a.M && c0 < a.Nz) {
+                    float* crow = a.C + gm * a.ldc + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int gn = c0 + j;
+                        float x = v[j];
+                        if (gn >= a.N) x = 0.0f;
+                        else if (EPI == UEPI_SIGMOID_DROP) {
+                            x = sigmoid32(x);
+                            if (a.drop_p > 0.0f)
+                                x *= uniform24(a.seed, a.stream, (uint64_t)gm * (uint64_t)a.N + gn) < (1.0f - a.drop_p) ? inv_keep : 0.0f;
+                        } else if (EPI == UEPI_DSIGMOID) {
+                            x *= dsigmoid_drop(__ldg(a.H + gm * a.ldh + gn), a.drop_p);
+                        }
+                        v[j] = x;
+                    }
+                    const int nvalid = min(16, a.Nz - c0);          // Nz and ldc are multiples of 4
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        if (j < nvalid) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, ncols);
+}
+
+// W (logical [rows, cols], stride ld) → hi / lo TF32 split, optionally transposed, into padded
+// K-major operand buffers [orows_pad, ocols_pad] (stride old); padding stays zero.
+__global__ void __launch_bounds__(256)
+k_split_weights(const float* __restrict__ W, long ld, int rows, int cols, int transpose,
+                float* __restrict__ hi, float* __restrict__ lo, long old) {
+    const long n = (long)rows * cols;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i % cols);
+        const float x = W[(long)r * ld + c];
+        const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        const long o = transpose ? (long)c * old + r : (long)r * old + c;
+        hi[o] = h; lo[o] = x - h;
+    }
+}
+
+}  // namespace umma
+}  // namespace ctr
