@@ -261,7 +261,7 @@ int umma_init(ctr_handle* h) {
     RET(make_map(h, &u.mA_H0d, h->H0d, h->Bmax, h->H0p, h->H0p, umma::kBlockM));
     RET(make_map(h, &u.mA_dZ1, h->dZ1, h->Bmax, h->H1p, h->H1p, umma::kBlockM));
     RET(make_map(h, &u.mA_dZ0, h->dZ0, h->Bmax, h->H0p, h->H0p, umma::kBlockM));
-    const size_t smax = umma_smem(256, 2);
+    const size_t smax = (size_t)227 * 1024;
     CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
     CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
     CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
@@ -292,7 +292,7 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
 }
 
 bool use_umma(const ctr_handle* h) {
-    return h->cfg.gemm == CTR_GEMM_TCGEN05_3XTF32 && umma_supported(h);
+    return h->cfg.gemm != CTR_GEMM_FP32 && umma_supported(h);     // AUTO → tcgen05 when the shape qualifies
 }
 
 // One pass of the hot path over one batch (model.go:107-196 inner loop body).
