@@ -12,7 +12,7 @@ constexpr int kWarp = 32;
 __device__ __forceinline__ float sigmoid32(float x) {
     if (x < -88.0f) return 0.0f;
     if (x > 15.0f) return 1.0f;
-    return 1.0f / (1.0f + __expf(-x));
+    return __fdividef(1.0f, 1.0f + __expf(-x));       // MUFU.EX2 + MUFU.RCP, rel. error ~1e-7
 }
 
 // Counter RNG (spec shared with the test oracle; implemented independently here): dropout masks
@@ -25,8 +25,15 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint32_t seed, uint32_t strea
     z ^= z >> 31;
     return z;
 }
+// dropout draws: a 32-bit multiply-xorshift hash of (seed, stream, counter) — ~8 integer ops per
+// element, cheap enough for a GEMM epilogue
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t seed, uint32_t stream, uint32_t ctr) {
+    uint32_t x = ctr ^ (seed * 0x9E3779B1u) ^ (stream * 0x85EBCA77u + 0xC2B2AE3Du);
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
 __host__ __device__ __forceinline__ float uniform24(uint32_t seed, uint32_t stream, uint64_t ctr) {
-    return (float)(mix64(seed, stream, ctr) >> 40) * (1.0f / 16777216.0f);
+    return (float)(hash32(seed, stream, (uint32_t)ctr) >> 8) * (1.0f / 16777216.0f);
 }
 // dropout keep-factor: 0 or 1/(1-p)
 __device__ __forceinline__ float drop_keep(float p, uint32_t seed, uint32_t stream, uint64_t ctr) {

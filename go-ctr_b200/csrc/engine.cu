@@ -288,7 +288,7 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
     const int tiles = (a.M + umma::kBlockM - 1) / umma::kBlockM;
     const int grid = std::min(tiles, h->num_sms);
     const size_t smem = umma_smem(a.bn, a.stages);
-    return launch(h, name, [&] { umma::k_umma_gemm<EPI, true><<<grid, 256, smem, h->stream>>>(mA, mB[0], mB[1], a); });
+    return launch(h, name, [&] { umma::k_umma_gemm<EPI, true><<<grid, 384, smem, h->stream>>>(mA, mB[0], mB[1], a); });
 }
 
 bool use_umma(const ctr_handle* h) {

@@ -10,15 +10,17 @@
 // HBM exactly once) is split inside the kernel by two converter warps, tile by tile in shared
 // memory — the operation is elementwise, so it is oblivious to the 128-byte swizzle TMA applied.
 //
-// One persistent CTA per SM, 8 warps, warp-specialised:
+// One persistent CTA per SM, 12 warps, warp-specialised:
 //   warp 0   TMA producer: cp.async.bulk.tensor 2D, SWIZZLE_128B, {32 fp32 x 128 rows} A boxes and
 //            {32 x BLOCK_N} B_hi/B_lo boxes into a STAGES-deep smem ring (mbarrier complete_tx)
 //   warp 1   MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BLOCK_N,
 //            K=8 per instruction; 4 k-steps x 3 products per 32-wide k-block; tcgen05.commit frees
 //            the smem stage and, after the last k-block, publishes the TMEM accumulator
 //   warps 2-3 converters (warp 2 also owns tcgen05.alloc/dealloc)
-//   warps 4-7 epilogue: tcgen05.ld 32x32b.x16 (TMEM lane = tile row), fused sigmoid+dropout /
-//            dsigmoid / plain store, 64-byte row segments to global
+//   warps 4-11 epilogue: tcgen05.ld 32x32b.x16 (TMEM lane = tile row; warp w reads lane quadrant
+//            w%4, the two warps of a quadrant take alternate 16-column chunks), next chunk's TMEM
+//            load in flight while the current one is transformed; fused sigmoid+dropout / dsigmoid /
+//            plain store, 64-byte row segments to global
 // Two TMEM accumulators (double buffering) overlap tile i's epilogue with tile i+1's MMAs.
 #pragma once
 #include <cuda.h>
@@ -91,16 +93,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
+// asynchronous TMEM → register load of 16 consecutive columns of this thread's lane; the registers
+// are valid only after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B: rows of 128 bytes, 8-row groups
 // 1024 bytes apart (SBO), LBO unused (=1); version 1 (sm_100); layout type 2.
@@ -123,7 +124,7 @@ __device__ __forceinline__ size_t stage_bytes(int bn, bool split3) {
 }
 
 template <int EPI, bool SPLIT3>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
             const __grid_constant__ CUtensorMap tmBlo, Args a) {
     extern __shared__ uint8_t smem_raw[];
@@ -149,7 +150,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; s++) { mbar_init(full(s), 1); mbar_init(conv(s), 64); mbar_init(empty(s), 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 128); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 256); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, ncols);
@@ -231,10 +232,13 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
             }
         }
-    } else {                                                        // ---------------- epilogue (warps 4..7)
+    } else {                                                        // ---------------- epilogue (warps 4..11)
         const int q = warp & 3;                                     // TMEM lane quadrant this warp may read
+        const int half = (warp - 4) >> 2;                           // which alternate 16-column chunks
         const int row_in_tile = q * 32 + lane;
         const float inv_keep = a.drop_p > 0.0f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+        const float keep_thr = 1.0f - a.drop_p;
+        const int nchunks = bn / 16;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
             const int acc = tcount & 1; const uint32_t aph = (tcount >> 1) & 1u;
@@ -242,22 +246,37 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc_fence_after();
             const long gm = (long)tile * kBlockM + row_in_tile;
             const uint32_t trow = tmem_base + (uint32_t)(acc * acc_stride) + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < bn; c0 += 16) {
-                float v[16];
-                tmem_ld16(trow + (uint32_t)c0, v);
+            const uint32_t ctr0 = (uint32_t)((uint64_t)gm * (uint64_t)a.N);
+            uint32_t rb[2][16];
+            int ci = half;
+            if (ci < nchunks) tmem_ld16_async(trow + (uint32_t)(ci * 16), rb[0]);
+            int cur = 0;
+            for (; ci < nchunks; ci += 2, cur ^= 1) {
+                tmem_ld_wait();
+                if (ci + 2 < nchunks) tmem_ld16_async(trow + (uint32_t)((ci + 2) * 16), rb[cur ^ 1]);   // in flight during the math below
+                const int c0 = ci * 16;
                 if (gm < a.M && c0 < a.Nz) {
+                    float v[16];
                     float* crow = a.C + gm * a.ldc + c0;
+                    float hsrc[16];
+                    if (EPI == UEPI_DSIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 t = (c0 + j < a.Nz) ? ldg4(a.H + gm * a.ldh + c0 + j) : zero4();
+                            hsrc[j] = t.x; hsrc[j + 1] = t.y; hsrc[j + 2] = t.z; hsrc[j + 3] = t.w;
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const int gn = c0 + j;
-                        float x = v[j];
+                        float x = __uint_as_float(rb[cur][j]);
                         if (gn >= a.N) x = 0.0f;
                         else if (EPI == UEPI_SIGMOID_DROP) {
                             x = sigmoid32(x);
                             if (a.drop_p > 0.0f)
-                                x *= uniform24(a.seed, a.stream, (uint64_t)gm * (uint64_t)a.N + gn) < (1.0f - a.drop_p) ? inv_keep : 0.0f;
+                                x *= uniform24(a.seed, a.stream, ctr0 + (uint32_t)gn) < keep_thr ? inv_keep : 0.0f;
                         } else if (EPI == UEPI_DSIGMOID) {
-                            x *= dsigmoid_drop(__ldg(a.H + gm * a.ldh + gn), a.drop_p);
+                            x *= dsigmoid_drop(hsrc[j], a.drop_p);
                         }
                         v[j] = x;
                     }

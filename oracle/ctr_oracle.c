@@ -163,8 +163,14 @@ uint64_t orc_mix64(uint32_t seed, uint32_t stream, uint64_t ctr) {
     z ^= z >> 31;
     return z;
 }
+/* dropout draws: 32-bit multiply-xorshift hash of (seed, stream, low 32 bits of the counter) */
+static uint32_t orc_hash32(uint32_t seed, uint32_t stream, uint32_t ctr) {
+    uint32_t x = ctr ^ (seed * 0x9E3779B1u) ^ (stream * 0x85EBCA77u + 0xC2B2AE3Du);
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
 float orc_uniform24(uint32_t seed, uint32_t stream, uint64_t ctr) {
-    return (float)(orc_mix64(seed, stream, ctr) >> 40) * (1.0f / 16777216.0f);
+    return (float)(orc_hash32(seed, stream, (uint32_t)ctr) >> 8) * (1.0f / 16777216.0f);
 }
 void orc_gaussian_init(float* w, long n, uint32_t seed, uint32_t stream) {
     for (long i = 0; i < n; i++) {   /* Box–Muller, one draw per element */
