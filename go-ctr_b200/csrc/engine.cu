@@ -85,6 +85,8 @@ struct ctr_handle {
         CUtensorMap mB_Wt0[2], mB_Wt1[2], mB_W1s[2], mB_W0s[2];
     } um;
 
+    unsigned long long* umma_dbg = nullptr;     // CTR_UMMA_TIMELINE=1: timeline buffer of the last umma launch
+
     Comm comm;
 };
 
@@ -265,6 +267,7 @@ int umma_init(ctr_handle* h) {
     CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
     CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
     CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    if (getenv("CTR_UMMA_TIMELINE")) RET(dalloc(h, &h->umma_dbg, 8192));
     u.ready = true; u.dirty = true;
     return CTR_OK;
 }
@@ -288,7 +291,24 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
     const int tiles = (a.M + umma::kBlockM - 1) / umma::kBlockM;
     const int grid = std::min(tiles, h->num_sms);
     const size_t smem = umma_smem(a.bn, a.stages);
-    return launch(h, name, [&] { umma::k_umma_gemm<EPI, true><<<grid, 384, smem, h->stream>>>(mA, mB[0], mB[1], a); });
+    a.dbg = h->umma_dbg;
+    int rc = launch(h, name, [&] { umma::k_umma_gemm<EPI, true><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a); });
+    if (rc == CTR_OK && h->umma_dbg) {
+        std::vector<unsigned long long> t(8192);
+        cudaStreamSynchronize(h->stream);
+        cudaMemcpy(t.data(), h->umma_dbg, 8192 * 8, cudaMemcpyDeviceToHost);
+        cudaMemset(h->umma_dbg, 0, 8192 * 8);
+        FILE* f = fopen("gpurun_out/umma_timeline.txt", "a");
+        if (f) {
+            unsigned long long t0 = t[0];
+            fprintf(f, "# %s M=%d N=%d K=%d bn=%d stages=%d\n", name, a.M, a.N, a.K, a.bn, a.stages);
+            for (int it = 0; it < 40 && t[it * 8]; it++)
+                fprintf(f, "it %d tma_issue %llu conv_saw_full %llu conv_done %llu mma_saw %llu mma_issued %llu\n", it, t[it * 8] - t0, t[it * 8 + 1] - t0, t[it * 8 + 2] - t0, t[it * 8 + 3] - t0, t[it * 8 + 4] - t0);
+            for (int tc = 0; tc < 5 && t[4096 + tc * 4]; tc++) fprintf(f, "tile %d epi_start %llu epi_done %llu\n", tc, t[4096 + tc * 4] - t0, t[4096 + tc * 4 + 1] - t0);
+            fclose(f);
+        }
+    }
+    return rc;
 }
 
 bool use_umma(const ctr_handle* h) {

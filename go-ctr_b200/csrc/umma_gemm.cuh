@@ -10,14 +10,14 @@
 // HBM exactly once) is split inside the kernel by two converter warps, tile by tile in shared
 // memory — the operation is elementwise, so it is oblivious to the 128-byte swizzle TMA applied.
 //
-// One persistent CTA per SM, 12 warps, warp-specialised:
+// One persistent CTA per SM, 14 warps, warp-specialised:
 //   warp 0   TMA producer: cp.async.bulk.tensor 2D, SWIZZLE_128B, {32 fp32 x 128 rows} A boxes and
 //            {32 x BLOCK_N} B_hi/B_lo boxes into a STAGES-deep smem ring (mbarrier complete_tx)
 //   warp 1   MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BLOCK_N,
 //            K=8 per instruction; 4 k-steps x 3 products per 32-wide k-block; tcgen05.commit frees
 //            the smem stage and, after the last k-block, publishes the TMEM accumulator
-//   warps 2-3 converters (warp 2 also owns tcgen05.alloc/dealloc)
-//   warps 4-11 epilogue: tcgen05.ld 32x32b.x16 (TMEM lane = tile row; warp w reads lane quadrant
+//   warps 2-5 converters (warp 2 also owns tcgen05.alloc/dealloc)
+//   warps 6-13 epilogue: tcgen05.ld 32x32b.x16 (TMEM lane = tile row; warp w reads lane quadrant
 //            w%4, the two warps of a quadrant take alternate 16-column chunks), next chunk's TMEM
 //            load in flight while the current one is transformed; fused sigmoid+dropout / dsigmoid /
 //            plain store, 64-byte row segments to global
@@ -42,7 +42,11 @@ struct Args {
     const float* H; long ldh;   // UEPI_DSIGMOID: stored post-dropout activation
     float drop_p; uint32_t seed, stream;
     int stages;
+    unsigned long long* dbg;    // optional timeline of CTA 0 (globaltimer ns): [it*8 + event], tiles at [4096 + t*4 + e]
 };
+
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define UDBG(idx) do { if (a.dbg && blockIdx.x == 0 && (idx) < 8192) a.dbg[(idx)] = gtimer(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -124,7 +128,7 @@ __device__ __forceinline__ size_t stage_bytes(int bn, bool split3) {
 }
 
 template <int EPI, bool SPLIT3>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(448, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
             const __grid_constant__ CUtensorMap tmBlo, Args a) {
     extern __shared__ uint8_t smem_raw[];
@@ -149,7 +153,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t ncols = 2u * acc_stride;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; s++) { mbar_init(full(s), 1); mbar_init(conv(s), 64); mbar_init(empty(s), 1); }
+        for (int s = 0; s < stages; s++) { mbar_init(full(s), 1); mbar_init(conv(s), 128); mbar_init(empty(s), 1); }
         for (int i = 0; i < 2; i++) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 256); }
         fence_barrier_init();
     }
@@ -171,6 +175,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
                     mbar_wait(empty(s), ph ^ 1u);
                     mbar_expect_tx(full(s), (uint32_t)kABytes + bBytes * (SPLIT3 ? 2u : 1u));
+                    UDBG(it * 8 + 0);
                     tma_load_2d(sA(s), &tmA, full(s), kb * kBlockK, tile * kBlockM);
                     tma_load_2d(sBhi(s), &tmBhi, full(s), kb * kBlockK, 0);
                     if (SPLIT3) tma_load_2d(sBlo(s), &tmBlo, full(s), kb * kBlockK, 0);
@@ -189,6 +194,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int kb = 0; kb < num_k; kb++, it++) {
                     const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
                     mbar_wait(SPLIT3 ? conv(s) : full(s), ph);
+                    UDBG(it * 8 + 3);
                     tc_fence_after();
                     const uint64_t dAhi = desc_k_sw128(sA(s)), dBhi = desc_k_sw128(sBhi(s));
                     const uint64_t dAlo = SPLIT3 ? desc_k_sw128(sAlo(s)) : 0, dBlo = SPLIT3 ? desc_k_sw128(sBlo(s)) : 0;
@@ -202,39 +208,45 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                     umma_commit(empty(s));                          // smem stage reusable once these MMAs retire
+                    UDBG(it * 8 + 4);
                 }
                 umma_commit(tfull(acc));                            // accumulator complete
             }
         }
-    } else if (warp < 4) {
-        if (SPLIT3) {                                               // ---------------- converters (64 threads)
+    } else if (warp < 6) {
+        if (SPLIT3) {                                               // ---------------- converters (warps 2..5, 128 threads)
             const int c = threadIdx.x - 64;
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < num_k; kb++, it++) {
                     const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
                     mbar_wait(full(s), ph);
+                    if (c == 0) UDBG(it * 8 + 1);
                     const uint32_t pa = sA(s), pl = sAlo(s);
-#pragma unroll 4
-                    for (int i = c; i < kABytes / 16; i += 64) {
-                        float4 x;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(pa + 16u * i));
+                    float4 x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++)                     // 8 x 128 threads x 16 B = the 16 KB tile; all loads first
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                                     : "r"(pa + 16u * (c + 128 * i)));
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
                         float4 h, l;
-                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
-                        h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
-                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
-                        h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pa + 16u * i), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pl + 16u * i), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                        h.x = __uint_as_float(__float_as_uint(x[i].x) & 0xFFFFE000u); l.x = x[i].x - h.x;
+                        h.y = __uint_as_float(__float_as_uint(x[i].y) & 0xFFFFE000u); l.y = x[i].y - h.y;
+                        h.z = __uint_as_float(__float_as_uint(x[i].z) & 0xFFFFE000u); l.z = x[i].z - h.z;
+                        h.w = __uint_as_float(__float_as_uint(x[i].w) & 0xFFFFE000u); l.w = x[i].w - h.w;
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pa + 16u * (c + 128 * i)), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pl + 16u * (c + 128 * i)), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
                     }
                     fence_proxy_async();                            // generic-proxy writes → visible to tcgen05.mma
                     mbar_arrive(conv(s));
+                    if (c == 0) UDBG(it * 8 + 2);
                 }
             }
         }
-    } else {                                                        // ---------------- epilogue (warps 4..11)
+    } else {                                                        // ---------------- epilogue (warps 6..13)
         const int q = warp & 3;                                     // TMEM lane quadrant this warp may read
-        const int half = (warp - 4) >> 2;                           // which alternate 16-column chunks
+        const int half = (warp - 6) >> 2;                           // which alternate 16-column chunks
         const int row_in_tile = q * 32 + lane;
         const float inv_keep = a.drop_p > 0.0f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
         const float keep_thr = 1.0f - a.drop_p;
@@ -243,51 +255,73 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
             const int acc = tcount & 1; const uint32_t aph = (tcount >> 1) & 1u;
             mbar_wait(tfull(acc), aph);
+            if (threadIdx.x == 192) UDBG(4096 + tcount * 4 + 0);
             tc_fence_after();
             const long gm = (long)tile * kBlockM + row_in_tile;
             const uint32_t trow = tmem_base + (uint32_t)(acc * acc_stride) + ((uint32_t)(q * 32) << 16);
             const uint32_t ctr0 = (uint32_t)((uint64_t)gm * (uint64_t)a.N);
-            uint32_t rb[2][16];
-            int ci = half;
-            if (ci < nchunks) tmem_ld16_async(trow + (uint32_t)(ci * 16), rb[0]);
-            int cur = 0;
-            for (; ci < nchunks; ci += 2, cur ^= 1) {
-                tmem_ld_wait();
-                if (ci + 2 < nchunks) tmem_ld16_async(trow + (uint32_t)((ci + 2) * 16), rb[cur ^ 1]);   // in flight during the math below
+            // one 16-column chunk: registers → fused epilogue → 64 contiguous bytes of this thread's row.
+            // Straight-line and branch-free so the 16 elements overlap in the pipes.
+            auto process = [&](const uint32_t (&r)[16], int ci) {
                 const int c0 = ci * 16;
-                if (gm < a.M && c0 < a.Nz) {
-                    float v[16];
-                    float* crow = a.C + gm * a.ldc + c0;
-                    float hsrc[16];
-                    if (EPI == UEPI_DSIGMOID) {
+                if (gm >= a.M || c0 >= a.Nz) return;
+                float v[16];
+                float* crow = a.C + gm * a.ldc + c0;
+                if (EPI == UEPI_DSIGMOID) {
+                    float hs[16];
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 t = (c0 + j < a.Nz) ? ldg4(a.H + gm * a.ldh + c0 + j) : zero4();
-                            hsrc[j] = t.x; hsrc[j + 1] = t.y; hsrc[j + 2] = t.z; hsrc[j + 3] = t.w;
-                        }
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 t = (c0 + j < a.Nz) ? ldg4(a.H + gm * a.ldh + c0 + j) : zero4();
+                        hs[j] = t.x; hs[j + 1] = t.y; hs[j + 2] = t.z; hs[j + 3] = t.w;
                     }
+                    const float kp = a.drop_p > 0.0f ? 1.0f - a.drop_p : 1.0f;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {                  // keep*h*(1-h) with h = hd*(1-p); hd == 0 → 0
+                        const float hh = hs[j] * kp;
+                        v[j] = __uint_as_float(r[j]) * (inv_keep * hh * (1.0f - hh));
+                    }
+                } else if (EPI == UEPI_SIGMOID_DROP) {
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
-                        const int gn = c0 + j;
-                        float x = __uint_as_float(rb[cur][j]);
-                        if (gn >= a.N) x = 0.0f;
-                        else if (EPI == UEPI_SIGMOID_DROP) {
-                            x = sigmoid32(x);
-                            if (a.drop_p > 0.0f)
-                                x *= uniform24(a.seed, a.stream, ctr0 + (uint32_t)gn) < keep_thr ? inv_keep : 0.0f;
-                        } else if (EPI == UEPI_DSIGMOID) {
-                            x *= dsigmoid_drop(hsrc[j], a.drop_p);
-                        }
-                        v[j] = x;
+                        const float x = __uint_as_float(r[j]);
+                        float sg = __fdividef(1.0f, 1.0f + __expf(-x));   // x < -88 → exp = inf → 0
+                        sg = x > 15.0f ? 1.0f : sg;
+                        sg = x < -88.0f ? 0.0f : sg;
+                        v[j] = sg;
                     }
-                    const int nvalid = min(16, a.Nz - c0);          // Nz and ldc are multiples of 4
+                    if (a.drop_p > 0.0f) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        if (j < nvalid) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 16; j++)
+                            v[j] *= uniform24(a.seed, a.stream, ctr0 + (uint32_t)(c0 + j)) < keep_thr ? inv_keep : 0.0f;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]);
                 }
+#pragma unroll
+                for (int j = 0; j < 16; j++) v[j] = (c0 + j < a.N) ? v[j] : 0.0f;
+                const int nvalid = min(16, a.Nz - c0);              // Nz and ldc are multiples of 4
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    if (j < nvalid) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            };
+            uint32_t ra[16], rb[16];                                // ping-pong, statically indexed (registers)
+            int ci = half;
+            if (ci < nchunks) tmem_ld16_async(trow + (uint32_t)(ci * 16), ra);
+            while (ci < nchunks) {
+                tmem_ld_wait();
+                if (ci + 2 < nchunks) tmem_ld16_async(trow + (uint32_t)((ci + 2) * 16), rb);    // in flight during the math below
+                process(ra, ci);
+                ci += 2;
+                if (ci >= nchunks) break;
+                tmem_ld_wait();
+                if (ci + 2 < nchunks) tmem_ld16_async(trow + (uint32_t)((ci + 2) * 16), ra);
+                process(rb, ci);
+                ci += 2;
             }
             tc_fence_before();
             mbar_arrive(tempty(acc));
+            if (threadIdx.x == 192) UDBG(4096 + tcount * 4 + 1);
         }
     }
     tc_fence_before();
