@@ -83,6 +83,8 @@ struct ctr_handle {
         float *Wt0[2] = {}, *Wt1[2] = {}, *W1s[2] = {}, *W0s[2] = {};     // [hi, lo]
         CUtensorMap mA_X0, mA_H0d, mA_dZ1, mA_dZ0;
         CUtensorMap mB_Wt0[2], mB_Wt1[2], mB_W1s[2], mB_W0s[2];
+        CUtensorMap mK_X0, mK_H0d, mK_dZ0, mK_dZ1;      // {32 x 32} boxes over [batch, width] for the weight-gradient GEMMs
+        int dw_stages0 = 0, dw_stages1 = 0;
     } um;
 
     unsigned long long* umma_dbg = nullptr;     // CTR_UMMA_TIMELINE=1: timeline buffer of the last umma launch
@@ -212,7 +214,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(ctr_handle* h, CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_map(ctr_handle* h, CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         cudaDriverEntryPointQueryResult q;
@@ -226,7 +229,7 @@ int make_map(ctr_handle* h, CUtensorMap* m, const float* base, uint64_t rows, ui
     cuuint32_t box[2] = {(cuuint32_t)umma::kBlockK, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(h, CTR_ECUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
     return CTR_OK;
 }
@@ -263,6 +266,14 @@ int umma_init(ctr_handle* h) {
     RET(make_map(h, &u.mA_H0d, h->H0d, h->Bmax, h->H0p, h->H0p, umma::kBlockM));
     RET(make_map(h, &u.mA_dZ1, h->dZ1, h->Bmax, h->H1p, h->H1p, umma::kBlockM));
     RET(make_map(h, &u.mA_dZ0, h->dZ0, h->Bmax, h->H0p, h->H0p, umma::kBlockM));
+    // weight-gradient operands: rows limited to the training batch so that TMA zero-fills the K tail
+    RET(make_map(h, &u.mK_X0, h->X0, c.batch, h->Kp, h->Kp, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    RET(make_map(h, &u.mK_H0d, h->H0d, c.batch, h->H0p, h->H0p, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    RET(make_map(h, &u.mK_dZ0, h->dZ0, c.batch, h->H0p, h->H0p, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    RET(make_map(h, &u.mK_dZ1, h->dZ1, c.batch, h->H1p, h->H1p, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    u.dw_stages0 = (int)std::min<size_t>(4, ((size_t)227 * 1024 - 2048) / ((size_t)8 * 4096 + (size_t)(h->H0p / 32) * 4096));
+    u.dw_stages1 = (int)std::min<size_t>(4, ((size_t)227 * 1024 - 2048) / ((size_t)8 * 4096 + (size_t)(h->H1p / 32) * 4096));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const size_t smax = (size_t)227 * 1024;
     CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
     CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
@@ -309,6 +320,19 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
         }
     }
     return rc;
+}
+
+int umma_dw(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtensorMap& mB, umma::DwArgs a) {
+    const int total_kb = (a.K + 31) / 32;
+    const int grid = std::max(1, std::min(total_kb, h->num_sms));
+    const size_t smem = (size_t)a.stages * ((size_t)8 * 4096 + (size_t)a.nb * 4096) + 8 * (3 * a.stages + 2) + 16 + 1024;
+    return launch(h, name, [&] { umma::k_umma_dw<<<grid, 448, smem, h->stream>>>(mA, mB, a); });
+}
+
+// the weight-gradient GEMMs run on tcgen05 when the padded widths fit 8 column blocks and the batch
+// is the configured training batch (the TMA maps zero-fill rows beyond it)
+bool use_umma_dw(const ctr_handle* h, int B) {
+    return B == h->cfg.batch && h->Kp <= 256 && h->H0p <= 256 && h->H1p <= 256 && !getenv("CTR_DW_FP32");
 }
 
 bool use_umma(const ctr_handle* h) {
@@ -418,7 +442,12 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
     }
     if (!bwd) return CTR_OK;
 
-    {   // dW1 += h0dᵀ · dZ1
+    const bool umdw = um && use_umma_dw(h, B);
+    if (umdw) {   // dW1 += h0dᵀ · dZ1   (tcgen05, MN-major operands, split-K over the grid)
+        umma::DwArgs a{}; a.K = B; a.na = h->H0p / 32; a.nb = h->H1p / 32; a.M = c.H0; a.N = h->H1p; a.C = h->G[1]; a.ldc = h->H1p;
+        a.stages = h->um.dw_stages1;
+        RET(umma_dw(h, "umma_dW1_splitk", h->um.mK_H0d, h->um.mK_dZ1, a));
+    } else {   // dW1 += h0dᵀ · dZ1
         GemmArgs g{}; g.A = h->H0d; g.lda = h->H0p; g.B = h->dZ1; g.ldb = h->H1p; g.C = h->G[1]; g.ldc = h->H1p;
         g.M = c.H0; g.N = c.H1; g.K = B;
         RET(gemm_dw(h, "sgemm_dW1_splitk", g));
@@ -432,7 +461,11 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         g.M = B; g.N = c.H0; g.K = c.H1; g.Nz = h->H0p; g.H = h->H0d; g.ldh = h->H0p; g.drop_p = d0;
         RET((gemm_big<false, true, EPI_DSIGMOID>(h, "sgemm_dZ0_dsigmoid", g)));
     }
-    {   // dW0 += x0ᵀ · dZ0
+    if (umdw) {   // dW0 += x0ᵀ · dZ0
+        umma::DwArgs a{}; a.K = B; a.na = h->Kp / 32; a.nb = h->H0p / 32; a.M = h->in; a.N = h->H0p; a.C = h->G[0]; a.ldc = h->H0p;
+        a.stages = h->um.dw_stages0;
+        RET(umma_dw(h, "umma_dW0_splitk", h->um.mK_X0, h->um.mK_dZ0, a));
+    } else {   // dW0 += x0ᵀ · dZ0
         GemmArgs g{}; g.A = h->X0; g.lda = h->Kp; g.B = h->dZ0; g.ldb = h->H0p; g.C = h->G[0]; g.ldc = h->H0p;
         g.M = h->in; g.N = c.H0; g.K = B;
         RET(gemm_dw(h, "sgemm_dW0_splitk", g));

@@ -344,5 +344,173 @@ k_split_weights(const float* __restrict__ W, long ld, int rows, int cols, int tr
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Weight-gradient GEMM: C[M,N] += Aᵀ·B with A [K, M] and B [K, N] row-major — the reduction runs over
+// the batch (K = samples), so both operands are MN-major for the tensor core (model.go:56: d cost /
+// d mlp0 = concatᵀ·dZ0, d cost/d mlp1 = h0ᵀ·dZ1).  Split-K over the persistent grid: every CTA
+// reduces its own slice of the batch into two TMEM accumulators (rows 0..127 and 128..255 of C, all N
+// columns) and adds them into C with red.global.add.v4.f32.
+//   MN-major TF32 operands exist only in the SWIZZLE_128B_BASE32B shared-memory layout (32-byte swizzle
+//   atoms inside 128-byte rows, pattern period 4 rows): TMA boxes are {32 fp32 along M/N, 32 samples}
+//   written with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B — one 4 KB column block each — i.e. the canonical
+//   layout ((8,n),(4,k)) with LBO = 4096 (next 32-wide column block) and SBO = 512 (next 4 samples);
+//   a k-step of 8 samples starts 1024 bytes further on.
+//   Converter warps round both operands to TF32 (round-to-nearest-even, in place) so that the single
+//   tf32 product per k-step is unbiased; the 2^-12 relative rounding noise averages out over the batch.
+// -------------------------------------------------------------------------------------------------
+struct DwArgs {
+    int K;                      // batch rows to reduce (rows >= K are zero-filled by TMA)
+    int na, nb;                 // 32-wide column blocks of A (<= 8) and B (<= 8)
+    int M, N;                   // valid rows / cols of C
+    float* C; long ldc;
+    int stages;
+    int dbg;                    // probe only: 1 = epilogue adds 1.0, 2 = K-major descriptors, 3 = swap LBO/SBO, 4 = no swizzle-atom K offset
+};
+
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(4096 >> 4) << 16;          // LBO: next column block along M/N
+    d |= (uint64_t)(512 >> 4) << 32;           // SBO: next group of 4 samples along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                    // SWIZZLE_128B_BASE32B
+    return d;
+}
+__device__ __forceinline__ uint32_t idesc_tf32_mn(int M, int N) {
+    return idesc_tf32(M, N) | (1u << 15) | (1u << 16);      // A and B MN-major
+}
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u = __float_as_uint(x);
+    u += 0xFFFu + ((u >> 13) & 1u);
+    return __uint_as_float(u & 0xFFFFE000u);
+}
+
+__global__ void __launch_bounds__(448, 1)
+k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DwArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int stages = a.stages;
+    const uint32_t aBytes = (uint32_t)a.na * 4096u, bBytes = (uint32_t)a.nb * 4096u;
+    const uint32_t stBytes = 8u * 4096u + bBytes;                    // A always reserves 8 blocks (two M halves)
+    auto sA = [&](int s) { return base + (uint32_t)s * stBytes; };
+    auto sB = [&](int s) { return sA(s) + 8u * 4096u; };
+    const uint32_t bars = base + (uint32_t)stages * stBytes;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto conv = [&](int s) { return bars + 8u * (stages + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * stages + s); };
+    const uint32_t tdone = bars + 8u * (3 * stages);
+    const uint32_t tmem_slot = tdone + 8u;
+    const int bn = a.nb * 32;
+    const uint32_t ncols = 512;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++) { mbar_init(full(s), 1); mbar_init(conv(s), 128); mbar_init(empty(s), 1); }
+        mbar_init(tdone, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // this CTA's slice of the batch, in 32-sample k-blocks
+    const int total_kb = (a.K + 31) / 32;
+    const int per = (total_kb + gridDim.x - 1) / gridDim.x;
+    const int kb0 = blockIdx.x * per, kb1 = min(total_kb, kb0 + per);
+    const int nkb = max(0, kb1 - kb0);
+    const bool two_halves = a.M > 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nkb; it++) {
+                const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_expect_tx(full(s), aBytes + bBytes);
+                const int row = (kb0 + it) * 32;
+                for (int j = 0; j < a.na; j++) tma_load_2d(sA(s) + 4096u * j, &tmA, full(s), 32 * j, row);
+                for (int j = 0; j < a.nb; j++) tma_load_2d(sB(s) + 4096u * j, &tmB, full(s), 32 * j, row);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = a.dbg == 2 ? idesc_tf32(kBlockM, bn) : idesc_tf32_mn(kBlockM, bn);
+            for (int it = 0; it < nkb; it++) {
+                const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
+                mbar_wait(conv(s), ph);
+                tc_fence_after();
+                uint64_t dA0 = desc_mn_sw128(sA(s)), dA1 = desc_mn_sw128(sA(s) + 4u * 4096u), dB = desc_mn_sw128(sB(s));
+                if (a.dbg == 2) { dA0 = desc_k_sw128(sA(s)); dA1 = desc_k_sw128(sA(s) + 4u * 4096u); dB = desc_k_sw128(sB(s)); }
+                if (a.dbg == 3) {   // LBO <-> SBO
+                    auto sw = [](uint64_t d) { return (d & ~((uint64_t)0x3FFF << 16) & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(4096 >> 4) << 32); };
+                    dA0 = sw(dA0); dA1 = sw(dA1); dB = sw(dB);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {                       // 8 samples per k-step = +1024 bytes = +64 in the address field
+                    const uint64_t ko = (uint64_t)(k * 64);
+                    umma_tf32(tmem_base, dA0 + ko, dB + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    if (two_halves) umma_tf32(tmem_base + 256u, dA1 + ko, dB + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty(s));
+            }
+            umma_commit(tdone);
+        }
+    } else if (warp < 6) {                                          // converters: TF32 round-to-nearest in place
+        const int c = threadIdx.x - 64;
+        const int n16 = (int)((aBytes + bBytes) / 16u);
+        for (int it = 0; it < nkb; it++) {
+            const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
+            mbar_wait(full(s), ph);
+            const uint32_t pa = sA(s), pb = sB(s);
+            const int na16 = (int)(aBytes / 16u);
+            for (int i0 = c; i0 < n16; i0 += 128 * 4) {
+                float4 x[4]; uint32_t ad[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + 128 * u;
+                    ad[u] = i < na16 ? pa + 16u * i : pb + 16u * (i - na16);
+                    if (i < n16) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "r"(ad[u]));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (i0 + 128 * u < n16)
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ad[u]), "f"(tf32_rn(x[u].x)), "f"(tf32_rn(x[u].y)),
+                                     "f"(tf32_rn(x[u].z)), "f"(tf32_rn(x[u].w)) : "memory");
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(conv(s));
+        }
+    } else {                                                        // epilogue warps 6..13: C += accumulators
+        if (nkb > 0) {
+            const int q = warp & 3, half = (warp - 6) >> 2;
+            mbar_wait(tdone, 0);
+            tc_fence_after();
+            const int nchunks = bn / 16;
+            for (int h = 0; h < (two_halves ? 2 : 1); h++) {
+                const int m = h * 128 + q * 32 + lane;
+                const uint32_t trow = tmem_base + (uint32_t)(h * 256) + ((uint32_t)(q * 32) << 16);
+                for (int ci = half; ci < nchunks; ci += 2) {
+                    uint32_t r[16];
+                    tmem_ld16_async(trow + (uint32_t)(ci * 16), r);
+                    tmem_ld_wait();
+                    if (m < a.M) {
+                        float* crow = a.C + (long)m * a.ldc + ci * 16;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            if (ci * 16 + j < a.N)                  // N is a multiple of 4 on the padded grad storage
+                                red_add4(crow + j, a.dbg == 1 ? make_float4(1.f, 1.f, 1.f, 1.f) : make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, ncols);
+}
+
 }  // namespace umma
 }  // namespace ctr

@@ -12,6 +12,8 @@
 package ctrb200
 
 /*
+#cgo CFLAGS:  -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../go-ctr_b200 -lctr_b200 -Wl,-rpath,${SRCDIR}/../../go-ctr_b200
 #include <stdlib.h>
 #include "ctr_b200.h"
 */
