@@ -79,20 +79,26 @@ __device__ __forceinline__ float gate_cos(float dot, float nx2, float ny, float 
 // segment); a warp therefore carries 32/LPR rows per instruction group and the scalar gate math is
 // amortised over them.
 // -------------------------------------------------------------------------------------------------
-template <int LPR, int VPL, int UNR>
-__global__ void __launch_bounds__(256)
-k_attn_fwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
+// MODEL is a template parameter (no per-row branches); NT threads per block with at least MINB blocks
+// per SM: the micro-benchmark (tests/cuda/gather_probe.cu) shows occupancy, not software pipelining,
+// is what hides the gate's MUFU/shuffle latency — 32 warps/SM at <= 64 registers reach ~5.9 TB/s.
+template <int LPR, int VPL, int UNR, int MODEL, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_attn_fwd_vec(RowSrc r, Dims d, const float* __restrict__ att,
                float* __restrict__ X0, long ldx0, int Kp, int B) {
     extern __shared__ __align__(16) float smem[];
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int lir = lane % LPR, sub = lane / LPR;
-    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const int nwarps = gridDim.x * (NT / 32);
     float* row = smem + (long)wib * Kp;
     const float invS = 1.0f / (float)d.S;
     const bool use_hi = (!r.dense) && d.S <= 64;
+    // 128-bit copies of the dense per-sample features when every offset is 16-byte aligned
+    const bool feat4 = (!r.dense) && (d.uP % 4 == 0) && (d.D % 2 == 0) && (r.ldu % 4 == 0) && (r.ldi % 4 == 0);
+    const int nu4 = (d.uP + 3) / 4, nc4 = (d.cF + 3) / 4;
 
-    for (int b = blockIdx.x * (blockDim.x >> 5) + wib; b < B; b += nwarps) {
+    for (int b = blockIdx.x * (NT / 32) + wib; b < B; b += nwarps) {
         HistIdx hi; hi.load(r, d, b, lane);
         const float* ip = src_it(r, d, b);
         float4 v[VPL];
@@ -102,9 +108,15 @@ k_attn_fwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
         // dense per-sample features: issued before the row loop so they overlap it
         const float* pu = src_up(r, b);
         const float* pc = src_cx(r, b);
-        for (int j = lane; j < d.uP; j += 32) row[j] = pu ? __ldg(pu + j) : 0.0f;
-        for (int j = lane; j < d.cF; j += 32) row[d.uP + 2 * d.D + j] = pc ? __ldg(pc + j) : 0.0f;
-        for (int j = d.in + lane; j < Kp; j += 32) row[j] = 0.0f;
+        if (feat4) {            // table rows are zero-padded to a multiple of 4 floats (ctr_table_upload)
+            for (int j = lane; j < nu4; j += 32) *reinterpret_cast<float4*>(row + 4 * j) = pu ? ldg4(pu + 4 * j) : zero4();
+            for (int j = lane; j < nc4; j += 32) *reinterpret_cast<float4*>(row + d.uP + 2 * d.D + 4 * j) = pc ? ldg4(pc + 4 * j) : zero4();
+            for (int j = d.uP + 2 * d.D + 4 * nc4 + lane; j < Kp; j += 32) row[j] = 0.0f;
+        } else {
+            for (int j = lane; j < d.uP; j += 32) row[j] = pu ? __ldg(pu + j) : 0.0f;
+            for (int j = lane; j < d.cF; j += 32) row[d.uP + 2 * d.D + j] = pc ? __ldg(pc + j) : 0.0f;
+            for (int j = d.in + lane; j < Kp; j += 32) row[j] = 0.0f;
+        }
         const float ny = fsqrt_pos(group_sum<LPR>(ny2));
         float4 acc[VPL];
 #pragma unroll
@@ -121,14 +133,14 @@ k_attn_fwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
             for (int j = 0; j < UNR; j++) {
                 const int s = s0 + j * RPW + sub;
                 float a = 1.0f;
-                if (model == MODEL_DIN_COS) {
+                if (MODEL == MODEL_DIN_COS) {
                     float dot = 0.0f, nx2 = 0.0f;
 #pragma unroll
                     for (int q = 0; q < VPL; q++) { dot += dot4(u[j][q], v[q]); nx2 += dot4(u[j][q], u[j][q]); }
                     dot = group_sum<LPR>(dot); nx2 = group_sum<LPR>(nx2);
                     const float cs = dot * frcp(fsqrt_pos(nx2) * ny + 1e-8f);
                     a = sigmoid_fast((cs + 1.0f) * 0.5f * (s < d.S ? __ldg(att + s) : 0.0f));
-                } else if (model == MODEL_DIN_EUC) {
+                } else if (MODEL == MODEL_DIN_EUC) {
                     float d2 = 0.0f;
 #pragma unroll
                     for (int q = 0; q < VPL; q++) {
@@ -250,34 +262,31 @@ struct BwdOut {
     float* dIt;         // [B,D]   or null
     int    sgd;         // fused scatter-add + SGD into r.emb
     float  neg_lr;      // -table_lr
-    float* hot_acc;     // [hot_reps, hot_rows, D] replica accumulators (unscaled gradient sums)
+    float* hot_acc;     // [hot_reps, hot_rows, D] replica accumulators (sums of -lr * gradient)
     int    hot_rows, hot_reps;
 };
 
-__device__ __forceinline__ void scatter_row(const RowSrc& r, const Dims& d, const BwdOut& o, int idx, int rep,
-                                            int col, float4 g) {
-    if (idx < o.hot_rows) {
-        red_add4(o.hot_acc + ((long)rep * o.hot_rows + idx) * d.D + col, g);
-    } else {
-        red_add4(const_cast<float*>(r.emb) + (long)idx * r.lde + col,
-                 make_float4(o.neg_lr * g.x, o.neg_lr * g.y, o.neg_lr * g.z, o.neg_lr * g.w));
-    }
+// destination of one row's (already -lr scaled) gradient: a hot-row replica accumulator or the table row
+__device__ __forceinline__ float* scatter_dst(const RowSrc& r, const Dims& d, const BwdOut& o, int idx, int rep) {
+    return idx < o.hot_rows ? o.hot_acc + ((long)rep * o.hot_rows + idx) * d.D
+                            : const_cast<float*>(r.emb) + (long)idx * r.lde;
 }
 
-template <int LPR, int VPL, int UNR>
-__global__ void __launch_bounds__(256)
-k_attn_bwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
+template <int LPR, int VPL, int UNR, int MODEL, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_attn_bwd_vec(RowSrc r, Dims d, const float* __restrict__ att,
                const float* __restrict__ dX, long lddx, BwdOut o, int B) {
     extern __shared__ __align__(16) float smem[];     // datt partials [S]
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int lir = lane % LPR, sub = lane / LPR;
-    const int gwarp = blockIdx.x * (blockDim.x >> 5) + wib;
-    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const int gwarp = blockIdx.x * (NT / 32) + wib;
+    const int nwarps = gridDim.x * (NT / 32);
     const int rep = o.hot_reps > 0 ? gwarp % o.hot_reps : 0;
     const float invS = 1.0f / (float)d.S;
+    const float sc = o.sgd ? o.neg_lr : 1.0f;         // fused SGD: gradients leave pre-scaled by -lr
     const bool use_hi = (!r.dense) && d.S <= 64;
-    for (int j = threadIdx.x; j < d.S; j += blockDim.x) smem[j] = 0.0f;
+    for (int j = threadIdx.x; j < d.S; j += NT) smem[j] = 0.0f;
     __syncthreads();
 
     for (int b = gwarp; b < B; b += nwarps) {
@@ -295,7 +304,7 @@ k_attn_bwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
         ny2 = group_sum<LPR>(ny2);
         const float ny = fsqrt_pos(ny2);
         const float rny = ny2 > 0.0f ? rsqrtf(ny2) : 0.0f;
-        float kvsum = 0.0f;                               // coefficient of -v in dv (cosine)
+        float kvsum = 0.0f;                               // coefficient of -v in dv
         for (int s0 = 0; s0 < d.S; s0 += UNR * RPW) {
             float4 u[UNR][VPL]; int idx[UNR]; bool have[UNR];
 #pragma unroll
@@ -308,22 +317,22 @@ k_attn_bwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
 #pragma unroll
             for (int j = 0; j < UNR; j++) {
                 const int s = s0 + j * RPW + sub;
-                // du = c1*g + c2*v + c3*u ; dv += c4*u (+ c5*v accumulated as a scalar)
+                // du = c1*g + c2*v + c3*u ; dv += c4*u - (kv coefficient)*v
                 float c1 = invS, c2 = 0.0f, c3 = 0.0f, c4 = 0.0f;
-                if (model != MODEL_YOUTUBE) {
+                if (MODEL != MODEL_YOUTUBE) {
                     const float att_s = s < d.S ? __ldg(att + s) : 0.0f;
                     float gu = 0.0f, dot = 0.0f, nx2 = 0.0f;
 #pragma unroll
                     for (int q = 0; q < VPL; q++) {
                         gu += dot4(g[q], u[j][q]);
-                        if (model == MODEL_DIN_COS) { dot += dot4(u[j][q], v[q]); nx2 += dot4(u[j][q], u[j][q]); }
+                        if (MODEL == MODEL_DIN_COS) { dot += dot4(u[j][q], v[q]); nx2 += dot4(u[j][q], u[j][q]); }
                         else {
                             const float4 e = make_float4(u[j][q].x - v[q].x, u[j][q].y - v[q].y, u[j][q].z - v[q].z, u[j][q].w - v[q].w);
                             nx2 += dot4(e, e);
                         }
                     }
                     gu = group_sum<LPR>(gu); nx2 = group_sum<LPR>(nx2);
-                    if (model == MODEL_DIN_COS) {
+                    if (MODEL == MODEL_DIN_COS) {
                         dot = group_sum<LPR>(dot);
                         const float nx = fsqrt_pos(nx2);
                         const float iden = frcp(nx * ny + 1e-8f);
@@ -349,15 +358,17 @@ k_attn_bwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
                     }
                 }
                 if (s < d.S) {
+                    const float e1 = c1 * sc, e2 = c2 * sc, e3 = c3 * sc;
+                    float* dst = (o.sgd && have[j]) ? scatter_dst(r, d, o, idx[j], rep) : nullptr;
 #pragma unroll
                     for (int q = 0; q < VPL; q++) {
                         const float4 uu = u[j][q];
                         float4 du;
-                        du.x = fmaf(c3, uu.x, fmaf(c2, v[q].x, c1 * g[q].x)); du.y = fmaf(c3, uu.y, fmaf(c2, v[q].y, c1 * g[q].y));
-                        du.z = fmaf(c3, uu.z, fmaf(c2, v[q].z, c1 * g[q].z)); du.w = fmaf(c3, uu.w, fmaf(c2, v[q].w, c1 * g[q].w));
+                        du.x = fmaf(e3, uu.x, fmaf(e2, v[q].x, e1 * g[q].x)); du.y = fmaf(e3, uu.y, fmaf(e2, v[q].y, e1 * g[q].y));
+                        du.z = fmaf(e3, uu.z, fmaf(e2, v[q].z, e1 * g[q].z)); du.w = fmaf(e3, uu.w, fmaf(e2, v[q].w, e1 * g[q].w));
                         dvu[q] = fma4(c4, uu, dvu[q]);
                         if (o.dUb) *reinterpret_cast<float4*>(o.dUb + ((long)b * d.S + s) * d.D + (q * LPR + lir) * 4) = du;
-                        if (o.sgd && have[j]) scatter_row(r, d, o, idx[j], rep, (q * LPR + lir) * 4, du);
+                        if (dst) red_add4(dst + (q * LPR + lir) * 4, du);
                     }
                 }
             }
@@ -376,25 +387,26 @@ k_attn_bwd_vec(RowSrc r, Dims d, int model, const float* __restrict__ att,
             }
         }
         if (sub == 0) {
-            const int irow = (o.sgd && ip) ? r.item_row[b] : -1;
+            float* dst = (o.sgd && ip) ? scatter_dst(r, d, o, r.item_row[b], rep) : nullptr;
 #pragma unroll
             for (int q = 0; q < VPL; q++) {
                 const float4 gi = ldg4(dX + (long)b * lddx + d.D + (q * LPR + lir) * 4);
                 float4 dv;
-                dv.x = gi.x + dvu[q].x - kvsum * v[q].x; dv.y = gi.y + dvu[q].y - kvsum * v[q].y;
-                dv.z = gi.z + dvu[q].z - kvsum * v[q].z; dv.w = gi.w + dvu[q].w - kvsum * v[q].w;
+                dv.x = (gi.x + dvu[q].x - kvsum * v[q].x) * sc; dv.y = (gi.y + dvu[q].y - kvsum * v[q].y) * sc;
+                dv.z = (gi.z + dvu[q].z - kvsum * v[q].z) * sc; dv.w = (gi.w + dvu[q].w - kvsum * v[q].w) * sc;
                 if (o.dIt) *reinterpret_cast<float4*>(o.dIt + (long)b * d.D + (q * LPR + lir) * 4) = dv;
-                if (irow >= 0) scatter_row(r, d, o, irow, rep, (q * LPR + lir) * 4, dv);
+                if (dst) red_add4(dst + (q * LPR + lir) * 4, dv);
             }
         }
     }
     __syncthreads();
-    if (model != MODEL_YOUTUBE && o.datt)
-        for (int j = threadIdx.x; j < d.S; j += blockDim.x)
+    if (MODEL != MODEL_YOUTUBE && o.datt)
+        for (int j = threadIdx.x; j < d.S; j += NT)
             if (smem[j] != 0.0f) atomicAdd(o.datt + j, smem[j]);
 }
 
-// folds the hot-row replica accumulators into the table: row -= lr * sum_rep acc ; acc = 0
+// folds the hot-row replica accumulators into the table: row += scale * sum_rep acc ; acc = 0
+// (the accumulators already hold -lr * gradient, so scale = 1)
 __global__ void __launch_bounds__(256)
 k_hot_apply(float* __restrict__ emb, long lde, float* __restrict__ hot_acc, int hot_rows, int hot_reps,
             int D, float neg_lr) {

@@ -141,32 +141,45 @@ bool vec_ok(const ctr_handle* h, const RowSrc& r) {
     int D = h->cfg.D;
     if (D % 4) return false;
     int lpr = D / 4;
-    if (lpr > 32 || (lpr & (lpr - 1))) return false;      // D in {4,8,16,32,64,128}
+    if (lpr < 4 || lpr > 32 || (lpr & (lpr - 1))) return false;      // D in {16,32,64,128}; others use the generic kernels
     if (r.dense) return (r.ldx % 4 == 0) && (r.ub0 % 4 == 0) && (r.it0 % 4 == 0) && (((uintptr_t)r.X) % 16 == 0);
     return r.lde % 4 == 0;
 }
 
-// Lane mapping of the vector attention kernels for a row of D floats: LPR lanes x VPL float4 each.
-// Forward keeps 16 floats per lane when it can (8 rows per load-instruction group at D=64), backward
-// 8 (it also holds g, v and the item gradient); UNR groups are in flight before any arithmetic.
-template <int LPR, int VPL, int UNR>
-void launch_fwd_vec(ctr_handle* h, const RowSrc& r, int B) {
-    size_t smem = (size_t)8 * h->Kp * sizeof(float);
-    k_attn_fwd_vec<LPR, VPL, UNR><<<grid_for_warps(h, B), 256, smem, h->stream>>>(r, dims_of(h), h->cfg.model, h->W[3], h->X0, h->Kp, h->Kp, B);
+// Lane mapping of the vector attention kernels for a row of D floats: LPR lanes x VPL float4 each, one
+// load group in flight per warp, 128-thread blocks at >= 6-8 blocks/SM (tests/cuda/gather_probe.cu,
+// bwd_probe.cu: occupancy beats deeper per-warp unrolling on B200).
+int grid_attn(const ctr_handle* h, int B) {
+    int blocks = (B + 3) / 4;
+    return std::max(1, std::min(blocks, h->num_sms * 32));
 }
-template <int LPR, int VPL, int UNR>
+template <int LPR, int VPL, int MINB>
+void launch_fwd_vec(ctr_handle* h, const RowSrc& r, int B) {
+    size_t smem = (size_t)4 * h->Kp * sizeof(float);
+    const int g = grid_attn(h, B);
+    switch (h->cfg.model) {
+        case CTR_MODEL_YOUTUBE: k_attn_fwd_vec<LPR, VPL, 1, MODEL_YOUTUBE, 128, MINB><<<g, 128, smem, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
+        case CTR_MODEL_DIN_COS: k_attn_fwd_vec<LPR, VPL, 1, MODEL_DIN_COS, 128, MINB><<<g, 128, smem, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
+        default:                k_attn_fwd_vec<LPR, VPL, 1, MODEL_DIN_EUC, 128, MINB><<<g, 128, smem, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
+    }
+}
+template <int LPR, int VPL, int MINB>
 void launch_bwd_vec(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
     size_t smem = (size_t)std::max(h->cfg.S, 1) * sizeof(float);
-    k_attn_bwd_vec<LPR, VPL, UNR><<<grid_for_warps(h, B), 256, smem, h->stream>>>(r, dims_of(h), h->cfg.model, h->W[3], h->dX, h->lddx, o, B);
+    const int g = grid_attn(h, B);
+    switch (h->cfg.model) {
+        case CTR_MODEL_YOUTUBE: k_attn_bwd_vec<LPR, VPL, 1, MODEL_YOUTUBE, 128, MINB><<<g, 128, smem, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); break;
+        case CTR_MODEL_DIN_COS: k_attn_bwd_vec<LPR, VPL, 1, MODEL_DIN_COS, 128, MINB><<<g, 128, smem, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); break;
+        default:                k_attn_bwd_vec<LPR, VPL, 1, MODEL_DIN_EUC, 128, MINB><<<g, 128, smem, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); break;
+    }
 }
 
 int attn_forward(ctr_handle* h, const RowSrc& r, int B) {
     if (vec_ok(h, r)) {
         return launch(h, "attn_fwd_vec", [&] {
             switch (h->cfg.D / 4) {           // float4 per row
-                case 1: launch_fwd_vec<1, 1, 2>(h, r, B); break;   case 2: launch_fwd_vec<2, 1, 2>(h, r, B); break;
-                case 4: launch_fwd_vec<4, 1, 2>(h, r, B); break;   case 8: launch_fwd_vec<4, 2, 2>(h, r, B); break;
-                case 16: launch_fwd_vec<4, 4, 2>(h, r, B); break;  default: launch_fwd_vec<8, 4, 2>(h, r, B); break;
+                case 4: launch_fwd_vec<4, 1, 8>(h, r, B); break;    case 8: launch_fwd_vec<4, 2, 8>(h, r, B); break;
+                case 16: launch_fwd_vec<4, 4, 8>(h, r, B); break;   default: launch_fwd_vec<8, 4, 8>(h, r, B); break;
             }
         });
     }
@@ -179,9 +192,8 @@ int attn_backward(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
     if (vec_ok(h, r)) {
         return launch(h, "attn_bwd_vec", [&] {
             switch (h->cfg.D / 4) {
-                case 1: launch_bwd_vec<1, 1, 2>(h, r, o, B); break;   case 2: launch_bwd_vec<2, 1, 2>(h, r, o, B); break;
-                case 4: launch_bwd_vec<4, 1, 2>(h, r, o, B); break;   case 8: launch_bwd_vec<4, 2, 2>(h, r, o, B); break;
-                case 16: launch_bwd_vec<8, 2, 2>(h, r, o, B); break;  default: launch_bwd_vec<16, 2, 2>(h, r, o, B); break;
+                case 4: launch_bwd_vec<4, 1, 8>(h, r, o, B); break;    case 8: launch_bwd_vec<4, 2, 8>(h, r, o, B); break;
+                case 16: launch_bwd_vec<8, 2, 8>(h, r, o, B); break;   default: launch_bwd_vec<16, 2, 8>(h, r, o, B); break;
             }
         });
     }
@@ -492,7 +504,7 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         if (hot && h->hot_rows > 0)
             RET(launch(h, "hot_rows_apply", [&] {
                 k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(h->tab[CTR_TABLE_ITEM_EMB], h->tab_ld[CTR_TABLE_ITEM_EMB], h->hot_acc,
-                                                                h->hot_rows, h->hot_reps, c.D, -c.table_lr);
+                                                                h->hot_rows, h->hot_reps, c.D, 1.0f);
             }));
         if (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC) RET(deterministic_table_update(h, r, B));
     }
