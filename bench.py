@@ -272,32 +272,43 @@ def main():
         return dict(ms=ms, wall=wall, clocks=clocks, launches=launches, host=host, cost=cost, prof=eng.profile_dump() if profile else None)
 
     def e2e_leg(eng, w, B, steps, warmup):
-        """Same metric through the public host-buffer entry point: pinned host indices/labels are
-        copied H2D and the step's cost is read back D2H inside every timed call."""
+        """Same metric through the public host-buffer entry point ctr_train_idx (one model.Train pass over
+        `steps` batches held in pinned HOST memory): every batch's ids/labels are copied H2D inside the call
+        (overlapped with the previous batch's compute on a second stream) and every batch's cost is read
+        back D2H before the call returns.  Single-GPU; with sharded tables (world > 1) the per-batch entry
+        point ctr_train_step_idx is timed instead."""
         host = make_batches(w, B, 4, 200)
-        pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
-        st = g.StepStats()
-        for i in range(warmup):
-            ur, ir, hist, y = pinned[i % 4]
-            eng.train_step_idx_ptr(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B, st)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(steps):
-            ur, ir, hist, y = pinned[(warmup + i) % 4]
-            eng.train_step_idx_ptr(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B, st)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
+            pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
+            st = g.StepStats()
+            for i in range(warmup):
+                ur, ir, hist, y = pinned[i % 4]
+                eng.train_step_idx_ptr(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B, st)
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                ur, ir, hist, y = pinned[(warmup + i) % 4]
+                eng.train_step_idx_ptr(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B, st)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        h2d = sum(a.numel() * a.element_size() for a in pinned[0])
+            dt = float(t.item()); last = st.cost
+            h2d = sum(a.numel() * a.element_size() for a in pinned[0])
+        else:
+            cat = [torch.from_numpy(np.concatenate([host[i % 4][j] for i in range(steps)])).pin_memory() for j in range(4)]
+            costs = torch.empty(steps, dtype=torch.float32).pin_memory()
+            eng.train_idx_ptr(cat[0].data_ptr(), cat[1].data_ptr(), cat[2].data_ptr(), cat[3].data_ptr(), B * min(steps, max(warmup, 2)), costs.data_ptr())
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            eng.train_idx_ptr(cat[0].data_ptr(), cat[1].data_ptr(), cat[2].data_ptr(), cat[3].data_ptr(), B * steps, costs.data_ptr())
+            dt = time.perf_counter() - t0
+            last = float(costs[-1])
+            h2d = sum(a.numel() * a.element_size() for a in cat) // steps
         return dict(value=B * world * steps / dt, unit="samples/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=8,
-                    ms_per_step=1e3 * dt / steps, last_cost=st.cost)
+                    ms_per_step=1e3 * dt / steps, last_cost=last)
 
-    def roofline_of(w, leg, prof, B):
+    def roofline_of(w, leg, prof, B, workload_name=None):
         ur, ir, hist, y = leg["host"][0]
         gbytes, sbytes, rows = algorithmic_bytes(w, hist, ir)
         kern = {}
@@ -318,7 +329,7 @@ def main():
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(wname, {}).get(dom)
+            traffic = json.load(open(tp)).get(workload_name or wname, {}).get(dom)
         pair_ms = sum(kern[k]["ms_per_launch"] for k in cand)
         rl = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
               "frac": kern[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
@@ -335,7 +346,7 @@ def main():
     leg = timed_leg(eng, w, B, args.steps, args.warmup)
     prof_leg = timed_leg(eng, w, B, args.steps, 1, profile=True)
     rl, kern = roofline_of(w, prof_leg, prof_leg["prof"], B)
-    e2e = e2e_leg(eng, w, B, max(3, args.steps // 2), 2)
+    e2e = e2e_leg(eng, w, B, max(3, min(args.steps, 40)), 2)
     value = B * world * args.steps / (leg["ms"] * 1e-3)
     step_ms = sum(v["ms_per_launch"] * v["launches_per_step"] for v in kern.values())
     for v in kern.values():
@@ -360,7 +371,7 @@ def main():
         leg2 = timed_leg(eng2, w2, w2["B"], max(5, args.steps // 2), 3)
         p2 = timed_leg(eng2, w2, w2["B"], max(5, args.steps // 2), 1, profile=True)
         steps_saved = args.steps; args.steps = max(5, args.steps // 2)
-        rl2, kern2 = roofline_of(w2, p2, p2["prof"], w2["B"])
+        rl2, kern2 = roofline_of(w2, p2, p2["prof"], w2["B"], "din_100m_shard")
         args.steps = steps_saved
         line["hbm_roofline"] = {"workload": "din_100m_shard", "note": w2["note"], "items": w2["I"], "per_gpu_batch": w2["B"],
                                 "samples_per_sec": w2["B"] * max(5, steps_saved // 2) / (leg2["ms"] * 1e-3),

@@ -66,6 +66,11 @@ struct ctr_handle {
     float* hot_acc = nullptr; int hot_rows = 0, hot_reps = 0;
     // staging for host-pointer entry points
     int *s_user = nullptr, *s_item = nullptr, *s_hist = nullptr; float* s_label = nullptr;
+    // second staging set + copy stream for the pipelined epoch entry point (ctr_train_idx)
+    int *p_user = nullptr, *p_item = nullptr, *p_hist = nullptr; float* p_label = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    double* d_costs = nullptr; size_t d_costs_cap = 0;
     // dense-X residency
     float* dXd = nullptr; float* dYd = nullptr; size_t dXd_cap = 0, dYd_cap = 0;
 
@@ -685,6 +690,9 @@ void ctr_destroy(ctr_handle* h) {
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]); }
+    for (void* p : {(void*)h->p_user, (void*)h->p_item, (void*)h->p_hist, (void*)h->p_label, (void*)h->d_costs}) if (p) cudaFree(p);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -894,6 +902,51 @@ int ctr_train_step_idx(ctr_handle* h, const int32_t* user_row, const int32_t* it
     float cost = 0;
     RET(read_cost(h, B * std::max(1, h->comm.world > 1 ? 1 : 1), &cost));
     if (stats) { stats->cost = cost; stats->ms_device = 0; stats->launches = (int32_t)(h->launches - l0); stats->reserved = 0; }
+    return CTR_OK;
+}
+
+int ctr_train_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row, const int32_t* hist, const float* label,
+                  int64_t n, float* costs) {
+    if (!h || !user_row || !item_row || !hist || !label || n < 1) return set_err(h, CTR_EINVAL, "bad train arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    if (h->comm.world > 1) return set_err(h, CTR_ESTATE, "ctr_train_idx: sharded tables use ctr_train_step_idx per batch");
+    RET(check_tables(h));
+    const int B = h->cfg.batch, S = h->cfg.S;
+    const int64_t nb = (n + B - 1) / B;                      // model.go:96-99
+    if (!h->copy_stream) {
+        CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) { CU(h, cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)); CU(h, cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming)); }
+        RET(dalloc(h, &h->p_user, (size_t)h->Bmax)); RET(dalloc(h, &h->p_item, (size_t)h->Bmax));
+        RET(dalloc(h, &h->p_hist, (size_t)h->Bmax * S)); RET(dalloc(h, &h->p_label, (size_t)h->Bmax));
+    }
+    if (h->d_costs_cap < (size_t)nb) { if (h->d_costs) cudaFree(h->d_costs); h->d_costs = nullptr; RET(dalloc(h, &h->d_costs, (size_t)nb)); h->d_costs_cap = (size_t)nb; }
+    int* su[2] = {h->s_user, h->p_user}; int* si[2] = {h->s_item, h->p_item}; int* sh[2] = {h->s_hist, h->p_hist}; float* sl[2] = {h->s_label, h->p_label};
+    CU(h, cudaStreamSynchronize(h->stream));                 // staging set 0 may still be in use by an earlier call
+    for (int64_t b = 0; b < nb; b++) {
+        const int slot = (int)(b & 1);
+        const int64_t start = b * B; const int nv = (int)std::min<int64_t>(B, n - start);
+        // H2D of batch b on the copy stream, after the compute that last used this slot (batch b-2)
+        if (b >= 2) CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
+        CU(h, cudaMemcpyAsync(su[slot], user_row + start, sizeof(int) * (size_t)nv, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(h, cudaMemcpyAsync(si[slot], item_row + start, sizeof(int) * (size_t)nv, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(h, cudaMemcpyAsync(sh[slot], hist + start * S, sizeof(int) * (size_t)nv * S, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(h, cudaMemcpyAsync(sl[slot], label + start, sizeof(float) * (size_t)nv, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(h, cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+        // compute of batch b on the engine stream (overlaps the H2D of batch b+1)
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
+        RowSrc r = idx_src(h, su[slot], si[slot], sh[slot], B);
+        r.nvalid = nv;                                       // ragged tail → zero rows with label 0 (model.go:357-371)
+        StepOpts o; o.training = true; o.update = true; o.d_label = sl[slot];
+        RET(step_core(h, r, B, o));
+        CU(h, cudaMemcpyAsync(h->d_costs + b, h->d_cost, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CU(h, cudaEventRecord(h->ev_consumed[slot], h->stream));
+    }
+    std::vector<double> hc((size_t)nb);
+    CU(h, cudaMemcpyAsync(hc.data(), h->d_costs, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaStreamSynchronize(h->copy_stream));
+    if (costs) for (int64_t b = 0; b < nb; b++) costs[b] = -(float)(hc[(size_t)b] / (double)B);
     return CTR_OK;
 }
 

@@ -21,7 +21,7 @@ GEMM_AUTO, GEMM_FP32, GEMM_TCGEN05_3XTF32 = 0, 1, 2
 # every symbol include/ctr_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ["ctr_abi_version", "ctr_config_default", "ctr_create", "ctr_destroy", "ctr_last_error",
            "ctr_init_weights", "ctr_set_weights", "ctr_get_weights", "ctr_table_upload", "ctr_table_download", "ctr_table_fill",
-           "ctr_gather_rows", "ctr_train_dense", "ctr_predict_dense", "ctr_train_step_idx", "ctr_predict_idx",
+           "ctr_gather_rows", "ctr_train_dense", "ctr_predict_dense", "ctr_train_step_idx", "ctr_train_idx", "ctr_predict_idx",
            "ctr_train_step_idx_dev", "ctr_predict_idx_dev", "ctr_last_cost", "ctr_sync", "ctr_get_stream",
            "ctr_set_stream", "ctr_launch_count", "ctr_profile_enable", "ctr_profile_get", "ctr_profile_reset",
            "ctr_profile_dump", "ctr_debug_grads_idx", "ctr_roc_auc", "ctr_comm_unique_id", "ctr_comm_init"]
@@ -196,6 +196,19 @@ class Engine:
         """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous."""
         self._ck(self.L.ctr_train_step_idx_dev(self.h, C.c_void_p(d_user), C.c_void_p(d_item), C.c_void_p(d_hist),
                                                C.c_void_p(d_label), C.c_int32(B)))
+
+    def train_idx(self, user_row, item_row, hist, label):
+        """One pass over n samples in batches of cfg.batch (pipelined H2D); returns the batch costs."""
+        u, up = _i(user_row); it, ip = _i(item_row); hs, hp = _i(hist); y, yp = _f(label)
+        nb = (u.size + self.cfg.batch - 1) // self.cfg.batch
+        costs = np.empty(nb, np.float32)
+        self._ck(self.L.ctr_train_idx(self.h, up, ip, hp, yp, C.c_int64(u.size), costs.ctypes.data_as(_fp)))
+        return costs
+
+    def train_idx_ptr(self, up, ip, hp, yp, n, costs_ptr=None):
+        """Raw host pointers (pinned buffers owned by the caller)."""
+        self._ck(self.L.ctr_train_idx(self.h, C.c_void_p(up), C.c_void_p(ip), C.c_void_p(hp), C.c_void_p(yp), C.c_int64(n),
+                                      C.c_void_p(costs_ptr) if costs_ptr else None))
 
     def predict_idx(self, user_row, item_row, hist):
         u, up = _i(user_row); it, ip = _i(item_row); hs, hp = _i(hist)

@@ -125,6 +125,12 @@ int ctr_predict_dense(ctr_handle* h, const float* X, int64_t n, int32_t xcols,
  * B must equal cfg.batch.  Host buffers: copied H2D inside the call. */
 int ctr_train_step_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row,
                        const int32_t* hist_rows, const float* label, int32_t B, ctr_step_stats* stats);
+/* model.Train's batch loop for one pass over n samples (model.go:107-196) fed by row ids: batches of
+ * cfg.batch are consumed in order, the ragged tail is zero-padded with label 0 (model.go:357-371), and
+ * the host→device copy of batch i+1 overlaps the compute of batch i (second stream).  One coarse call
+ * per epoch is the shape a cgo caller wants.  costs (may be NULL) receives ceil(n/batch) batch costs. */
+int ctr_train_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row,
+                  const int32_t* hist_rows, const float* label, int64_t n, float* costs);
 /* recommend.BatchPredict → model.Predict (rcmd.go:277-337) fed by indices. out is [n]. */
 int ctr_predict_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row,
                     const int32_t* hist_rows, int64_t n, float* out);

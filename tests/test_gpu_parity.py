@@ -262,3 +262,28 @@ def test_full_size_properties_at_north_star_batch():
     assert scale > 0
     np.testing.assert_allclose(got, -100.0 * want, rtol=2e-2, atol=2e-2 * 100.0 * scale)
     assert abs(got.sum() + 100.0 * want.sum()) <= 2e-3 * 100.0 * np.abs(want).sum()
+
+
+def test_pipelined_epoch_entry_matches_per_batch_steps():
+    """ctr_train_idx (one pass over n samples, H2D of batch i+1 overlapping batch i, ragged tail zero-padded
+    with label 0) == the same batches through ctr_train_step_idx."""
+    B, nfull = 256, 3
+    engA, cfg, ocfg, W, (uf, itf, emb), _ = setup(g.MODEL_DIN_COS, "ref", B, seed=11)
+    engB, *_ = setup(g.MODEL_DIN_COS, "ref", B, seed=11)
+    rng = np.random.default_rng(5)
+    n = nfull * B + 100
+    ur, ir, hist, y = make_batch(rng, uf.shape[0], itf.shape[0], n, cfg.S)
+    costs = engA.train_idx(ur, ir, hist, y)
+    assert costs.shape == (nfull + 1,)
+    want = []
+    for b in range(nfull):
+        sl = slice(b * B, (b + 1) * B)
+        want.append(engB.train_step_idx(ur[sl], ir[sl], hist[sl], y[sl]).cost)
+    # tail: pad explicitly with missing rows (zeros) and label 0
+    pad = B - 100
+    urt = np.concatenate([ur[nfull * B:], np.full(pad, -1, np.int32)]); irt = np.concatenate([ir[nfull * B:], np.full(pad, -1, np.int32)])
+    ht = np.concatenate([hist[nfull * B:], np.full((pad, cfg.S), -1, np.int32)]); yt = np.concatenate([y[nfull * B:], np.zeros(pad, np.float32)])
+    want.append(engB.train_step_idx(urt, irt, ht, yt).cost)
+    np.testing.assert_allclose(costs, np.array(want, np.float32), rtol=2e-5, atol=1e-6)
+    for a, b_ in zip(engA.get_weights(), engB.get_weights()):
+        assert_mostly_close(a, b_, 1e-3, 1e-4, 0.995, "weights after pipelined pass")
