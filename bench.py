@@ -138,7 +138,7 @@ def run_reference(args, w, wname):
     print(json.dumps(line))
 
 
-def cpu_baseline(w, seconds=12.0, Bc=4096):
+def cpu_baseline(w, seconds=12.0, Bc=16384):
     from oracle import oracle as orc
     from tests.util import make_batch
     rng = np.random.default_rng(43)
@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="din_ml20m", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
-    ap.add_argument("--cpu-batch", type=int, default=4096)
+    ap.add_argument("--cpu-batch", type=int, default=16384)
     ap.add_argument("--table-opt", default="sgd", choices=["sgd", "det", "frozen"])
     ap.add_argument("--gemm", default="auto", choices=["auto", "fp32", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -559,6 +559,13 @@ void orc_predict_dense(const orc_cfg* c, const float* W0, const float* W1, const
  * then trains on it — this does the same per batch).  Row update is the engine's extension:
  * the reference never learns embeddings (din.go:161-169).
  * ---------------------------------------------------------------------------------------------- */
+typedef struct { int32_t row; long pos; } orc_rp;
+static int orc_cmp_rp(const void* a, const void* b) {
+    const orc_rp *x = (const orc_rp*)a, *y = (const orc_rp*)b;
+    if (x->row != y->row) return x->row < y->row ? -1 : 1;
+    return x->pos < y->pos ? -1 : (x->pos > y->pos);
+}
+
 float orc_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_state* st,
                          float* W0, float* W1, float* W2, float* att,
                          const float* user_feat, long ldu, const float* item_feat, long ldi,
@@ -590,24 +597,30 @@ float orc_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_state* 
     if (c->model != ORC_YOUTUBE)
         orc_adam_step(att, ga, st->ma, st->va, S, st->t, s->lr, s->l2, (float)B, s->b1, s->b2, s->eps);
     if (table_lr != 0.0f) {
-        /* accumulate duplicates in (b, slot) order in double, then one SGD update per row */
-        double* acc = (double*)calloc((size_t)n_items * (size_t)D, sizeof(double));
-        unsigned char* touched = (unsigned char*)calloc((size_t)n_items, 1);
-        for (int b = 0; b < B; b++) {
-            for (int sl = 0; sl < S; sl++) {
-                int32_t row = hist[(long)b * S + sl];
-                if (row < 0) continue;
-                touched[row] = 1;
-                for (int k = 0; k < D; k++) acc[(long)row * D + k] += (double)dUb[((long)b * S + sl) * D + k];
-            }
-            int32_t row = item_row[b];
-            if (row >= 0) { touched[row] = 1; for (int k = 0; k < D; k++) acc[(long)row * D + k] += (double)dIt[(long)b * D + k]; }
+        /* accumulate duplicates in (b, slot) order in double, then one SGD update per row.
+         * Sparse: sort the (row, position) pairs instead of clearing an n_items x D accumulator. */
+        long npos = (long)B * (S + 1), m = 0;
+        orc_rp* rp = (orc_rp*)malloc(sizeof(orc_rp) * (size_t)npos);
+        for (long p = 0; p < npos; p++) {
+            int b = (int)(p / (S + 1)), sl = (int)(p % (S + 1));
+            int32_t row = sl < S ? hist[(long)b * S + sl] : item_row[b];
+            if (row >= 0) { rp[m].row = row; rp[m].pos = p; m++; }
         }
-        for (long row = 0; row < n_items; row++)
-            if (touched[row])
-                for (int k = 0; k < D; k++)
-                    item_emb[row * lde + k] = (float)((double)item_emb[row * lde + k] - (double)table_lr * acc[row * D + k]);
-        free(acc); free(touched);
+        qsort(rp, (size_t)m, sizeof(orc_rp), orc_cmp_rp);
+        for (long i = 0; i < m;) {
+            long j = i; double acc[512];
+            for (int k = 0; k < D; k++) acc[k] = 0.0;
+            while (j < m && rp[j].row == rp[i].row) {
+                int b = (int)(rp[j].pos / (S + 1)), sl = (int)(rp[j].pos % (S + 1));
+                const float* gsrc = sl < S ? dUb + ((long)b * S + sl) * D : dIt + (long)b * D;
+                for (int k = 0; k < D; k++) acc[k] += (double)gsrc[k];
+                j++;
+            }
+            float* e = item_emb + (long)rp[i].row * lde;
+            for (int k = 0; k < D; k++) e[k] = (float)((double)e[k] - (double)table_lr * acc[k]);
+            i = j;
+        }
+        free(rp);
     }
     orc_ws_free(ws);
     free(X); free(g0); free(g1); free(g2); free(ga); free(dUb); free(dIt);
