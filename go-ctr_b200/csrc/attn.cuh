@@ -264,12 +264,14 @@ struct BwdOut {
     float  neg_lr;      // -table_lr
     float* hot_acc;     // [hot_reps, hot_rows, D] replica accumulators (sums of -lr * gradient)
     int    hot_rows, hot_reps;
+    float* scatter_base;    // where row gradients are added (row idx * lde): the table itself, or the per-lookup
+                            // gradient buffer of the sharded path
 };
 
 // destination of one row's (already -lr scaled) gradient: a hot-row replica accumulator or the table row
 __device__ __forceinline__ float* scatter_dst(const RowSrc& r, const Dims& d, const BwdOut& o, int idx, int rep) {
     return idx < o.hot_rows ? o.hot_acc + ((long)rep * o.hot_rows + idx) * d.D
-                            : const_cast<float*>(r.emb) + (long)idx * r.lde;
+                            : o.scatter_base + (long)idx * r.lde;
 }
 
 template <int LPR, int VPL, int UNR, int MODEL, int NT, int MINB>
@@ -505,7 +507,7 @@ k_attn_bwd_gen(RowSrc r, Dims d, int model, const float* __restrict__ att,
                 int k = lane + 32 * j;
                 if (k < d.D) {
                     if (o.dUb) o.dUb[((long)b * d.S + s) * d.D + k] = du[j];
-                    if (o.sgd && up) atomicAdd(const_cast<float*>(up) + k, o.neg_lr * du[j]);
+                    if (o.sgd && up) atomicAdd(o.scatter_base + (up - r.emb) + k, o.neg_lr * du[j]);
                 }
             }
         }
@@ -514,7 +516,7 @@ k_attn_bwd_gen(RowSrc r, Dims d, int model, const float* __restrict__ att,
             int k = lane + 32 * j;
             if (k < d.D) {
                 if (o.dIt) o.dIt[(long)b * d.D + k] = dv[j];
-                if (o.sgd && ip) atomicAdd(const_cast<float*>(ip) + k, o.neg_lr * dv[j]);
+                if (o.sgd && ip) atomicAdd(o.scatter_base + (ip - r.emb) + k, o.neg_lr * dv[j]);
             }
         }
     }

@@ -1,7 +1,10 @@
-// comm.cuh — multi-GPU state of one rank: ITEM_EMB rows are sharded
-// owner(row) = row % world; indices travel to the owners with an NCCL all-to-all, rows come back,
-// row gradients return the same way, dense gradients are all-reduced.  NCCL is loaded with dlopen
-// so that a process that already carries torch's bundled libnccl shares it.
+// comm.cuh — multi-GPU state of one rank.  ITEM_EMB rows are sharded
+// owner(row) = row % world, local row = row / world; the dense weights and the small feature tables
+// are replicated.  Per step: the (S+1)*B lookups of the local batch are bucketed by owner on the
+// device, their ids travel to the owners (all-to-all), the owners gather the rows and send them back,
+// the local attention/MLP kernels run on the received rows, row gradients return the same way and
+// the owners apply them; dense gradients are all-reduced so every rank takes the identical Adam step.
+// NCCL is loaded with dlopen so that a process that already carries torch's bundled libnccl shares it.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,17 +15,22 @@ namespace ctr {
 
 struct Comm {
     int rank = 0, world = 1;
-    void* lib = nullptr;          // dlopen handle of libnccl
     void* nccl = nullptr;         // ncclComm_t
     bool ready = false;
-    // exchange buffers (device)
-    int* send_rows = nullptr;  int* recv_rows = nullptr;      // requested row ids, bucketed by owner
-    int* send_cnt = nullptr;   int* recv_cnt = nullptr;       // [world] counts (device)
-    float* send_buf = nullptr; float* recv_buf = nullptr;     // row payloads
-    int* slot_of = nullptr;                                   // [B*(S+1)] position of each lookup in recv order
-    size_t cap_rows = 0;
-    float* rows_local = nullptr;                              // [B, (S+1)*D] gathered rows in sample order
-    float* grads_local = nullptr;
+    // exchange plan of the current batch
+    int* d_cnt = nullptr;         // [world] lookups per owner            (device)
+    int* d_cursor = nullptr;      // [world] fill cursors                  (device)
+    int* d_rcnt = nullptr;        // [world] lookups requested from us     (device)
+    int* send_rows = nullptr;     // [L] owner-local row ids, bucketed by owner
+    int* slot_hist = nullptr;     // [B,S]  position of each history lookup in send order (-1 = missing)
+    int* slot_item = nullptr;     // [B]
+    int* recv_rows = nullptr;     // [n_recv] rows requested from this rank
+    float* rows_out = nullptr;    // [n_recv, D] gathered rows / received gradients (owner side)
+    float* rows_local = nullptr;  // [L, D] rows of the local batch in send order
+    float* grad_local = nullptr;  // [L, D] -lr/world * gradient per lookup
+    size_t cap_L = 0, cap_recv = 0;
+    int h_scnt[64] = {0}, h_rcnt[64] = {0}, h_soff[65] = {0}, h_roff[65] = {0};
+    double bytes_sent = 0;        // payload bytes this rank has put on NVLink (rows + gradients + ids)
 };
 
 }  // namespace ctr

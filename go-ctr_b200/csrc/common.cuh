@@ -89,6 +89,7 @@ struct RowSrc {
     const float* ufeat; long ldu;     // USER_FEAT [U, uP]
     const float* ifeat; long ldi;     // ITEM_FEAT [I, cF]
     const int* user_row; const int* item_row; const int* hist;   // [B] [B] [B,S]
+    const int* item_feat_row;    // row of ITEM_FEAT when it differs from item_row (sharded tables: item_row is a slot)
     const float* X; long ldx; int up0, ub0, it0, cx0;            // dense mode
     int dense;
     int nvalid;          // rows >= nvalid are the zero-padded tail (model.go:357-371)
@@ -117,7 +118,7 @@ __device__ __forceinline__ const float* src_up(const RowSrc& r, int b) {
 __device__ __forceinline__ const float* src_cx(const RowSrc& r, int b) {
     if (b >= r.nvalid) return nullptr;
     if (r.dense) return r.X + (long)b * r.ldx + r.cx0;
-    int idx = r.item_row[b];
+    int idx = r.item_feat_row ? r.item_feat_row[b] : r.item_row[b];
     return idx >= 0 ? r.ifeat + (long)idx * r.ldi : nullptr;
 }
 

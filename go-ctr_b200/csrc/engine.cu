@@ -362,6 +362,9 @@ struct StepOpts {
     bool training = false, update = false;
     bool want_rows = false;              // fill h->dUb / h->dIt
     const float* d_label = nullptr;
+    // sharded-table step (comm_impl.cuh): rows live in a per-lookup buffer, gradients are scaled to the
+    // global mean and the dense gradients are all-reduced before Adam
+    bool comm = false; float* scatter_base = nullptr; float grad_scale = 1.0f; int adam_batch = 0;
 };
 
 int ensure_rowgrad_buffers(ctr_handle* h, int B) {
@@ -499,11 +502,12 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
             g.C = h->dX; g.ldc = h->lddx; g.M = B; g.N = 2 * c.D; g.K = c.H0; g.Nz = h->lddx;
             RET((gemm_big<false, true, EPI_STORE>(h, "sgemm_dX", g)));
         }
-        const bool buffers = o.want_rows || (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC);
+        const bool buffers = o.want_rows || (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC && !o.comm);
         if (buffers) RET(ensure_rowgrad_buffers(h, B));
         BwdOut bo{}; bo.datt = h->G[3]; bo.dUb = buffers ? h->dUb : nullptr; bo.dIt = buffers ? h->dIt : nullptr;
-        bo.sgd = (learn_rows && c.table_opt == CTR_TABLE_SGD) ? 1 : 0; bo.neg_lr = -c.table_lr;
-        const bool hot = bo.sgd && vec_ok(h, r);
+        bo.sgd = (learn_rows && (c.table_opt == CTR_TABLE_SGD || o.comm)) ? 1 : 0; bo.neg_lr = -c.table_lr * o.grad_scale;
+        bo.scatter_base = o.scatter_base ? o.scatter_base : h->tab[CTR_TABLE_ITEM_EMB];
+        const bool hot = bo.sgd && vec_ok(h, r) && !o.comm;
         if (hot) { RET(ensure_hot(h)); bo.hot_acc = h->hot_acc; bo.hot_rows = h->hot_rows; bo.hot_reps = h->hot_reps; }
         RET(attn_backward(h, r, bo, B));
         if (hot && h->hot_rows > 0)
@@ -511,10 +515,10 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
                 k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(h->tab[CTR_TABLE_ITEM_EMB], h->tab_ld[CTR_TABLE_ITEM_EMB], h->hot_acc,
                                                                 h->hot_rows, h->hot_reps, c.D, 1.0f);
             }));
-        if (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC) RET(deterministic_table_update(h, r, B));
+        if (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC && !o.comm) RET(deterministic_table_update(h, r, B));
     }
     if (o.update) {
-        if (h->comm.world > 1) RET(comm_allreduce_grads(h));
+        if (o.comm) RET(comm_allreduce_grads(h));
         AdamArgs a{};
         const int in = h->in;
         a.t[0] = AdamTensor{h->W[0], h->G[0], h->Mo[0], h->Vo[0], in, c.H0, h->H0p};
@@ -523,7 +527,9 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         a.t[3] = AdamTensor{h->W[3], h->G[3], h->Mo[3], h->Vo[3], 1, c.S, h->Sp};
         a.nt = c.model == CTR_MODEL_YOUTUBE ? 3 : 4;       // Learnable(): dnn.go:153 vs din.go:161-169
         const int t = (int)h->step + 1;
-        a.lr = c.lr; a.l2 = c.l2; a.inv_batch = B > 1 ? 1.0f / (float)B : 1.0f; a.b1 = c.beta1; a.b2 = c.beta2; a.eps = c.eps;
+        const int ab = o.adam_batch > 0 ? o.adam_batch : B;
+        a.gscale = o.grad_scale;
+        a.lr = c.lr; a.l2 = c.l2; a.inv_batch = ab > 1 ? 1.0f / (float)ab : 1.0f; a.b1 = c.beta1; a.b2 = c.beta2; a.eps = c.eps;
         a.c1 = (float)(1.0 - std::pow((double)c.beta1, (double)t));
         a.c2 = (float)(1.0 - std::pow((double)c.beta2, (double)t));
         RET(launch(h, "adam_dense", [&] { k_adam<<<h->num_sms, 256, 0, h->stream>>>(a); }));
@@ -900,7 +906,7 @@ int ctr_train_step_idx(ctr_handle* h, const int32_t* user_row, const int32_t* it
     RET(stage_idx(h, user_row, item_row, hist, label, B));
     RET(ctr_train_step_idx_dev(h, h->s_user, h->s_item, h->s_hist, h->s_label, B));
     float cost = 0;
-    RET(read_cost(h, B * std::max(1, h->comm.world > 1 ? 1 : 1), &cost));
+    RET(read_cost(h, B * h->comm.world, &cost));      // d_cost was summed over the ranks
     if (stats) { stats->cost = cost; stats->ms_device = 0; stats->launches = (int32_t)(h->launches - l0); stats->reserved = 0; }
     return CTR_OK;
 }
@@ -979,7 +985,7 @@ int ctr_predict_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_
 int ctr_last_cost(ctr_handle* h, float* cost) {
     if (!h || !cost) return CTR_EINVAL;
     CU(h, cudaSetDevice(h->dev));
-    return read_cost(h, h->cfg.batch, cost);
+    return read_cost(h, h->cfg.batch * h->comm.world, cost);
 }
 
 int ctr_sync(ctr_handle* h) {

@@ -223,6 +223,7 @@ struct AdamTensor { float* w; float* g; float* m; float* v; int rows, cols; long
 struct AdamArgs {
     AdamTensor t[4]; int nt;
     float lr, l2, inv_batch, b1, b2, eps, c1, c2;
+    float gscale;       // 1/world after the all-reduce(sum) of the ranks' local-mean gradients, else 1
 };
 
 __global__ void __launch_bounds__(256) k_adam(AdamArgs a) {
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) k_adam(AdamArgs a) {
         for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
             long off = (i / t.cols) * t.ld + (i % t.cols);
             float w = t.w[off];
-            float g = t.g[off];
+            float g = t.g[off] * a.gscale;
             if (a.l2 != 0.0f) g = g + a.l2 * w;
             g = g * a.inv_batch;
             float m = a.b1 * t.m[off] + (1.0f - a.b1) * g;

@@ -1,0 +1,85 @@
+"""Two-rank NCCL test of the sharded-table path (needs >= 2 GPUs: `gpurun --gpus 2`): a step on 2 GPUs with
+per-GPU batch B == a step on 1 GPU with batch 2B (same samples), for scores, cost, dense weights and the
+updated embedding table."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import go_ctr_b200 as g
+from tests.util import assert_mostly_close, make_batch, make_tables
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+DIMS = dict(uP=52, S=10, D=16, cF=53)
+U, I, B, STEPS = 97, 211, 256, 3
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _data():
+    rng = np.random.default_rng(77)
+    uf, itf, emb = make_tables(rng, U, I, DIMS["uP"], DIMS["cF"], DIMS["D"])
+    batches = [make_batch(rng, U, I, 2 * B, DIMS["S"], zipf=True) for _ in range(STEPS)]
+    return uf, itf, emb, batches
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank)
+    uf, itf, emb, batches = _data()
+    cfg = g.engine.default_config(g.MODEL_DIN_COS, batch=B, pred_batch=B, table_opt=g.TABLE_SGD, table_lr=0.7, dropout0=0.0, dropout1=0.0,
+                                  seed=3, device=rank, rank=rank, world=world, **DIMS)
+    eng = g.Engine(cfg)
+    ids = [eng.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    eng.comm_init(ids[0])
+    eng.table_upload(g.TABLE_USER_FEAT, uf); eng.table_upload(g.TABLE_ITEM_FEAT, itf); eng.table_upload(g.TABLE_ITEM_EMB, emb)
+    costs = []
+    sl = slice(rank * B, (rank + 1) * B)
+    for ur, ir, hist, y in batches:
+        costs.append(eng.train_step_idx(ur[sl], ir[sl], hist[sl], y[sl]).cost)
+    ur, ir, hist, y = batches[0]
+    p = eng.predict_idx(ur[sl], ir[sl], hist[sl])
+    np.save(os.path.join(out_dir, "p%d.npy" % rank), p)
+    np.save(os.path.join(out_dir, "cost%d.npy" % rank), np.array(costs, np.float32))
+    np.save(os.path.join(out_dir, "emb%d.npy" % rank), eng.table_download(g.TABLE_ITEM_EMB, I, DIMS["D"]))
+    for i, w in enumerate(eng.get_weights()):
+        np.save(os.path.join(out_dir, "w%d_%d.npy" % (i, rank)), w)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_step_equals_single_gpu_global_batch(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    uf, itf, emb, batches = _data()
+    cfg = g.engine.default_config(g.MODEL_DIN_COS, batch=2 * B, pred_batch=2 * B, table_opt=g.TABLE_SGD_DETERMINISTIC, table_lr=0.7,
+                                  dropout0=0.0, dropout1=0.0, seed=3, **DIMS)
+    ref = g.Engine(cfg)
+    ref.table_upload(g.TABLE_USER_FEAT, uf); ref.table_upload(g.TABLE_ITEM_FEAT, itf); ref.table_upload(g.TABLE_ITEM_EMB, emb)
+    want_cost = [ref.train_step_idx(*b).cost for b in batches]
+    got_cost = np.load(tmp_path / "cost0.npy")
+    np.testing.assert_allclose(got_cost, np.load(tmp_path / "cost1.npy"), rtol=0, atol=0)     # every rank reports the global mean
+    np.testing.assert_allclose(got_cost, np.array(want_cost, np.float32), rtol=2e-4, atol=1e-6)
+    for i, w in enumerate(ref.get_weights()):
+        w0 = np.load(tmp_path / ("w%d_0.npy" % i))
+        assert w0.tobytes() == np.load(tmp_path / ("w%d_1.npy" % i)).tobytes()               # identical Adam step on every rank
+        assert_mostly_close(w0, w, 2e-3, 2e-4, 0.995, "weights %d" % i)
+    got_emb = np.zeros_like(emb)
+    for r in range(world):
+        got_emb[r::world] = np.load(tmp_path / ("emb%d.npy" % r))[r::world]
+    want_emb = ref.table_download(g.TABLE_ITEM_EMB, I, DIMS["D"])
+    assert np.abs(want_emb - emb).max() > 1e-5
+    np.testing.assert_allclose(got_emb, want_emb, rtol=2e-3, atol=2e-5)
+    p = np.concatenate([np.load(tmp_path / "p0.npy"), np.load(tmp_path / "p1.npy")])
+    np.testing.assert_allclose(p, ref.predict_idx(*batches[0][:3]), rtol=2e-3, atol=1e-5)
