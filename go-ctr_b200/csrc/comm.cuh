@@ -31,6 +31,14 @@ struct Comm {
     size_t cap_L = 0, cap_recv = 0;
     int h_scnt[64] = {0}, h_rcnt[64] = {0}, h_soff[65] = {0}, h_roff[65] = {0};
     double bytes_sent = 0;        // payload bytes this rank has put on NVLink (rows + gradients + ids)
+    // de-duplicated exchange (tables up to 32M rows): each distinct row of the batch crosses NVLink once
+    bool dedup = false;
+    long Imax = 0, Q = 0;         // q(row) = (row % world) * Imax + row / world, Q = world * Imax
+    int* flags = nullptr;         // [Q+1] 1 where the batch touches q
+    int* pos = nullptr;           // [Q+1] exclusive scan of flags = slot of q in owner-bucketed send order
+    void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+    float* rep_acc = nullptr;     // [reps, cap_U, D] replica accumulators of the per-row gradients
+    int reps = 0; size_t cap_U = 0;
 };
 
 }  // namespace ctr

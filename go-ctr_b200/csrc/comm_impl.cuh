@@ -62,7 +62,17 @@ __global__ void k_owner_fill(const int* __restrict__ hist, const int* __restrict
         const int b = (int)(p / (S + 1)), sl = (int)(p % (S + 1));
         const int row = sl < S ? hist[(long)b * S + sl] : item_row[b];
         int pos = -1;
-        if (row >= 0) { pos = atomicAdd(cursor + row % world, 1); send_rows[pos] = row / world; }
+        // one atomic per (warp, owner): lanes that target the same owner claim a contiguous run together
+        const int own = row >= 0 ? row % world : -1;
+        const unsigned peers = __match_any_sync(__activemask(), own);
+        if (row >= 0) {
+            const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(cursor + own, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            pos = base + __popc(peers & ((1u << lane) - 1u));
+            send_rows[pos] = row / world;
+        }
         if (sl < S) slot_hist[(long)b * S + sl] = pos; else slot_item[b] = pos;
     }
 }
@@ -85,10 +95,55 @@ __global__ void k_scatter_local(const int* __restrict__ rows, long n, const floa
     }
 }
 
+// ---- de-duplicated plan: mark → exclusive scan → emit --------------------------------------------------
+__global__ void k_dd_mark(const int* __restrict__ hist, const int* __restrict__ item_row, int S, int B, int world, long Imax, int* __restrict__ flags) {
+    const long n = (long)B * (S + 1);
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n; p += (long)gridDim.x * blockDim.x) {
+        const int b = (int)(p / (S + 1)), sl = (int)(p % (S + 1));
+        const int row = sl < S ? hist[(long)b * S + sl] : item_row[b];
+        if (row >= 0) {
+            int* f = flags + (long)(row % world) * Imax + row / world;
+            if (*reinterpret_cast<volatile int*>(f) == 0) *f = 1;      // popular rows: read-mostly instead of a store storm on one line
+        }
+    }
+}
+__global__ void k_dd_counts(const int* __restrict__ pos, long Imax, int world, int* __restrict__ cnt) {
+    const int j = threadIdx.x;
+    if (j < world) cnt[j] = pos[(long)(j + 1) * Imax] - pos[(long)j * Imax];
+}
+__global__ void k_dd_emit(const int* __restrict__ flags, const int* __restrict__ pos, long Q, long Imax, int* __restrict__ send_rows) {
+    for (long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < Q; q += (long)gridDim.x * blockDim.x)
+        if (flags[q]) send_rows[pos[q]] = (int)(q % Imax);
+}
+__global__ void k_dd_slots(const int* __restrict__ hist, const int* __restrict__ item_row, int S, int B, int world, long Imax,
+                           const int* __restrict__ pos, int* __restrict__ slot_hist, int* __restrict__ slot_item) {
+    const long n = (long)B * (S + 1);
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n; p += (long)gridDim.x * blockDim.x) {
+        const int b = (int)(p / (S + 1)), sl = (int)(p % (S + 1));
+        const int row = sl < S ? hist[(long)b * S + sl] : item_row[b];
+        const int slot = row >= 0 ? pos[(long)(row % world) * Imax + row / world] : -1;
+        if (sl < S) slot_hist[(long)b * S + sl] = slot; else slot_item[b] = slot;
+    }
+}
+
 int comm_ensure(ctr_handle* h, size_t L, size_t nrecv) {
     Comm& cm = h->comm;
     const int D = h->cfg.D, W = cm.world;
-    if (!cm.d_cnt) { RET(dalloc(h, &cm.d_cnt, (size_t)W)); RET(dalloc(h, &cm.d_cursor, (size_t)W)); RET(dalloc(h, &cm.d_rcnt, (size_t)W)); }
+    if (!cm.d_cnt) {
+        RET(dalloc(h, &cm.d_cnt, (size_t)W)); RET(dalloc(h, &cm.d_cursor, (size_t)W)); RET(dalloc(h, &cm.d_rcnt, (size_t)W));
+        const long I = (long)h->tab_rows[CTR_TABLE_ITEM_EMB];
+        cm.Imax = (I + W - 1) / W; cm.Q = cm.Imax * W;
+        cm.dedup = cm.Q <= ((long)32 << 20) && !getenv("CTR_NO_DEDUP");
+        if (cm.dedup) {
+            RET(dalloc(h, &cm.flags, (size_t)cm.Q + 1)); RET(dalloc(h, &cm.pos, (size_t)cm.Q + 1));
+            cub::DeviceScan::ExclusiveSum(nullptr, cm.scan_tmp_bytes, cm.flags, cm.pos, (int)(cm.Q + 1), h->stream);
+            CU(h, cudaMalloc(&cm.scan_tmp, cm.scan_tmp_bytes));
+            // replica accumulators for the per-row gradients (popular rows would otherwise serialise in L2)
+            cm.cap_U = (size_t)std::min<long>((long)L, cm.Q);
+            cm.reps = (int)std::min<size_t>(16, std::max<size_t>(1, ((size_t)64 << 20) / (cm.cap_U * D * sizeof(float))));
+            if (cm.reps > 1) RET(dalloc(h, &cm.rep_acc, (size_t)cm.reps * cm.cap_U * D));
+        }
+    }
     if (cm.cap_L < L) {
         for (void* p : {(void*)cm.send_rows, (void*)cm.slot_hist, (void*)cm.slot_item, (void*)cm.rows_local, (void*)cm.grad_local}) if (p) cudaFree(p);
         RET(dalloc(h, &cm.send_rows, L)); RET(dalloc(h, &cm.slot_hist, L)); RET(dalloc(h, &cm.slot_item, L));
@@ -113,8 +168,15 @@ int comm_fetch_rows(ctr_handle* h, const int* d_item, const int* d_hist, int B) 
     const size_t L = (size_t)B * (S + 1);
     RET(comm_ensure(h, L, cm.cap_recv));
     const int grid = std::min<int>((int)((L + 255) / 256), h->num_sms * 8);
-    CU(h, cudaMemsetAsync(cm.d_cnt, 0, sizeof(int) * W, h->stream));
-    RET(launch(h, "shard_owner_count", [&] { k_owner_count<<<grid, 256, 0, h->stream>>>(d_hist, d_item, S, B, W, cm.d_cnt); }));
+    if (cm.dedup) {
+        CU(h, cudaMemsetAsync(cm.flags, 0, sizeof(int) * ((size_t)cm.Q + 1), h->stream));
+        RET(launch(h, "shard_dedup_mark", [&] { k_dd_mark<<<grid, 256, 0, h->stream>>>(d_hist, d_item, S, B, W, cm.Imax, cm.flags); }));
+        RET(launch(h, "cub_exclusive_scan", [&] { cub::DeviceScan::ExclusiveSum(cm.scan_tmp, cm.scan_tmp_bytes, cm.flags, cm.pos, (int)(cm.Q + 1), h->stream); }));
+        RET(launch(h, "shard_dedup_counts", [&] { k_dd_counts<<<1, 64, 0, h->stream>>>(cm.pos, cm.Imax, W, cm.d_cnt); }));
+    } else {
+        CU(h, cudaMemsetAsync(cm.d_cnt, 0, sizeof(int) * W, h->stream));
+        RET(launch(h, "shard_owner_count", [&] { k_owner_count<<<grid, 256, 0, h->stream>>>(d_hist, d_item, S, B, W, cm.d_cnt); }));
+    }
     // counts to every owner (one int each way), then both count vectors to the host to size the exchange
     NC(h, g_nccl.GroupStart());
     for (int j = 0; j < W; j++) {
@@ -128,10 +190,17 @@ int comm_fetch_rows(ctr_handle* h, const int* d_item, const int* d_hist, int B) 
     cm.h_soff[0] = cm.h_roff[0] = 0;
     for (int j = 0; j < W; j++) { cm.h_soff[j + 1] = cm.h_soff[j] + cm.h_scnt[j]; cm.h_roff[j + 1] = cm.h_roff[j] + cm.h_rcnt[j]; }
     RET(comm_ensure(h, L, (size_t)cm.h_roff[W]));
-    CU(h, cudaMemcpyAsync(cm.d_cursor, cm.h_soff, sizeof(int) * W, cudaMemcpyHostToDevice, h->stream));
-    RET(launch(h, "shard_owner_fill", [&] {
-        k_owner_fill<<<grid, 256, 0, h->stream>>>(d_hist, d_item, S, B, W, cm.d_cursor, cm.send_rows, cm.slot_hist, cm.slot_item);
-    }));
+    if (cm.dedup) {
+        RET(launch(h, "shard_dedup_emit", [&] {
+            k_dd_emit<<<std::min<long>((cm.Q + 255) / 256, (long)h->num_sms * 8), 256, 0, h->stream>>>(cm.flags, cm.pos, cm.Q, cm.Imax, cm.send_rows);
+        }));
+        RET(launch(h, "shard_dedup_slots", [&] { k_dd_slots<<<grid, 256, 0, h->stream>>>(d_hist, d_item, S, B, W, cm.Imax, cm.pos, cm.slot_hist, cm.slot_item); }));
+    } else {
+        CU(h, cudaMemcpyAsync(cm.d_cursor, cm.h_soff, sizeof(int) * W, cudaMemcpyHostToDevice, h->stream));
+        RET(launch(h, "shard_owner_fill", [&] {
+            k_owner_fill<<<grid, 256, 0, h->stream>>>(d_hist, d_item, S, B, W, cm.d_cursor, cm.send_rows, cm.slot_hist, cm.slot_item);
+        }));
+    }
     // ids to the owners
     NC(h, g_nccl.GroupStart());
     for (int j = 0; j < W; j++) {
@@ -201,6 +270,7 @@ static int comm_train_step(ctr_handle* h, const int32_t* d_user, const int32_t* 
     if (learn) CU(h, cudaMemsetAsync(cm.grad_local, 0, (size_t)cm.h_soff[W] * D * sizeof(float), h->stream));
     StepOpts o; o.training = true; o.update = true; o.d_label = d_label;
     o.comm = true; o.scatter_base = cm.grad_local; o.grad_scale = 1.0f / (float)W; o.adam_batch = B * W;
+    if (cm.dedup && cm.reps > 1) { o.rep_acc = cm.rep_acc; o.rep_rows = cm.h_soff[W]; o.rep_n = cm.reps; }
     RET(step_core(h, r, B, o));
     if (learn) {
         // row gradients go home: the reverse of the row exchange, then the owners apply them
@@ -255,6 +325,7 @@ static int comm_init(ctr_handle* h, const void* id, int32_t id_bytes) {
 
 static void comm_destroy(ctr_handle* h) {
     Comm& cm = h->comm;
+    for (void* p : {(void*)cm.flags, (void*)cm.pos, cm.scan_tmp, (void*)cm.rep_acc}) if (p) cudaFree(p);
     for (void* p : {(void*)cm.d_cnt, (void*)cm.d_cursor, (void*)cm.d_rcnt, (void*)cm.send_rows, (void*)cm.slot_hist, (void*)cm.slot_item,
                     (void*)cm.recv_rows, (void*)cm.rows_out, (void*)cm.rows_local, (void*)cm.grad_local}) if (p) cudaFree(p);
     if (cm.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(cm.nccl);

@@ -9,6 +9,7 @@
 #include "comm.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -365,6 +366,7 @@ struct StepOpts {
     // sharded-table step (comm_impl.cuh): rows live in a per-lookup buffer, gradients are scaled to the
     // global mean and the dense gradients are all-reduced before Adam
     bool comm = false; float* scatter_base = nullptr; float grad_scale = 1.0f; int adam_batch = 0;
+    float* rep_acc = nullptr; int rep_rows = 0, rep_n = 0;      // replica accumulators over the batch's distinct rows
 };
 
 int ensure_rowgrad_buffers(ctr_handle* h, int B) {
@@ -509,7 +511,12 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         bo.scatter_base = o.scatter_base ? o.scatter_base : h->tab[CTR_TABLE_ITEM_EMB];
         const bool hot = bo.sgd && vec_ok(h, r) && !o.comm;
         if (hot) { RET(ensure_hot(h)); bo.hot_acc = h->hot_acc; bo.hot_rows = h->hot_rows; bo.hot_reps = h->hot_reps; }
+        if (o.comm && o.rep_acc && bo.sgd) { bo.hot_acc = o.rep_acc; bo.hot_rows = o.rep_rows; bo.hot_reps = o.rep_n; }
         RET(attn_backward(h, r, bo, B));
+        if (o.comm && o.rep_acc && bo.sgd && o.rep_rows > 0)
+            RET(launch(h, "shard_fold_replicas", [&] {
+                k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(o.scatter_base, c.D, o.rep_acc, o.rep_rows, o.rep_n, c.D, 1.0f);
+            }));
         if (hot && h->hot_rows > 0)
             RET(launch(h, "hot_rows_apply", [&] {
                 k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(h->tab[CTR_TABLE_ITEM_EMB], h->tab_ld[CTR_TABLE_ITEM_EMB], h->hot_acc,
