@@ -6,6 +6,7 @@
 #include "mlp.cuh"
 #include "umma_gemm.cuh"
 #include "auc.cuh"
+#include "ubcache.cuh"
 #include "comm.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -92,6 +93,9 @@ struct ctr_handle {
         CUtensorMap mK_X0, mK_H0d, mK_dZ0, mK_dZ1;      // {32 x 32} boxes over [batch, width] for the weight-gradient GEMMs
         int dw_stages0 = 0, dw_stages1 = 0;
     } um;
+
+    // device-side ubcache (ubcache.cuh)
+    long long *ub_off = nullptr, *ub_ts = nullptr; int* ub_items = nullptr; int64_t ub_users = 0, ub_n = 0;
 
     unsigned long long* umma_dbg = nullptr;     // CTR_UMMA_TIMELINE=1: timeline buffer of the last umma launch
 
@@ -695,6 +699,7 @@ void ctr_destroy(ctr_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     comm_destroy(h);
     for (int i = 0; i < 3; i++) if (h->tab[i]) cudaFree(h->tab[i]);
+    for (void* p : {(void*)h->ub_off, (void*)h->ub_ts, (void*)h->ub_items}) if (p) cudaFree(p);
     for (int i = 0; i < 2; i++) for (float* p : {h->um.Wt0[i], h->um.Wt1[i], h->um.W1s[i], h->um.W0s[i]}) if (p) cudaFree(p);
     for (int i = 0; i < 4; i++) for (float* p : {h->W[i], h->G[i], h->Mo[i], h->Vo[i]}) if (p) cudaFree(p);
     for (void* p : {(void*)h->X0, (void*)h->H0d, (void*)h->H1d, (void*)h->P, (void*)h->Z, (void*)h->dZ1, (void*)h->dZ0, (void*)h->dX,
@@ -1062,6 +1067,53 @@ int ctr_debug_grads_idx(ctr_handle* h, const int32_t* user_row, const int32_t* i
     RET(zero_grads(h));
     CU(h, cudaStreamSynchronize(h->stream));
     return CTR_OK;
+}
+
+int ctr_ubcache_upload(ctr_handle* h, const int64_t* offsets, const int64_t* ts, const int32_t* item_rows, int64_t n_users, int64_t n) {
+    if (!h || !offsets || n_users < 1 || n < 0 || (n > 0 && (!ts || !item_rows))) return set_err(h, CTR_EINVAL, "bad ubcache arguments");
+    if (offsets[0] != 0 || offsets[n_users] != n) return set_err(h, CTR_EINVAL, "ubcache offsets must run from 0 to n");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    for (void* p : {(void*)h->ub_off, (void*)h->ub_ts, (void*)h->ub_items}) if (p) cudaFree(p);
+    h->ub_off = h->ub_ts = nullptr; h->ub_items = nullptr;
+    RET(dalloc(h, &h->ub_off, (size_t)n_users + 1, false)); RET(dalloc(h, &h->ub_ts, (size_t)n, false)); RET(dalloc(h, &h->ub_items, (size_t)n, false));
+    CU(h, cudaMemcpyAsync(h->ub_off, offsets, sizeof(int64_t) * (size_t)(n_users + 1), cudaMemcpyHostToDevice, h->stream));
+    if (n > 0) {
+        CU(h, cudaMemcpyAsync(h->ub_ts, ts, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(h->ub_items, item_rows, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->ub_users = n_users; h->ub_n = n;
+    return CTR_OK;
+}
+
+int ctr_ubcache_window_dev(ctr_handle* h, const int32_t* d_user_row, const int64_t* d_max_ts, int32_t B, int32_t* d_hist_rows) {
+    if (!h || !d_user_row || !d_max_ts || !d_hist_rows || B < 1) return set_err(h, CTR_EINVAL, "bad ubcache window arguments");
+    if (!h->ub_off) return set_err(h, CTR_ESTATE, "ubcache not uploaded");
+    CU(h, cudaSetDevice(h->dev));
+    return launch(h, "ubcache_window", [&] {
+        k_ub_window<<<grid_for_warps(h, B), 256, 0, h->stream>>>(h->ub_off, h->ub_ts, h->ub_items, d_user_row, (const long long*)d_max_ts, B, h->cfg.S,
+                                                               (long)h->ub_users, d_hist_rows);
+    });
+}
+
+int ctr_ubcache_window(ctr_handle* h, const int32_t* user_row, const int64_t* max_ts, int32_t B, int32_t* hist_rows) {
+    if (!h || !user_row || !max_ts || !hist_rows || B < 1) return set_err(h, CTR_EINVAL, "bad ubcache window arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    int* du = nullptr; long long* dt = nullptr; int* dh = nullptr;
+    int rc = CTR_OK;
+    if (cudaMalloc(&du, sizeof(int) * (size_t)B) != cudaSuccess || cudaMalloc(&dt, sizeof(long long) * (size_t)B) != cudaSuccess ||
+        cudaMalloc(&dh, sizeof(int) * (size_t)B * h->cfg.S) != cudaSuccess) rc = set_err(h, CTR_ENOMEM, "ubcache window buffers");
+    if (rc == CTR_OK) {
+        cudaMemcpyAsync(du, user_row, sizeof(int) * (size_t)B, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(dt, max_ts, sizeof(long long) * (size_t)B, cudaMemcpyHostToDevice, h->stream);
+        rc = ctr_ubcache_window_dev(h, du, (const int64_t*)dt, B, dh);
+        if (rc == CTR_OK && (cudaMemcpyAsync(hist_rows, dh, sizeof(int) * (size_t)B * h->cfg.S, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                             cudaStreamSynchronize(h->stream) != cudaSuccess)) rc = set_err(h, CTR_ECUDA, "ubcache window copy: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    for (void* p : {(void*)du, (void*)dt, (void*)dh}) if (p) cudaFree(p);
+    return rc;
 }
 
 int ctr_roc_auc(ctr_handle* h, const float* pred, const float* y, int64_t n, double* auc) {

@@ -24,7 +24,7 @@ EXPORTS = ["ctr_abi_version", "ctr_config_default", "ctr_create", "ctr_destroy",
            "ctr_gather_rows", "ctr_train_dense", "ctr_predict_dense", "ctr_train_step_idx", "ctr_train_idx", "ctr_predict_idx",
            "ctr_train_step_idx_dev", "ctr_predict_idx_dev", "ctr_last_cost", "ctr_sync", "ctr_get_stream",
            "ctr_set_stream", "ctr_launch_count", "ctr_profile_enable", "ctr_profile_get", "ctr_profile_reset",
-           "ctr_profile_dump", "ctr_debug_grads_idx", "ctr_roc_auc", "ctr_comm_unique_id", "ctr_comm_init"]
+           "ctr_profile_dump", "ctr_debug_grads_idx", "ctr_ubcache_upload", "ctr_ubcache_window", "ctr_ubcache_window_dev", "ctr_roc_auc", "ctr_comm_unique_id", "ctr_comm_init"]
 
 
 class CtrError(RuntimeError):
@@ -276,6 +276,17 @@ class Engine:
 
     def comm_init(self, uid):
         self._ck(self.L.ctr_comm_init(self.h, C.c_char_p(uid), C.c_int32(len(uid))))
+
+    def ubcache_upload(self, offsets, ts, item_rows):
+        off = np.ascontiguousarray(offsets, np.int64); t = np.ascontiguousarray(ts, np.int64); it = np.ascontiguousarray(item_rows, np.int32)
+        self._ck(self.L.ctr_ubcache_upload(self.h, off.ctypes.data_as(C.POINTER(C.c_int64)), t.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           it.ctypes.data_as(_ip), C.c_int64(off.size - 1), C.c_int64(t.size)))
+
+    def ubcache_window(self, user_row, max_ts):
+        u, up = _i(user_row); t = np.ascontiguousarray(max_ts, np.int64)
+        out = np.empty((u.size, self.cfg.S), np.int32)
+        self._ck(self.L.ctr_ubcache_window(self.h, up, t.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int32(u.size), out.ctypes.data_as(_ip)))
+        return out
 
     def roc_auc(self, pred, y):
         p, pp = _f(pred); t, tp = _f(y)

@@ -165,6 +165,16 @@ int ctr_debug_grads_idx(ctr_handle* h, const int32_t* user_row, const int32_t* i
                         float* dmlp0, float* dmlp1, float* dmlp2, float* datt0,
                         float* dUb, float* dIt, float* p, float* logit, float* cost);
 
+/* feature/ubcache on the device.  upload: every user's behaviour sequence in
+ * time-DESCENDING order (ubcache.TimeSeq, cache.go:9-12) as one CSR: offsets [n_users+1], ts [n],
+ * item_rows [n] (dense ITEM_EMB rows).  window: TimeSeq.Filter(maxTs, S) for a batch (cache.go:71-94;
+ * maxTs == 0 means "from the newest"), i.e. what GetUserBehavior(uid, S, -1, sample.Timestamp) returns
+ * (prepare.go:13-38), written as hist_rows [B,S], -1 padded.  The _dev variant leaves the result in
+ * device memory for ctr_train_step_idx_dev / ctr_predict_idx_dev. */
+int ctr_ubcache_upload(ctr_handle* h, const int64_t* offsets, const int64_t* ts, const int32_t* item_rows, int64_t n_users, int64_t n);
+int ctr_ubcache_window(ctr_handle* h, const int32_t* user_row, const int64_t* max_ts, int32_t B, int32_t* hist_rows);
+int ctr_ubcache_window_dev(ctr_handle* h, const int32_t* d_user_row, const int64_t* d_max_ts, int32_t B, int32_t* d_hist_rows);
+
 /* utils.RocAuc32 (util.go:131-148 → nn/metrics/ranking.go:144): labels binarised at 0.5, tied
  * scores grouped, trapezoid. Sorted on the device. */
 int ctr_roc_auc(ctr_handle* h, const float* pred, const float* y, int64_t n, double* auc);

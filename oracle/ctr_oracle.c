@@ -599,28 +599,44 @@ float orc_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_state* 
     if (table_lr != 0.0f) {
         /* accumulate duplicates in (b, slot) order in double, then one SGD update per row.
          * Sparse: sort the (row, position) pairs instead of clearing an n_items x D accumulator. */
-        long npos = (long)B * (S + 1), m = 0;
-        orc_rp* rp = (orc_rp*)malloc(sizeof(orc_rp) * (size_t)npos);
-        for (long p = 0; p < npos; p++) {
-            int b = (int)(p / (S + 1)), sl = (int)(p % (S + 1));
-            int32_t row = sl < S ? hist[(long)b * S + sl] : item_row[b];
-            if (row >= 0) { rp[m].row = row; rp[m].pos = p; m++; }
-        }
-        qsort(rp, (size_t)m, sizeof(orc_rp), orc_cmp_rp);
-        for (long i = 0; i < m;) {
-            long j = i; double acc[512];
-            for (int k = 0; k < D; k++) acc[k] = 0.0;
-            while (j < m && rp[j].row == rp[i].row) {
-                int b = (int)(rp[j].pos / (S + 1)), sl = (int)(rp[j].pos % (S + 1));
-                const float* gsrc = sl < S ? dUb + ((long)b * S + sl) * D : dIt + (long)b * D;
-                for (int k = 0; k < D; k++) acc[k] += (double)gsrc[k];
-                j++;
+        long npos = (long)B * (S + 1);
+        int T = 1;
+#ifdef _OPENMP
+        T = omp_get_max_threads();
+#endif
+        /* every thread owns the rows with row % T == tid: it collects their (row, position) pairs in
+         * position order, sorts by row (stable through the pos key) and applies its rows' updates */
+#pragma omp parallel num_threads(T)
+        {
+            int tid = 0;
+#ifdef _OPENMP
+            tid = omp_get_thread_num();
+#endif
+            long m = 0, cap = npos / T + 1024;
+            orc_rp* rp = (orc_rp*)malloc(sizeof(orc_rp) * (size_t)cap);
+            for (long p = 0; p < npos; p++) {
+                int b = (int)(p / (S + 1)), sl = (int)(p % (S + 1));
+                int32_t row = sl < S ? hist[(long)b * S + sl] : item_row[b];
+                if (row < 0 || row % T != tid) continue;
+                if (m == cap) { cap *= 2; rp = (orc_rp*)realloc(rp, sizeof(orc_rp) * (size_t)cap); }
+                rp[m].row = row; rp[m].pos = p; m++;
             }
-            float* e = item_emb + (long)rp[i].row * lde;
-            for (int k = 0; k < D; k++) e[k] = (float)((double)e[k] - (double)table_lr * acc[k]);
-            i = j;
+            qsort(rp, (size_t)m, sizeof(orc_rp), orc_cmp_rp);
+            for (long i = 0; i < m;) {
+                long j = i; double acc[512];
+                for (int k = 0; k < D; k++) acc[k] = 0.0;
+                while (j < m && rp[j].row == rp[i].row) {
+                    int b = (int)(rp[j].pos / (S + 1)), sl = (int)(rp[j].pos % (S + 1));
+                    const float* gsrc = sl < S ? dUb + ((long)b * S + sl) * D : dIt + (long)b * D;
+                    for (int k = 0; k < D; k++) acc[k] += (double)gsrc[k];
+                    j++;
+                }
+                float* e = item_emb + (long)rp[i].row * lde;
+                for (int k = 0; k < D; k++) e[k] = (float)((double)e[k] - (double)table_lr * acc[k]);
+                i = j;
+            }
+            free(rp);
         }
-        free(rp);
     }
     orc_ws_free(ws);
     free(X); free(g0); free(g1); free(g2); free(ga); free(dUb); free(dIt);

@@ -287,3 +287,32 @@ def test_pipelined_epoch_entry_matches_per_batch_steps():
     np.testing.assert_allclose(costs, np.array(want, np.float32), rtol=2e-5, atol=1e-6)
     for a, b_ in zip(engA.get_weights(), engB.get_weights()):
         assert_mostly_close(a, b_, 1e-3, 1e-4, 0.995, "weights after pipelined pass")
+
+
+def test_ubcache_window_on_device_matches_timeseq_filter():
+    """feature/ubcache TimeSeq.Filter (cache.go:71-94) for a batch on the device vs the oracle, including
+    the reference's own table (cache_test.go:9-38), maxTs == 0, unknown users and short histories."""
+    eng = g.Engine(g.engine.default_config(g.MODEL_DIN_COS, S=5, batch=8, pred_batch=8))
+    ts0 = np.array([10, 9, 8, 7, 6, 5, 4, 3, 2, 1], np.int64)
+    eng.ubcache_upload([0, 10], ts0, ts0.astype(np.int32))
+    got = eng.ubcache_window(np.zeros(4, np.int32), np.array([0, 5, 100, -3], np.int64))
+    assert got[0].tolist() == [10, 9, 8, 7, 6]            # Filter(0, 5)
+    assert got[1].tolist() == [5, 4, 3, 2, 1]             # Filter(5, 5)
+    assert got[2].tolist() == [10, 9, 8, 7, 6]
+    assert got[3].tolist() == [-1] * 5                    # nothing that old
+    rng = np.random.default_rng(0)
+    U, S = 300, 7
+    eng = g.Engine(g.engine.default_config(g.MODEL_DIN_COS, S=S, batch=8, pred_batch=8))
+    lens = rng.integers(0, 40, U); off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ts = np.concatenate([np.sort(rng.integers(1, 1000, n))[::-1] for n in lens]).astype(np.int64)
+    items = rng.integers(0, 5000, ts.size).astype(np.int32)
+    eng.ubcache_upload(off, ts, items)
+    ub = rng.integers(-1, U + 2, 2000).astype(np.int32); mt = rng.integers(0, 1100, 2000).astype(np.int64); mt[::9] = 0
+    got = eng.ubcache_window(ub, mt)
+    for b in range(2000):
+        want = [-1] * S
+        if 0 <= ub[b] < U and lens[ub[b]] > 0:
+            seg = ts[off[ub[b]]:off[ub[b] + 1]]
+            start, cnt = orc.ub_filter(seg, int(mt[b]), S)
+            want[:cnt] = items[off[ub[b]] + start: off[ub[b]] + start + cnt].tolist()
+        assert got[b].tolist() == want, (b, ub[b], mt[b])
