@@ -123,3 +123,48 @@ float orc_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_state* 
 }
 #endif
 #endif
+
+/* ============================================================================================== *
+ * item2vec (BASELINE config 5): embedding.TrainEmbedding (wordemb.go:9-32) =
+ * wego word2vec SkipGram + HierarchicalSoftmax, float64, restated single-threaded.
+ * PARITY UNPINNED: the reference's tests assert only dimensions / non-zero vectors
+ * (wordemb_test.go:23) and the trainer is Hogwild + time-seeded (racy global LCG modelutil.go:22-29,
+ * math/rand init word2vec.go:103-111) — not reproducible even against itself.
+ * ============================================================================================== */
+#ifndef CTR_ORACLE_I2V_H
+#define CTR_ORACLE_I2V_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct {
+    int dim, window, iter;       /* wordemb.go:9: (window, dim, iter) ; rcmd.go:22-26: 16, 5, 1 */
+    int min_count, max_depth;    /* options.go: 5, 100 */
+    double init_lr, min_lr;      /* 0.025, 0.025e-4 */
+    double subsample;            /* 1e-3 */
+    int update_lr_batch;         /* 100000 */
+    uint32_t seed;
+    int rng_mode;                /* 0: del from the global LCG in token order (modelutil.go:26-29), 1: counter RNG per position (the parallelisable spec the engine uses) */
+} orc_i2v_cfg;
+
+/* Huffman tree exactly as dictionary.HuffnamTree builds it (huffman.go:23-57): stable sort by count,
+ * merge the two smallest, insert the merged node before the first node with Val >= merged.Val.
+ * parent[2V-1]: nodes 0..V-1 are the words, V..2V-2 the merged nodes in creation order (root = 2V-2,
+ * parent[root] = -1); code[2V-1]: 0 = left, 1 = right.  literal != 0 uses the reference's O(V^2) array
+ * procedure, 0 an O(V log V) equivalent.  V >= 2. */
+void orc_i2v_huffman(const int64_t* count, int V, int literal, int32_t* parent, uint8_t* code);
+/* path of word w: inner nodes from the root down, truncated like Node.GetPath(max_depth)
+ * (node.go:26-43): returns n = number of (node, child code) steps, node ids are merged-node indices
+ * 0..V-2 */
+int orc_i2v_path(const int32_t* parent, const uint8_t* code, int V, int w, int max_depth, int32_t* nodes, uint8_t* codes);
+/* full trainer.  tokens: word ids in [0,V) in corpus order (dictionary.Add assigns ids by first
+ * appearance, dictionary.go:70-81).  emb_out [V, dim] float32 (GenEmbeddingMap32, word2vec.go:298).
+ * syn1_out (may be NULL) [V-1, dim] float64 inner-node vectors.  Returns trained positions. */
+long orc_i2v_train(const orc_i2v_cfg* c, const int32_t* tokens, long n, int V, float* emb_out, double* syn1_out);
+/* the 1000-entry sigmoid table (sigmoid_table.go:28-45) */
+double orc_i2v_sigmoid_lut(double x);
+/* initial embedding value of element i: (u - 0.5)/dim with the counter RNG (word2vec.go:103-111 uses math/rand) */
+double orc_i2v_init(uint32_t seed, long i, int dim);
+#ifdef __cplusplus
+}
+#endif
+#endif

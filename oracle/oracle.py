@@ -16,7 +16,7 @@ YOUTUBE, DIN_COS, DIN_EUC = 0, 1, 2
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("ctr_oracle.c", "ctr_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ctr_oracle.c", "i2v_oracle.c", "ctr_oracle.h", "Makefile")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src)):
         return _SO
@@ -68,6 +68,11 @@ def lib():
         L.orc_backward.restype = C.c_float
         L.orc_train_step_idx.restype = C.c_float
         L.orc_hash_onehot32.argtypes = [C.c_char_p, C.c_int]
+        L.orc_i2v_train.restype = C.c_long
+        L.orc_i2v_sigmoid_lut.restype = C.c_double
+        L.orc_i2v_sigmoid_lut.argtypes = [C.c_double]
+        L.orc_i2v_init.restype = C.c_double
+        L.orc_i2v_init.argtypes = [C.c_uint32, C.c_long, C.c_int]
         _lib = L
     return _lib
 
@@ -289,3 +294,39 @@ class IdxTrainer:
             self.emb.ctypes.data_as(_fp), C.c_long(self.emb.shape[1]), C.c_long(self.emb.shape[0]),
             urp, irp, hsp, yp, C.c_int(B), C.c_float(table_lr), p.ctypes.data_as(_fp), C.c_int(nthreads))
         return float(cost), p
+
+
+# ---- item2vec (BASELINE config 5) -----------------------------------------------------------------
+class I2vCfg(C.Structure):
+    _fields_ = [("dim", C.c_int), ("window", C.c_int), ("iter", C.c_int), ("min_count", C.c_int), ("max_depth", C.c_int),
+                ("init_lr", C.c_double), ("min_lr", C.c_double), ("subsample", C.c_double), ("update_lr_batch", C.c_int),
+                ("seed", C.c_uint32), ("rng_mode", C.c_int)]
+
+
+def i2v_cfg(dim=16, window=5, iters=1, min_count=5, max_depth=100, init_lr=0.025, subsample=1e-3, seed=0, rng_mode=1):
+    """embedding.TrainEmbedding's fixed options (wordemb.go:9-32, options.go:41-60)."""
+    return I2vCfg(dim, window, iters, min_count, max_depth, init_lr, init_lr * 1e-4, subsample, 100000, seed, rng_mode)
+
+
+def i2v_huffman(count, literal=True):
+    cnt = np.ascontiguousarray(count, np.int64); V = cnt.size
+    parent = np.empty(2 * V - 1, np.int32); code = np.empty(2 * V - 1, np.uint8)
+    lib().orc_i2v_huffman(cnt.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(V), C.c_int(int(literal)),
+                          parent.ctypes.data_as(_ip), code.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return parent, code
+
+
+def i2v_path(parent, code, V, w, max_depth=100):
+    nodes = np.empty(4096, np.int32); codes = np.empty(4096, np.uint8)
+    n = lib().orc_i2v_path(parent.ctypes.data_as(_ip), code.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int(V), C.c_int(w),
+                           C.c_int(max_depth), nodes.ctypes.data_as(_ip), codes.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return nodes[:n].copy(), codes[:n].copy()
+
+
+def i2v_train(cfg, tokens, V, want_syn1=False):
+    tok, tp = _i(tokens)
+    emb = np.empty((V, cfg.dim), np.float32)
+    syn1 = np.zeros((max(V - 1, 1), cfg.dim), np.float64) if want_syn1 else None
+    trained = lib().orc_i2v_train(C.byref(cfg), tp, C.c_long(tok.size), C.c_int(V), emb.ctypes.data_as(_fp),
+                                  syn1.ctypes.data_as(C.POINTER(C.c_double)) if want_syn1 else None)
+    return (emb, syn1, trained) if want_syn1 else (emb, trained)
