@@ -7,6 +7,7 @@
 #include "umma_gemm.cuh"
 #include "auc.cuh"
 #include "ubcache.cuh"
+#include "item2vec.cuh"
 #include "comm.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -1121,6 +1122,151 @@ int ctr_roc_auc(ctr_handle* h, const float* pred, const float* y, int64_t n, dou
     std::lock_guard<std::mutex> lk(h->mu);
     CU(h, cudaSetDevice(h->dev));
     { cudaError_t e = auc_run(h->stream, pred, y, (long)n, auc); if (e != cudaSuccess) return set_err(h, CTR_ECUDA, "auc: %s", cudaGetErrorString(e)); return CTR_OK; }
+}
+
+void ctr_i2v_config_default(ctr_i2v_config* c) {
+    memset(c, 0, sizeof *c);
+    c->dim = 16; c->window = 5; c->iter = 1;                  // rcmd.go:22-26, 543
+    c->min_count = 5; c->max_depth = 100;                      // options.go:47-48
+    c->init_lr = 0.025f; c->min_lr = 0.025f * 1.0e-4f; c->subsample = 1.0e-3f; c->update_lr_batch = 100000;
+    c->seed = 0; c->device = 0;
+}
+
+int ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, int32_t V, float* emb_out, ctr_i2v_stats* stats) {
+    if (!cfg || !tokens || !emb_out || n < 1 || V < 2) return set_err(nullptr, CTR_EINVAL, "bad item2vec arguments");
+    const ctr_i2v_config& c = *cfg;
+    const int D = c.dim, W = c.window;
+    if (D < 4 || D > 128 || (D & (D - 1)) || W < 1 || c.iter < 1 || c.max_depth < 2 || c.update_lr_batch < 1)
+        return set_err(nullptr, CTR_EINVAL, "item2vec: dim must be a power of two in [4,128], window/iter >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_err(nullptr, CTR_ENODEV, "no CUDA device: this engine has no CPU fallback"); }
+#define CI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = set_err(nullptr, CTR_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); goto done; } } while (0)
+    int rc = CTR_OK;
+    // ---- host: dictionary counts, MinCount filter, subsample thresholds, Huffman paths
+    std::vector<int64_t> cnt((size_t)V, 0);
+    for (int64_t i = 0; i < n; i++) { if (tokens[i] < 0 || tokens[i] >= V) return set_err(nullptr, CTR_EINVAL, "token %lld outside [0, vocab)", (long long)i); cnt[(size_t)tokens[i]]++; }
+    std::vector<int> doc; doc.reserve((size_t)n);
+    for (int64_t i = 0; i < n; i++) if (!(0 <= c.min_count && cnt[(size_t)tokens[i]] < c.min_count)) doc.push_back(tokens[i]);   // cpsutil.go:74-78
+    const long nd = (long)doc.size();
+    std::vector<double> z((size_t)V);
+    for (int i = 0; i < V; i++) { double v = cnt[(size_t)i] > 0 ? 1.0 - std::sqrt((double)c.subsample / (double)cnt[(size_t)i]) : 0.0; z[(size_t)i] = v < 0 ? 0 : v; }
+    // Huffman (huffman.go:23-57): stable order by count; merged nodes are created in non-decreasing value
+    // order and inserted before every queued node of equal value, so they win ties and equal-valued merged
+    // nodes pop newest-first
+    std::vector<int> parent((size_t)2 * V - 1, -1); std::vector<unsigned char> code((size_t)2 * V - 1, 0);
+    std::vector<int64_t> node_val((size_t)V - 1, 0);       // subtree frequency of every merged node
+    {
+        std::vector<int> leaves((size_t)V);
+        for (int i = 0; i < V; i++) leaves[(size_t)i] = i;
+        std::stable_sort(leaves.begin(), leaves.end(), [&](int x, int y) { return cnt[(size_t)x] < cnt[(size_t)y]; });
+        std::vector<std::pair<int64_t, int>> mq; mq.reserve((size_t)V);      // (value, node id), pop order = front..back
+        size_t lh = 0, mh = 0; int next_id = V;
+        for (int made = 0; made < V - 1; made++) {
+            std::pair<int64_t, int> pick[2];
+            for (int k = 0; k < 2; k++) {
+                const bool use_m = mh < mq.size() && (lh >= (size_t)V || mq[mh].first <= cnt[(size_t)leaves[lh]]);
+                if (use_m) pick[k] = mq[mh++]; else { pick[k] = {cnt[(size_t)leaves[lh]], leaves[lh]}; lh++; }
+            }
+            const int64_t val = pick[0].first + pick[1].first; const int id = next_id++;
+            node_val[(size_t)(id - V)] = val;
+            code[(size_t)pick[0].second] = 0; code[(size_t)pick[1].second] = 1;
+            parent[(size_t)pick[0].second] = id; parent[(size_t)pick[1].second] = id;
+            size_t pos = mq.size();
+            while (pos > mh && mq[pos - 1].first >= val) pos--;
+            mq.insert(mq.begin() + (long)pos, {val, id});
+        }
+    }
+    std::vector<long long> poff((size_t)V + 1, 0); std::vector<int> pnode; std::vector<unsigned char> pcode;
+    {
+        std::vector<int> chain;
+        for (int w = 0; w < V; w++) {                      // Node.GetPath(maxDepth), node.go:26-43
+            chain.clear();
+            for (int p = w; p != -1; p = parent[(size_t)p]) chain.push_back(p);
+            const int len = (int)chain.size(), depth = std::min(c.max_depth, len);
+            for (int i = 0; i < depth - 1; i++) { pnode.push_back(chain[(size_t)(len - 1 - i)] - V); pcode.push_back(code[(size_t)chain[(size_t)(len - 2 - i)]]); }
+            poff[(size_t)w + 1] = (long long)pnode.size();
+        }
+    }
+    std::vector<float> lut(1000);
+    for (int i = 0; i < 1000; i++) { double e = std::exp(((double)i / 1000.0 * 2.0 - 1.0) * 6.0); lut[(size_t)i] = (float)(e / (e + 1.0)); }
+    // ---- device
+    int *d_doc = nullptr, *d_pnode = nullptr; double* d_z = nullptr; long long* d_poff = nullptr; unsigned char* d_pcode = nullptr;
+    float *d_syn0 = nullptr, *d_syn1 = nullptr, *d_lr = nullptr, *d_nsc = nullptr, *d_wsc = nullptr; unsigned long long* d_cnt = nullptr;
+    cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms_total = 0; int launches = 0; unsigned long long hc[3] = {0, 0, 0};
+    {
+        CI(cudaSetDevice(c.device));
+        cudaDeviceProp prop{}; CI(cudaGetDeviceProperties(&prop, c.device));
+        if (prop.major != 10) { rc = set_err(nullptr, CTR_ENODEV, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor); goto done; }
+        CI(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); CI(cudaEventCreate(&e0)); CI(cudaEventCreate(&e1));
+        CI(cudaMalloc(&d_doc, sizeof(int) * (size_t)std::max<long>(nd, 1))); CI(cudaMalloc(&d_z, sizeof(double) * (size_t)V));
+        CI(cudaMalloc(&d_poff, sizeof(long long) * ((size_t)V + 1))); CI(cudaMalloc(&d_pnode, sizeof(int) * std::max<size_t>(pnode.size(), 1)));
+        CI(cudaMalloc(&d_pcode, std::max<size_t>(pcode.size(), 1))); CI(cudaMalloc(&d_syn0, sizeof(float) * (size_t)V * D));
+        CI(cudaMalloc(&d_syn1, sizeof(float) * (size_t)(V - 1) * D)); CI(cudaMalloc(&d_cnt, 3 * sizeof(unsigned long long)));
+        const long nchunks = nd / c.update_lr_batch + 2;
+        CI(cudaMalloc(&d_lr, sizeof(float) * (size_t)nchunks));
+        if (nd > 0) CI(cudaMemcpyAsync(d_doc, doc.data(), sizeof(int) * (size_t)nd, cudaMemcpyHostToDevice, st));
+        CI(cudaMemcpyAsync(d_z, z.data(), sizeof(double) * (size_t)V, cudaMemcpyHostToDevice, st));
+        CI(cudaMemcpyAsync(d_poff, poff.data(), sizeof(long long) * ((size_t)V + 1), cudaMemcpyHostToDevice, st));
+        if (!pnode.empty()) { CI(cudaMemcpyAsync(d_pnode, pnode.data(), sizeof(int) * pnode.size(), cudaMemcpyHostToDevice, st)); CI(cudaMemcpyAsync(d_pcode, pcode.data(), pcode.size(), cudaMemcpyHostToDevice, st)); }
+        CI(cudaMemcpyToSymbolAsync(c_i2v_lut, lut.data(), sizeof(float) * 1000, 0, cudaMemcpyHostToDevice, st));
+        CI(cudaMemsetAsync(d_syn1, 0, sizeof(float) * (size_t)(V - 1) * D, st));       // huffman.go:40
+        CI(cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), st));
+        k_i2v_init<<<prop.multiProcessorCount * 8, 256, 0, st>>>(d_syn0, (long)V * D, D, c.seed); launches++;
+        // concurrency: (centre, context) pairs in flight ~ vocabulary / 4, at most the whole machine
+        const int rpw = 32 / (D / 4);
+        const long max_warps = (long)prop.multiProcessorCount * 8 * 8;
+        const long warps = std::max<long>(1, std::min<long>(std::min<long>(max_warps, (nd + 63) / 64), std::max<long>(1, (long)V / 4 / rpw)));
+        const int grid = (int)((warps + 7) / 8);
+        const double Ceff = (double)grid * 8 * rpw;
+        {
+            double total = 0; for (int i = 0; i < V; i++) total += (double)cnt[(size_t)i];
+            std::vector<float> nsc((size_t)V - 1), wsc((size_t)V);
+            for (int i = 0; i < V - 1; i++) nsc[(size_t)i] = (float)(1.0 / std::max(1.0, Ceff * (double)node_val[(size_t)i] / total));
+            for (int i = 0; i < V; i++) wsc[(size_t)i] = (float)(1.0 / std::max(1.0, Ceff * (double)cnt[(size_t)i] / total));
+            CI(cudaMalloc(&d_nsc, sizeof(float) * ((size_t)V - 1))); CI(cudaMalloc(&d_wsc, sizeof(float) * (size_t)V));
+            CI(cudaMemcpyAsync(d_nsc, nsc.data(), sizeof(float) * ((size_t)V - 1), cudaMemcpyHostToDevice, st));
+            CI(cudaMemcpyAsync(d_wsc, wsc.data(), sizeof(float) * (size_t)V, cudaMemcpyHostToDevice, st));
+            CI(cudaStreamSynchronize(st));
+        }
+        std::vector<float> lr_tab((size_t)nchunks);
+        double lr = c.init_lr;                                                           // w.currentlr persists across iterations
+        for (int it = 0; it < c.iter; it++) {
+            for (long k = 0; k < nchunks; k++) {                                         // observe(), word2vec.go:223-233
+                lr_tab[(size_t)k] = (float)lr;
+                const double seen = (double)(k + 1) * c.update_lr_batch;
+                if (seen <= (double)nd) lr = lr < (double)c.min_lr ? (double)c.min_lr : (double)c.init_lr * (1.0 - seen / (double)n);
+            }
+            CI(cudaMemcpyAsync(d_lr, lr_tab.data(), sizeof(float) * (size_t)nchunks, cudaMemcpyHostToDevice, st));
+            I2vArgs a{}; a.doc = d_doc; a.nd = nd; a.z = d_z; a.poff = d_poff; a.pnode = d_pnode; a.pcode = d_pcode; a.syn0 = d_syn0; a.syn1 = d_syn1;
+            a.D = D; a.W = W; a.lr_tab = d_lr; a.upd = c.update_lr_batch; a.seed = c.seed; a.iter = it; a.counters = d_cnt;
+            a.node_scale = d_nsc; a.word_scale = d_wsc;
+            CI(cudaEventRecord(e0, st));
+            switch (D / 4) {
+                case 1: k_i2v_skipgram_hs<1><<<grid, 256, 0, st>>>(a); break;   case 2: k_i2v_skipgram_hs<2><<<grid, 256, 0, st>>>(a); break;
+                case 4: k_i2v_skipgram_hs<4><<<grid, 256, 0, st>>>(a); break;   case 8: k_i2v_skipgram_hs<8><<<grid, 256, 0, st>>>(a); break;
+                case 16: k_i2v_skipgram_hs<16><<<grid, 256, 0, st>>>(a); break; default: k_i2v_skipgram_hs<32><<<grid, 256, 0, st>>>(a); break;
+            }
+            launches++;
+            CI(cudaGetLastError());
+            CI(cudaEventRecord(e1, st)); CI(cudaStreamSynchronize(st));                   // lr_tab is reused by the next iteration
+            float ms = 0; CI(cudaEventElapsedTime(&ms, e0, e1)); ms_total += ms;
+        }
+        CI(cudaMemcpyAsync(emb_out, d_syn0, sizeof(float) * (size_t)V * D, cudaMemcpyDeviceToHost, st));
+        CI(cudaMemcpyAsync(hc, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st));
+        CI(cudaStreamSynchronize(st));
+        if (stats) {
+            stats->doc_len = nd; stats->trained_positions = (int64_t)hc[0]; stats->pairs = (int64_t)hc[1]; stats->node_visits = (int64_t)hc[2];
+            stats->algorithmic_bytes = 2.0 * D * 4.0 * ((double)hc[1] + (double)hc[2]); stats->ms_device = ms_total; stats->launches = launches;
+        }
+    }
+done:
+#undef CI
+    for (void* p : {(void*)d_doc, (void*)d_z, (void*)d_poff, (void*)d_pnode, (void*)d_pcode, (void*)d_syn0, (void*)d_syn1, (void*)d_lr, (void*)d_cnt, (void*)d_nsc, (void*)d_wsc}) if (p) cudaFree(p);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return rc;
 }
 
 int ctr_comm_unique_id(void* id_out, int32_t* id_bytes) { return comm_unique_id(id_out, id_bytes); }

@@ -1,0 +1,108 @@
+// item2vec.cuh — embedding.TrainEmbedding (feature/embedding/wordemb.go:9-32) on the device: wego word2vec
+// SkipGram + HierarchicalSoftmax (model/word2vec/model.go:48-78, optimizer.go:107-129).  BASELINE config 5,
+// SURVEY.md §8f row f1.  The dictionary counts, MinCount filter, Huffman tree (the reference's insertion
+// procedure, huffman.go:23-57, in O(V log V)) and the per-word root→leaf paths are built on the host;
+// both vector tables live in HBM: syn0 [V,D] (the item embeddings) and syn1 [V-1,D] (inner nodes).
+//
+// Kernel: one warp per centre position, Hogwild like the reference's goroutines (word2vec.go:165-169) but
+// ~10^4 positions in flight.  A vector of D = 4*LPR floats is held by LPR lanes, so a warp walks the
+// centre's Huffman path for 32/LPR contexts at once: per node one 128-bit load, a group dot product,
+// the 1000-entry sigmoid table, a register axpy into tmp and a red.global.add.v4.f32 into the node
+// vector; the context row takes tmp with one more red.add.  HBM/L2-bound: 2*D*4 bytes per visited node.
+//
+// Staleness compensation.  Sequential SGD (and the reference's <=NumCPU Hogwild goroutines) lets every
+// update of the root see the previous one; with C (centre, context) pairs in flight the root would take
+// C stale steps at once and |f| overshoots the +-6 cut-off for good.  So a vector that a fraction p of
+// all pairs touches is stepped with lr / max(1, C*p): the C*p concurrent gradients are averaged rather
+// than summed — top Huffman nodes (p = subtree frequency) and very frequent context items are damped,
+// rare nodes and items (C*p < 1) get the exact update.  C itself is kept proportional to the vocabulary
+// (small corpora run almost sequentially).  Deliberate adaptation to 10^3..10^5-way concurrency; quality is
+// checked against the sequential float64 oracle (tests/test_gpu_i2v.py).
+#pragma once
+#include "common.cuh"
+
+namespace ctr {
+
+__constant__ float c_i2v_lut[1000];       // sigmoid_table.go:28-45
+
+struct I2vArgs {
+    const int* doc; long nd;              // MinCount-filtered token ids
+    const double* z;                      // [V] subsample keep threshold (subsample.go:34-38)
+    const long long* poff; const int* pnode; const unsigned char* pcode;   // path CSR per word
+    float* syn0; float* syn1; int D, W;
+    const float* lr_tab; int upd;         // lr of positions [k*upd, (k+1)*upd)
+    const float* node_scale;              // [V-1] 1/max(1, C*p_node)
+    const float* word_scale;              // [V]   1/max(1, C*p_word)
+    uint32_t seed; int iter;
+    unsigned long long* counters;         // [0] trained positions, [1] (centre, context) pairs, [2] node visits
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_i2v_skipgram_hs(I2vArgs a) {
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, lir = lane % LPR, sub = lane / LPR;
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    unsigned long long n_tr = 0, n_pair = 0, n_node = 0;
+    for (long pos = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pos < a.nd; pos += nwarps) {
+        const int id = a.doc[pos];
+        // Subsampler.Trial (subsample.go:45-52): train when z[id] > U[0,1)
+        const double u = (double)(mix64(a.seed, 200u + (uint32_t)a.iter, (uint64_t)pos) >> 11) * (1.0 / 9007199254740992.0);
+        if (!(a.z[id] > u)) continue;
+        const int del = (int)(mix64(a.seed, 300u + (uint32_t)a.iter, (uint64_t)pos) % (uint64_t)a.W);   // modelutil.NextRandom(window)
+        const float lr = a.lr_tab[pos / a.upd];
+        const long long p0 = a.poff[id]; const int np = (int)(a.poff[id + 1] - p0);
+        const int nctx = 2 * (a.W - del);                                   // a in [del, 2W+1-del), a != W
+        n_tr++;
+        for (int k0 = 0; k0 < nctx; k0 += RPW) {
+            const int k = k0 + sub;
+            int aa = del + k; if (aa >= a.W) aa++;
+            const long cpos = pos - a.W + aa;
+            const bool active = k < nctx && cpos >= 0 && cpos < a.nd;       // model.go:63-66
+            const int cid = active ? a.doc[cpos] : 0;
+            float* cptr = a.syn0 + (long)cid * a.D + lir * 4;
+            const float4 c = active ? *reinterpret_cast<const float4*>(cptr) : zero4();
+            float4 tmp = zero4();
+            bool alive = active;
+            if (active && lir == 0) n_pair++;
+            for (int i = 0; i < np; i++) {                                  // optimizer.go:113-128
+                if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+                const int node = a.pnode[p0 + i];
+                float* nptr = a.syn1 + (long)node * a.D + lir * 4;
+                const float4 nv = *reinterpret_cast<const float4*>(nptr);
+                const float f = group_sum<LPR>(dot4(c, nv));
+                if (alive && (f <= -6.0f || f >= 6.0f)) alive = false;      // `return`: the rest of the path is abandoned
+                if (alive) {
+                    const float g = (1.0f - (float)a.pcode[p0 + i] - c_i2v_lut[(int)((f + 6.0f) * (1000.0f / 6.0f / 2.0f))]) * lr;
+                    tmp = fma4(g, nv, tmp);
+                    const float gs = g * __ldg(a.node_scale + node);
+                    red_add4(nptr, make_float4(gs * c.x, gs * c.y, gs * c.z, gs * c.w));
+                    if (lir == 0) n_node++;
+                }
+            }
+            if (active) {                                                   // model.go:74-76
+                const float ws = __ldg(a.word_scale + cid);
+                red_add4(cptr, make_float4(ws * tmp.x, ws * tmp.y, ws * tmp.z, ws * tmp.w));
+            }
+        }
+    }
+    n_tr = (lane == 0) ? n_tr : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+        n_pair += __shfl_xor_sync(0xffffffffu, n_pair, o); n_node += __shfl_xor_sync(0xffffffffu, n_node, o);
+    }
+    if (lane == 0) {
+        if (n_tr) atomicAdd(a.counters + 0, n_tr);
+        if (n_pair) atomicAdd(a.counters + 1, n_pair);
+        if (n_node) atomicAdd(a.counters + 2, n_node);
+    }
+}
+
+// syn0 = (U[0,1) - 0.5) / dim (word2vec.go:103-111) with the counter RNG
+__global__ void k_i2v_init(float* __restrict__ syn0, long n, int D, uint32_t seed) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const double u = (double)(mix64(seed, 100u, (uint64_t)i) >> 11) * (1.0 / 9007199254740992.0);
+        syn0[i] = (float)((u - 0.5) / (double)D);
+    }
+}
+
+}  // namespace ctr

@@ -6,3 +6,4 @@ __path__ = [_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__f
 
 from .engine import *          # noqa: F401,F403,E402
 from .model import *           # noqa: F401,F403,E402
+from .item2vec import *        # noqa: F401,F403,E402

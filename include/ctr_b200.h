@@ -179,6 +179,35 @@ int ctr_ubcache_window_dev(ctr_handle* h, const int32_t* d_user_row, const int64
  * scores grouped, trapezoid. Sorted on the device. */
 int ctr_roc_auc(ctr_handle* h, const float* pred, const float* y, int64_t n, double* auc);
 
+/* ---- item2vec (BASELINE config 5) ------------------------------------------------
+ * embedding.TrainEmbedding(ch, window, dim, iter) (feature/embedding/wordemb.go:9-32): SkipGram +
+ * HierarchicalSoftmax word2vec over the users' item sequences; its output is the ITEM_EMB table the hot
+ * path gathers from (recommend.Train, rcmd.go:207-213).  tokens are word ids in [0, vocab) in corpus
+ * order — ids are assigned by first appearance, as dictionary.Add does (dictionary.go:70-81); the Go side
+ * keeps the string↔id map.  emb_out [vocab, dim] float32 == GenEmbeddingMap32 (word2vec.go:298-324);
+ * words rarer than min_count keep their initial vector (they are filtered from the training document only,
+ * memory.go:53-62).  Stand-alone call: no handle; errors via ctr_last_error(NULL). */
+typedef struct {
+    int32_t dim, window, iter;            /* rcmd.go:22-26: 16, 5 ; iter 1 (rcmd.go:543) */
+    int32_t min_count, max_depth;         /* options.go: 5, 100 */
+    float   init_lr, min_lr, subsample;   /* 0.025, 0.025e-4, 1e-3 */
+    int32_t update_lr_batch;              /* 100000 */
+    uint32_t seed;
+    int32_t device;
+    int32_t reserved[8];
+} ctr_i2v_config;
+typedef struct {
+    int64_t doc_len;                      /* tokens left after the MinCount filter */
+    int64_t trained_positions;            /* positions that passed the subsampling trial, all iterations */
+    int64_t pairs, node_visits;           /* (centre, context) pairs trained; Huffman nodes updated */
+    double  algorithmic_bytes;            /* 2*dim*4 * (node_visits + pairs): row read-modify-writes */
+    float   ms_device;                    /* device time of the training kernels */
+    int32_t launches;
+} ctr_i2v_stats;
+void ctr_i2v_config_default(ctr_i2v_config* cfg);
+int  ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, int32_t vocab,
+                   float* emb_out, ctr_i2v_stats* stats);
+
 /* Multi-GPU (world > 1): one handle per rank/process.  The id is ncclUniqueId bytes produced on
  * rank 0 by ctr_comm_unique_id and distributed by the host (torch.distributed / Go). */
 int ctr_comm_unique_id(void* id_out, int32_t* id_bytes /* in: capacity, out: used */);
