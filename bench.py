@@ -172,7 +172,9 @@ def run_item2vec(args):
     V, n, D = args.i2v_vocab, args.i2v_tokens, args.i2v_dim
     rng = np.random.default_rng(42)
     # Zipf(1.0)-like item popularity over V items, ids by first appearance are not required by the engine
-    toks = (np.floor(np.exp(rng.random(n) * np.log(V))).astype(np.int64) - 1).clip(0, V - 1).astype(np.int32)
+    raw = (np.floor(np.exp(rng.random(n) * np.log(V))).astype(np.int64) - 1).clip(0, V - 1)
+    uniq, toks = np.unique(raw, return_inverse=True)              # the dictionary holds only words that occur (dictionary.go:70-81)
+    toks = toks.astype(np.int32); V = int(uniq.size)
     hbm_peak, peak_src = load_peaks()
     if args.impl == "reference":
         m = min(n, args.i2v_cpu_tokens)

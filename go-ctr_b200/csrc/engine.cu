@@ -630,6 +630,55 @@ void gaussian_fill(std::vector<float>& w, uint32_t seed, uint32_t stream) {
 
 #include "comm_impl.cuh"
 
+// item2vec host plan: Huffman tree as dictionary.HuffnamTree builds it (huffman.go:23-57) and every word's
+// root→leaf path as Node.GetPath(maxDepth) returns it (node.go:26-43), as a CSR of (inner node, child code).
+static void i2v_build_paths(const std::vector<int64_t>& cnt, int V, int max_depth, std::vector<int64_t>& node_val,
+                            std::vector<long long>& poff, std::vector<int>& pnode, std::vector<unsigned char>& pcode) {
+    node_val.assign((size_t)V - 1, 0);
+    poff.assign((size_t)V + 1, 0); pnode.clear(); pcode.clear();
+    ctr_config dummy; (void)dummy;
+    struct { int max_depth; } c{max_depth};
+    // Huffman (huffman.go:23-57): stable order by count; merged nodes are created in non-decreasing value
+    // order and inserted before every queued node of equal value, so they win ties and equal-valued merged
+    // nodes pop newest-first
+    std::vector<int> parent((size_t)2 * V - 1, -1); std::vector<unsigned char> code((size_t)2 * V - 1, 0);
+    {
+        std::vector<int> leaves((size_t)V);
+        for (int i = 0; i < V; i++) leaves[(size_t)i] = i;
+        std::stable_sort(leaves.begin(), leaves.end(), [&](int x, int y) { return cnt[(size_t)x] < cnt[(size_t)y]; });
+        // merged queue as runs of equal value; inside a run the newest node pops first (it was inserted
+        // before the older equal-valued ones), runs themselves are in non-decreasing value order
+        struct Run { int64_t val; std::vector<int> ids; };
+        std::vector<Run> runs; size_t rh = 0;
+        size_t lh = 0; int next_id = V;
+        for (int made = 0; made < V - 1; made++) {
+            std::pair<int64_t, int> pick[2];
+            for (int k = 0; k < 2; k++) {
+                while (rh + 1 < runs.size() && runs[rh].ids.empty()) rh++;          // never step past the last run: it may refill
+                const bool use_m = rh < runs.size() && !runs[rh].ids.empty() && (lh >= (size_t)V || runs[rh].val <= cnt[(size_t)leaves[lh]]);
+                if (use_m) { pick[k] = {runs[rh].val, runs[rh].ids.back()}; runs[rh].ids.pop_back(); }
+                else { pick[k] = {cnt[(size_t)leaves[lh]], leaves[lh]}; lh++; }
+            }
+            const int64_t val = pick[0].first + pick[1].first; const int id = next_id++;
+            node_val[(size_t)(id - V)] = val;
+            code[(size_t)pick[0].second] = 0; code[(size_t)pick[1].second] = 1;
+            parent[(size_t)pick[0].second] = id; parent[(size_t)pick[1].second] = id;
+            if (!runs.empty() && runs.back().val == val) runs.back().ids.push_back(id);
+            else runs.push_back(Run{val, {id}});
+        }
+    }
+    {
+        std::vector<int> chain;
+        for (int w = 0; w < V; w++) {                      // Node.GetPath(maxDepth), node.go:26-43
+            chain.clear();
+            for (int p = w; p != -1; p = parent[(size_t)p]) chain.push_back(p);
+            const int len = (int)chain.size(), depth = std::min(c.max_depth, len);
+            for (int i = 0; i < depth - 1; i++) { pnode.push_back(chain[(size_t)(len - 1 - i)] - V); pcode.push_back(code[(size_t)chain[(size_t)(len - 2 - i)]]); }
+            poff[(size_t)w + 1] = (long long)pnode.size();
+        }
+    }
+}
+
 // =====================================================================================================
 extern "C" {
 
@@ -1124,6 +1173,17 @@ int ctr_roc_auc(ctr_handle* h, const float* pred, const float* y, int64_t n, dou
     { cudaError_t e = auc_run(h->stream, pred, y, (long)n, auc); if (e != cudaSuccess) return set_err(h, CTR_ECUDA, "auc: %s", cudaGetErrorString(e)); return CTR_OK; }
 }
 
+int ctr_i2v_paths(const int64_t* count, int32_t V, int32_t max_depth, int64_t* path_off, int32_t* path_node, uint8_t* path_code, int64_t cap) {
+    if (!count || !path_off || V < 2 || max_depth < 2) return set_err(nullptr, CTR_EINVAL, "bad item2vec path arguments");
+    std::vector<int64_t> cnt(count, count + V), node_val; std::vector<long long> poff; std::vector<int> pnode; std::vector<unsigned char> pcode;
+    i2v_build_paths(cnt, V, max_depth, node_val, poff, pnode, pcode);
+    for (int i = 0; i <= V; i++) path_off[i] = poff[(size_t)i];
+    if ((int64_t)pnode.size() > cap) return set_err(nullptr, CTR_EINVAL, "path buffers too small: need %lld", (long long)pnode.size());
+    if (path_node) memcpy(path_node, pnode.data(), sizeof(int) * pnode.size());
+    if (path_code) memcpy(path_code, pcode.data(), pcode.size());
+    return CTR_OK;
+}
+
 void ctr_i2v_config_default(ctr_i2v_config* c) {
     memset(c, 0, sizeof *c);
     c->dim = 16; c->window = 5; c->iter = 1;                  // rcmd.go:22-26, 543
@@ -1150,43 +1210,8 @@ int ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, i
     const long nd = (long)doc.size();
     std::vector<double> z((size_t)V);
     for (int i = 0; i < V; i++) { double v = cnt[(size_t)i] > 0 ? 1.0 - std::sqrt((double)c.subsample / (double)cnt[(size_t)i]) : 0.0; z[(size_t)i] = v < 0 ? 0 : v; }
-    // Huffman (huffman.go:23-57): stable order by count; merged nodes are created in non-decreasing value
-    // order and inserted before every queued node of equal value, so they win ties and equal-valued merged
-    // nodes pop newest-first
-    std::vector<int> parent((size_t)2 * V - 1, -1); std::vector<unsigned char> code((size_t)2 * V - 1, 0);
-    std::vector<int64_t> node_val((size_t)V - 1, 0);       // subtree frequency of every merged node
-    {
-        std::vector<int> leaves((size_t)V);
-        for (int i = 0; i < V; i++) leaves[(size_t)i] = i;
-        std::stable_sort(leaves.begin(), leaves.end(), [&](int x, int y) { return cnt[(size_t)x] < cnt[(size_t)y]; });
-        std::vector<std::pair<int64_t, int>> mq; mq.reserve((size_t)V);      // (value, node id), pop order = front..back
-        size_t lh = 0, mh = 0; int next_id = V;
-        for (int made = 0; made < V - 1; made++) {
-            std::pair<int64_t, int> pick[2];
-            for (int k = 0; k < 2; k++) {
-                const bool use_m = mh < mq.size() && (lh >= (size_t)V || mq[mh].first <= cnt[(size_t)leaves[lh]]);
-                if (use_m) pick[k] = mq[mh++]; else { pick[k] = {cnt[(size_t)leaves[lh]], leaves[lh]}; lh++; }
-            }
-            const int64_t val = pick[0].first + pick[1].first; const int id = next_id++;
-            node_val[(size_t)(id - V)] = val;
-            code[(size_t)pick[0].second] = 0; code[(size_t)pick[1].second] = 1;
-            parent[(size_t)pick[0].second] = id; parent[(size_t)pick[1].second] = id;
-            size_t pos = mq.size();
-            while (pos > mh && mq[pos - 1].first >= val) pos--;
-            mq.insert(mq.begin() + (long)pos, {val, id});
-        }
-    }
-    std::vector<long long> poff((size_t)V + 1, 0); std::vector<int> pnode; std::vector<unsigned char> pcode;
-    {
-        std::vector<int> chain;
-        for (int w = 0; w < V; w++) {                      // Node.GetPath(maxDepth), node.go:26-43
-            chain.clear();
-            for (int p = w; p != -1; p = parent[(size_t)p]) chain.push_back(p);
-            const int len = (int)chain.size(), depth = std::min(c.max_depth, len);
-            for (int i = 0; i < depth - 1; i++) { pnode.push_back(chain[(size_t)(len - 1 - i)] - V); pcode.push_back(code[(size_t)chain[(size_t)(len - 2 - i)]]); }
-            poff[(size_t)w + 1] = (long long)pnode.size();
-        }
-    }
+    std::vector<int64_t> node_val; std::vector<long long> poff; std::vector<int> pnode; std::vector<unsigned char> pcode;
+    i2v_build_paths(cnt, V, c.max_depth, node_val, poff, pnode, pcode);
     std::vector<float> lut(1000);
     for (int i = 0; i < 1000; i++) { double e = std::exp(((double)i / 1000.0 * 2.0 - 1.0) * 6.0); lut[(size_t)i] = (float)(e / (e + 1.0)); }
     // ---- device

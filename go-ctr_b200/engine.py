@@ -24,7 +24,7 @@ EXPORTS = ["ctr_abi_version", "ctr_config_default", "ctr_create", "ctr_destroy",
            "ctr_gather_rows", "ctr_train_dense", "ctr_predict_dense", "ctr_train_step_idx", "ctr_train_idx", "ctr_predict_idx",
            "ctr_train_step_idx_dev", "ctr_predict_idx_dev", "ctr_last_cost", "ctr_sync", "ctr_get_stream",
            "ctr_set_stream", "ctr_launch_count", "ctr_profile_enable", "ctr_profile_get", "ctr_profile_reset",
-           "ctr_profile_dump", "ctr_debug_grads_idx", "ctr_ubcache_upload", "ctr_ubcache_window", "ctr_ubcache_window_dev", "ctr_roc_auc", "ctr_i2v_config_default", "ctr_i2v_train", "ctr_comm_unique_id", "ctr_comm_init"]
+           "ctr_profile_dump", "ctr_debug_grads_idx", "ctr_ubcache_upload", "ctr_ubcache_window", "ctr_ubcache_window_dev", "ctr_roc_auc", "ctr_i2v_config_default", "ctr_i2v_paths", "ctr_i2v_train", "ctr_comm_unique_id", "ctr_comm_init"]
 
 
 class CtrError(RuntimeError):

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import engine as _e
 
-__all__ = ["I2vConfig", "I2vStats", "i2v_default_config", "i2v_train_ids", "TrainEmbedding", "EmbeddingModel"]
+__all__ = ["i2v_paths", "I2vConfig", "I2vStats", "i2v_default_config", "i2v_train_ids", "TrainEmbedding", "EmbeddingModel"]
 
 
 class I2vConfig(C.Structure):
@@ -33,6 +33,19 @@ def i2v_default_config(**kw):
             raise AttributeError(k)
         setattr(cfg, k, v)
     return cfg
+
+
+def i2v_paths(count, max_depth=100):
+    """Host-side Huffman paths of the trainer (no GPU needed): returns (path_off [V+1], nodes, codes)."""
+    L = _e.load_library()
+    cnt = np.ascontiguousarray(count, np.int64); V = cnt.size
+    cap = V * min(max_depth, 64) + 64
+    off = np.empty(V + 1, np.int64); nodes = np.empty(cap, np.int32); codes = np.empty(cap, np.uint8)
+    rc = L.ctr_i2v_paths(cnt.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int32(V), C.c_int32(max_depth), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                         nodes.ctypes.data_as(C.POINTER(C.c_int32)), codes.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(cap))
+    if rc != 0:
+        raise _e.CtrError(rc, L.ctr_last_error(None).decode())
+    return off, nodes[:off[-1]], codes[:off[-1]]
 
 
 def i2v_train_ids(tokens, vocab, cfg=None, **kw):

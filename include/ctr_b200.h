@@ -205,6 +205,10 @@ typedef struct {
     int32_t launches;
 } ctr_i2v_stats;
 void ctr_i2v_config_default(ctr_i2v_config* cfg);
+/* host-only: the Huffman paths the trainer walks — dictionary.HuffnamTree (huffman.go:23-57) +
+ * Node.GetPath(max_depth) (node.go:26-43) for word counts `count[vocab]`; path_off [vocab+1], then
+ * (inner node id in creation order, child code) per step.  Runs without a GPU (used by the CPU tests). */
+int  ctr_i2v_paths(const int64_t* count, int32_t vocab, int32_t max_depth, int64_t* path_off, int32_t* path_node, uint8_t* path_code, int64_t cap);
 int  ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, int32_t vocab,
                    float* emb_out, ctr_i2v_stats* stats);
 

@@ -52,23 +52,30 @@ void orc_i2v_huffman(const int64_t* count, int V, int literal, int32_t* parent, 
         /* equivalent without the O(V) shifts: merged values are produced in non-decreasing order, a new
          * merged node goes before every queued node of equal value (older merged nodes and leaves), so
          * merged nodes of equal value form a LIFO run and win ties against leaves */
-        hnode* mq = (hnode*)malloc(sizeof(hnode) * (size_t)V);     /* merged queue, runs stored so that head..tail is pop order */
-        int lh = 0, mh = 0, mt = 0;                                 /* leaf head, merged head/tail */
-        /* runs: we keep the queue as an array where equal-valued run is stored newest-first */
+        /* merged nodes are produced in non-decreasing value order; equal values form a run that behaves as
+         * a stack (the newest was inserted before the older ones).  Only the last run receives pushes and
+         * runs are popped from their top, so one array in creation order plus (start, top) per run suffices. */
+        hnode* mq = (hnode*)malloc(sizeof(hnode) * (size_t)V);
+        long* rstart = (long*)malloc(sizeof(long) * (size_t)V); long* rtop = (long*)malloc(sizeof(long) * (size_t)V);
+        long nruns = 0, hr = 0, mt = 0; int lh = 0;
         for (int made = 0; made < V - 1; made++) {
             hnode pick[2];
             for (int k = 0; k < 2; k++) {
-                int use_m = mh < mt && (lh >= V || mq[mh].val <= nodes[lh].val);
-                pick[k] = use_m ? mq[mh++] : nodes[lh++];
+                while (hr < nruns - 1 && rtop[hr] == rstart[hr]) hr++;
+                int have_m = hr < nruns && rtop[hr] > rstart[hr];
+                int use_m = have_m && (lh >= V || mq[rstart[hr]].val <= nodes[lh].val);
+                if (use_m) { pick[k] = mq[--rtop[hr]]; if (hr == nruns - 1) mt = rtop[hr]; }
+                else pick[k] = nodes[lh++];
             }
             hnode merged; merged.val = pick[0].val + pick[1].val; merged.id = next_id++;
             code[pick[0].id] = 0; code[pick[1].id] = 1; parent[pick[0].id] = merged.id; parent[pick[1].id] = merged.id;
-            /* insert before the run of equal values at the tail */
-            int pos = mt;
-            while (pos > mh && mq[pos - 1].val >= merged.val) pos--;
-            memmove(mq + pos + 1, mq + pos, sizeof(hnode) * (size_t)(mt - pos));
-            mq[pos] = merged; mt++;
+            if (nruns > 0 && rtop[nruns - 1] == mt && ((rtop[nruns - 1] > rstart[nruns - 1] && mq[rstart[nruns - 1]].val == merged.val) ||
+                                                      (rtop[nruns - 1] == rstart[nruns - 1]))) {
+                if (rtop[nruns - 1] == rstart[nruns - 1]) { rstart[nruns - 1] = mt; }   /* reuse the emptied last run */
+                mq[mt++] = merged; rtop[nruns - 1] = mt;
+            } else { rstart[nruns] = mt; mq[mt++] = merged; rtop[nruns] = mt; nruns++; }
         }
+        free(rstart); free(rtop);
         free(mq);
     }
     free(nodes);

@@ -76,3 +76,23 @@ def test_marshal_schema_matches_reference_json():
     np.testing.assert_array_equal(back.weights[0], net.weights[0])
     y = g.NewYoutubeDnn(5, 3, 7, 7, 5); y.weights = net.weights
     assert "att0" not in json.loads(y.Marshal())                             # dnn.go:38-47
+
+
+def test_item2vec_host_plan_matches_the_reference_huffman_procedure():
+    """ctr_i2v_paths (host-only part of the item2vec trainer) == dictionary.HuffnamTree + Node.GetPath as the
+    oracle restates them (huffman.go:23-57, node.go:26-43), including ties and never-seen words."""
+    import time
+    import numpy as np
+    from oracle import oracle as orc
+    rng = np.random.default_rng(0)
+    for V, hi in ((2, 5), (9, 3), (300, 4), (2000, 100000)):
+        cnt = rng.integers(0, hi, V); cnt[0] = max(cnt[0], 1)
+        off, nodes, codes = g.i2v_paths(cnt)
+        parent, code = orc.i2v_huffman(cnt, literal=True)
+        for w in range(V):
+            n, c = orc.i2v_path(parent, code, V, w)
+            assert nodes[off[w]:off[w + 1]].tolist() == n.tolist() and codes[off[w]:off[w + 1]].tolist() == c.tolist(), (V, hi, w)
+    off, nodes, _ = g.i2v_paths(np.ones(50, np.int64), max_depth=3)
+    assert (np.diff(off) == 2).all()                                   # GetPath(3) → two (node, code) steps
+    cnt = np.floor(np.exp(rng.random(400000) * np.log(50))).astype(np.int64) - 1   # ~half zeros, heavy ties
+    t0 = time.perf_counter(); g.i2v_paths(cnt); assert time.perf_counter() - t0 < 20   # no quadratic insertion
