@@ -32,6 +32,9 @@ WORKLOADS = {
     "youtube_10m": dict(model="youtube", U=138493, I=10_000_000, D=64, S=50, uP=52, cF=53, B=16384, zipf=False,
                         note="BASELINE.json configs[2]"),
     # BASELINE.json configs[3] per-GPU shard: DIN, 100M rows / 8 GPUs = 12.5M rows (3.2 GB), batch 65536, S=50
+    # BASELINE.json configs[3] itself: 100M rows (25.6 GB) row-sharded over the GPUs, global batch 65536 at 8 GPUs
+    "din_100m": dict(model="din", U=138493, I=100_000_000, D=64, S=50, uP=52, cF=53, B=8192, zipf=False,
+                     note="BASELINE.json configs[3]: 100M-row table sharded row%world, 8192 samples per GPU (65536 global at 8 GPUs), uniform ids"),
     "din_100m_shard": dict(model="din", U=138493, I=12_500_000, D=64, S=50, uP=52, cF=53, B=65536, zipf=False,
                            note="BASELINE.json configs[3], one GPU's 1/8 row shard; uniform indices (worst case for caches)"),
 }
