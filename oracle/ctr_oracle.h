@@ -168,3 +168,48 @@ double orc_i2v_init(uint32_t seed, long i, int dim);
 }
 #endif
 #endif
+
+/* ============================================================================================== *
+ * float64 MLP (BASELINE configs[0]): model/mlp/mlp.go over
+ * nn/neural_network/basemlp64.go.  Oracle only (no GPU path is in scope for this row).
+ * Pinned: loss(θ=0)=ln 2 and gradient == finite differences (multilayer_perceptron_test.go:86-91,
+ * :118-130); everything else PARITY UNPINNED (dataset of the reference's tests is third-party).
+ * ============================================================================================== */
+#ifndef CTR_ORACLE_MLP64_H
+#define CTR_ORACLE_MLP64_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+enum { ORC_MLP_RELU = 0, ORC_MLP_LOGISTIC = 1, ORC_MLP_IDENTITY = 2 };
+typedef struct {
+    int n_layers;            /* len(layerUnits) = hidden + 2 */
+    int units[8];            /* [nFeatures, hidden..., nOutputs]  (basemlp64.go:495-497) */
+    int hidden_act;          /* ORC_MLP_*; output is always logistic + binary_log_loss (:423-425) */
+    int batch;               /* 200 (:233) */
+    int max_iter;            /* 200 (:238) */
+    int n_iter_no_change;    /* 10 (:254) */
+    int shuffle;             /* true (:241) */
+    int adaptive;            /* LearningRate == "adaptive" (feature_test.go:36) */
+    uint32_t seed;
+    double alpha;            /* 1e-4 (:232) */
+    double lr_init;          /* 1e-3 (:235) */
+    double beta1, beta2, eps;/* .9 .999 1e-8 (:250-252) */
+    double tol;              /* 1e-4 (:243) */
+} orc_mlp64_cfg;
+typedef struct { double *ms, *vs; double beta1t, beta2t, t, lr_init, lr; } orc_mlp64_adam_state;
+
+long   orc_mlp64_nparams(const orc_mlp64_cfg* c);
+void   orc_mlp64_init(const orc_mlp64_cfg* c, double* params);
+double orc_mlp64_loss_grad(const orc_mlp64_cfg* c, const double* params, const double* X, const double* y,
+                           long n, double* grads);
+void   orc_mlp64_adam(const orc_mlp64_cfg* c, orc_mlp64_adam_state* st, double* params, const double* grads, long np);
+int    orc_mlp64_fit(const orc_mlp64_cfg* c, double* params, const double* X, const double* y, long n,
+                     double* loss_curve, double* final_lr_init);
+void   orc_mlp64_predict(const orc_mlp64_cfg* c, const double* params, const double* X, long n, double* out);
+int    orc_mlp_fit_wrap(const orc_mlp64_cfg* c, double* params, const float* X32, const float* Y32, long n,
+                        double* loss_curve);
+void   orc_mlp_predict_wrap(const orc_mlp64_cfg* c, const double* params, const float* X32, long n, float* out);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -73,6 +73,8 @@ def lib():
         L.orc_i2v_sigmoid_lut.argtypes = [C.c_double]
         L.orc_i2v_init.restype = C.c_double
         L.orc_i2v_init.argtypes = [C.c_uint32, C.c_long, C.c_int]
+        L.orc_mlp64_nparams.restype = C.c_long
+        L.orc_mlp64_loss_grad.restype = C.c_double
         _lib = L
     return _lib
 
@@ -330,3 +332,96 @@ def i2v_train(cfg, tokens, V, want_syn1=False):
     trained = lib().orc_i2v_train(C.byref(cfg), tp, C.c_long(tok.size), C.c_int(V), emb.ctypes.data_as(_fp),
                                   syn1.ctypes.data_as(C.POINTER(C.c_double)) if want_syn1 else None)
     return (emb, syn1, trained) if want_syn1 else (emb, trained)
+
+
+# ---- float64 MLP (row a11, BASELINE configs[0]) -----------------------------------------------------
+class Mlp64Cfg(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("units", C.c_int * 8), ("hidden_act", C.c_int), ("batch", C.c_int),
+                ("max_iter", C.c_int), ("n_iter_no_change", C.c_int), ("shuffle", C.c_int), ("adaptive", C.c_int),
+                ("seed", C.c_uint32), ("alpha", C.c_double), ("lr_init", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("tol", C.c_double)]
+
+
+_dp = C.POINTER(C.c_double)
+MLP_ACT = {"relu": 0, "logistic": 1, "identity": 2}
+
+
+def mlp64_cfg(n_features, hidden=(100,), activation="relu", alpha=1e-4, batch=200, max_iter=200, lr_init=1e-3,
+              adaptive=False, shuffle=True, seed=0, tol=1e-4, n_iter_no_change=10, n_outputs=1):
+    """NewMLPClassifier(hidden, activation, "adam", alpha) with NewBaseMultilayerPerceptron64's defaults
+    (multilayer_perceptron.go:81-90, basemlp64.go:228-256)."""
+    units = [n_features, *hidden, n_outputs]
+    c = Mlp64Cfg()
+    c.n_layers = len(units)
+    for i, u in enumerate(units):
+        c.units[i] = u
+    c.hidden_act = MLP_ACT[activation]; c.batch = batch; c.max_iter = max_iter; c.n_iter_no_change = n_iter_no_change
+    c.shuffle = int(shuffle); c.adaptive = int(adaptive); c.seed = seed; c.alpha = alpha; c.lr_init = lr_init
+    c.beta1, c.beta2, c.eps, c.tol = 0.9, 0.999, 1e-8, tol
+    return c
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def mlp64_nparams(cfg):
+    return int(lib().orc_mlp64_nparams(C.byref(cfg)))
+
+
+def mlp64_init(cfg):
+    p = np.empty(mlp64_nparams(cfg), np.float64)
+    lib().orc_mlp64_init(C.byref(cfg), p.ctypes.data_as(_dp))
+    return p
+
+
+def mlp64_loss_grad(cfg, params, X, y):
+    X, xp = _d(X); y, yp = _d(y); params, pp = _d(params)
+    g = np.empty_like(params)
+    loss = lib().orc_mlp64_loss_grad(C.byref(cfg), pp, xp, yp, C.c_long(X.shape[0]), g.ctypes.data_as(_dp))
+    return float(loss), g
+
+
+def mlp64_fit(cfg, params, X, y):
+    """in-place on params; returns (n_iter, loss_curve, final lr_init)."""
+    X, xp = _d(X); y, yp = _d(y)
+    assert params.dtype == np.float64 and params.flags.c_contiguous
+    curve = np.zeros(cfg.max_iter, np.float64); lr = C.c_double(0)
+    it = lib().orc_mlp64_fit(C.byref(cfg), params.ctypes.data_as(_dp), xp, yp, C.c_long(X.shape[0]),
+                             curve.ctypes.data_as(_dp), C.byref(lr))
+    return it, curve[:it], lr.value
+
+
+def mlp64_predict(cfg, params, X):
+    X, xp = _d(X); params, pp = _d(params)
+    out = np.empty((X.shape[0], cfg.units[cfg.n_layers - 1]), np.float64)
+    lib().orc_mlp64_predict(C.byref(cfg), pp, xp, C.c_long(X.shape[0]), out.ctypes.data_as(_dp))
+    return out
+
+
+class SimpleMlpFitWrap:
+    """model/mlp/mlp.go:41-65 — float32 TrainSample in, predictor returning float32 [n,1] out."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+
+    def Fit(self, X32, Y32):
+        X, xp = _f(X32); Y, yp = _f(Y32)
+        params = np.empty(mlp64_nparams(self.cfg), np.float64)
+        curve = np.zeros(self.cfg.max_iter, np.float64)
+        it = lib().orc_mlp_fit_wrap(C.byref(self.cfg), params.ctypes.data_as(_dp), xp, yp, C.c_long(X.shape[0]),
+                                    curve.ctypes.data_as(_dp))
+        return SimpleMlpPredWrap(self.cfg, params, curve[:it])
+
+
+class SimpleMlpPredWrap:
+    def __init__(self, cfg, params, loss_curve):
+        self.cfg, self.params, self.loss_curve = cfg, params, loss_curve
+
+    def Predict(self, X32):
+        X, xp = _f(X32)
+        out = np.empty((X.shape[0], 1), np.float32)
+        lib().orc_mlp_predict_wrap(C.byref(self.cfg), self.params.ctypes.data_as(_dp), xp, C.c_long(X.shape[0]),
+                                   out.ctypes.data_as(_fp))
+        return out
