@@ -182,6 +182,125 @@ k_attn_fwd_vec(RowSrc r, Dims d, const float* __restrict__ att,
 }
 
 // -------------------------------------------------------------------------------------------------
+// forward, index path (the B200 fast path: rows come from the HBM tables).  Same lane mapping and math as
+// k_attn_fwd_vec, with everything the dense-X route needs compiled out:
+//   * the sample's ids for the NEXT sample and this lane's 16-byte chunk of the dense features travel
+//     through lane-private shared-memory slots with cp.async — no registers held, no load the warp must
+//     wait for in front of the row loop, and the id → address dependency is off the critical path;
+//   * the MLP input row is written straight from registers: lanes [0, uP/4) own the user-profile chunks,
+//     the following lanes the ctx chunks and the zero pad, the sub-group-0 lanes pooled + item.
+// Requires S <= 64, uP % 4 == 0, 16-byte aligned table rows and (Kp - 2D)/4 <= 32 (one chunk per lane).
+// -------------------------------------------------------------------------------------------------
+template <int LPR, int VPL, int MODEL, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_attn_fwd_idx(RowSrc r, Dims d, const float* __restrict__ att, float* __restrict__ X0, long ldx0, int Kp, int B) {
+    constexpr int RPW = 32 / LPR, DD = 4 * LPR * VPL;
+    __shared__ __align__(16) float4 s_feat[NT];      // lane-private: this lane's feature chunk of the current sample
+    __shared__ __align__(16) int4 s_ids[NT];         // lane-private: {hist id lane, hist id lane+32, item row, feature row} of the next sample
+    const int lane = threadIdx.x & 31, lir = lane % LPR, sub = lane / LPR;
+    const int nwarps = gridDim.x * (NT / 32);
+    int b = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float invS = 1.0f / (float)d.S;
+    const int nu4 = d.uP >> 2, nc4 = (d.cF + 3) >> 2;
+    const bool f_user = lane < nu4;
+    const int fc = f_user ? lane : lane - nu4;
+    const bool f_load = f_user || fc < nc4;
+    const int f_off = f_user ? 4 * lane : d.uP + 2 * DD + 4 * fc;
+    const float* f_tab = f_user ? r.ufeat : r.ifeat;
+    const long f_ld = f_user ? r.ldu : r.ldi;
+    const int* f_ids = f_user ? r.user_row : (r.item_feat_row ? r.item_feat_row : r.item_row);
+    int* my_ids = reinterpret_cast<int*>(&s_ids[threadIdx.x]);
+    float4* my_feat = &s_feat[threadIdx.x];
+
+    auto fetch_ids = [&](int bb) {           // asynchronous: lands in my_ids
+        const int* h = r.hist + (long)bb * d.S;
+        if (lane < d.S) cp_async4(my_ids, h + lane);
+        if (lane + 32 < d.S) cp_async4(my_ids + 1, h + lane + 32);
+        cp_async4(my_ids + 2, r.item_row + bb);
+        cp_async4(my_ids + 3, f_ids + bb);
+        cp_async_commit();
+    };
+    *reinterpret_cast<int4*>(my_ids) = make_int4(-1, -1, -1, -1);
+    fetch_ids(b);
+    for (;;) {
+        cp_async_wait_all();
+        const int4 id = *reinterpret_cast<const int4*>(my_ids);        // x: hist[lane], y: hist[lane+32], z: item, w: feature row
+        const int bn = b + nwarps;
+        if (bn < B) fetch_ids(bn);
+        if (f_load) cp_async16(my_feat, f_tab + (long)(id.w >= 0 ? id.w : 0) * f_ld + 4 * fc, id.w >= 0);
+        cp_async_commit();
+        float4 v[VPL], acc[VPL];
+        float ny2 = 0.0f;
+        const float* ip = r.emb + (long)(id.z >= 0 ? id.z : 0) * r.lde;
+#pragma unroll
+        for (int q = 0; q < VPL; q++) { v[q] = id.z >= 0 ? ldg4(ip + (q * LPR + lir) * 4) : zero4(); acc[q] = zero4(); }
+        bool first = true;
+        float ny = 0.0f;
+        for (int s0 = 0; s0 < d.S; s0 += RPW) {
+            const int s = s0 + sub;
+            const int a0 = __shfl_sync(0xffffffffu, id.x, s & 31), a1 = __shfl_sync(0xffffffffu, id.y, s & 31);
+            const int row = s < d.S ? (s < 32 ? a0 : a1) : -1;
+            float4 u[VPL];
+            const float* p = r.emb + (long)(row >= 0 ? row : 0) * r.lde;
+#pragma unroll
+            for (int q = 0; q < VPL; q++) u[q] = row >= 0 ? ldg4_stream(p + (q * LPR + lir) * 4) : zero4();
+            if (first) {         // the item row's norm is not needed before the first history rows are in flight
+#pragma unroll
+                for (int q = 0; q < VPL; q++) ny2 += dot4(v[q], v[q]);
+                ny = fsqrt_pos(group_sum<LPR>(ny2));
+                first = false;
+            }
+            float a = 1.0f;
+            if (MODEL == MODEL_DIN_COS) {
+                float dot = 0.0f, nx2 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < VPL; q++) { dot += dot4(u[q], v[q]); nx2 += dot4(u[q], u[q]); }
+                dot = group_sum<LPR>(dot); nx2 = group_sum<LPR>(nx2);
+                const float cs = dot * frcp(fsqrt_pos(nx2) * ny + 1e-8f);
+                a = sigmoid_fast((cs + 1.0f) * 0.5f * (s < d.S ? __ldg(att + s) : 0.0f));
+            } else if (MODEL == MODEL_DIN_EUC) {
+                float d2 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < VPL; q++) {
+                    const float4 e = make_float4(u[q].x - v[q].x, u[q].y - v[q].y, u[q].z - v[q].z, u[q].w - v[q].w);
+                    d2 += dot4(e, e);
+                }
+                a = sigmoid_fast((1.0f - fsqrt_pos(group_sum<LPR>(d2))) * (s < d.S ? __ldg(att + s) : 0.0f));
+            }
+#pragma unroll
+            for (int q = 0; q < VPL; q++) acc[q] = fma4(a, u[q], acc[q]);      // slots beyond S / missing rows carry u == 0
+        }
+#pragma unroll
+        for (int q = 0; q < VPL; q++) {
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+                acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+                acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+                acc[q].z += __shfl_xor_sync(0xffffffffu, acc[q].z, o);
+                acc[q].w += __shfl_xor_sync(0xffffffffu, acc[q].w, o);
+            }
+        }
+        float* xr = X0 + (long)b * ldx0;
+        if (sub == 0) {
+#pragma unroll
+            for (int q = 0; q < VPL; q++) {
+                *reinterpret_cast<float4*>(xr + d.uP + (q * LPR + lir) * 4) = make_float4(acc[q].x * invS, acc[q].y * invS, acc[q].z * invS, acc[q].w * invS);
+                *reinterpret_cast<float4*>(xr + d.uP + DD + (q * LPR + lir) * 4) = v[q];
+            }
+        }
+        if (f_off < Kp) {
+            // my feature chunk landed long ago unless the next sample's ids (committed before it) are still in
+            // flight: wait for all but that newest-but-one group is not expressible per lane → wait for both
+            cp_async_wait_all();
+            *reinterpret_cast<float4*>(xr + f_off) = f_load ? *my_feat : zero4();
+        }
+        if (bn >= B) break;
+        b = bn;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // forward, generic path (any D <= 256, unaligned sources — the dense-X compatibility route and odd
 // dims such as the reference test's D=7, model_test.go:24-28).
 // -------------------------------------------------------------------------------------------------
@@ -405,6 +524,151 @@ k_attn_bwd_vec(RowSrc r, Dims d, const float* __restrict__ att,
     if (MODEL != MODEL_YOUTUBE && o.datt)
         for (int j = threadIdx.x; j < d.S; j += NT)
             if (smem[j] != 0.0f) atomicAdd(o.datt + j, smem[j]);
+}
+
+// backward, index path: k_attn_bwd_vec's math with the dense-X route compiled out and the next sample's ids
+// prefetched through lane-private shared-memory slots (see k_attn_fwd_idx).  Requires S <= 64.
+template <int LPR, int VPL, int MODEL, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
+               const float* __restrict__ dX, long lddx, BwdOut o, int B) {
+    constexpr int RPW = 32 / LPR;
+    __shared__ float s_datt[64];
+    __shared__ __align__(16) int4 s_ids[NT];
+    const int lane = threadIdx.x & 31, lir = lane % LPR, sub = lane / LPR;
+    const int gwarp = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (NT / 32);
+    const int rep = o.hot_reps > 0 ? gwarp % o.hot_reps : 0;
+    const float invS = 1.0f / (float)d.S;
+    const float sc = o.sgd ? o.neg_lr : 1.0f;         // fused SGD: gradients leave pre-scaled by -lr
+    if (threadIdx.x < 64) s_datt[threadIdx.x] = 0.0f;
+    int* my_ids = reinterpret_cast<int*>(&s_ids[threadIdx.x]);
+    *reinterpret_cast<int4*>(my_ids) = make_int4(-1, -1, -1, -1);
+    __syncthreads();
+    auto fetch_ids = [&](int bb) {
+        const int* h = r.hist + (long)bb * d.S;
+        if (lane < d.S) cp_async4(my_ids, h + lane);
+        if (lane + 32 < d.S) cp_async4(my_ids + 1, h + lane + 32);
+        cp_async4(my_ids + 2, r.item_row + bb);
+        cp_async_commit();
+    };
+    int b = gwarp;
+    if (b < B) fetch_ids(b);
+    while (b < B) {
+        cp_async_wait_all();
+        const int4 id = *reinterpret_cast<const int4*>(my_ids);
+        const int bn = b + nwarps;
+        if (bn < B) fetch_ids(bn);
+        const float* ip = r.emb + (long)(id.z >= 0 ? id.z : 0) * r.lde;
+        float4 g[VPL], v[VPL], dvu[VPL];
+        float ny2 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < VPL; q++) {
+            g[q] = ldg4(dX + (long)b * lddx + (q * LPR + lir) * 4);
+            // the table is written by this kernel (sgd mode): coherent loads, no .nc
+            v[q] = id.z >= 0 ? *reinterpret_cast<const float4*>(ip + (q * LPR + lir) * 4) : zero4();
+            dvu[q] = zero4();
+        }
+        float ny = 0.0f, rny = 0.0f, kvsum = 0.0f;        // kvsum: coefficient of -v in dv
+        bool first = true;
+        for (int s0 = 0; s0 < d.S; s0 += RPW) {
+            const int s = s0 + sub;
+            const int a0 = __shfl_sync(0xffffffffu, id.x, s & 31), a1 = __shfl_sync(0xffffffffu, id.y, s & 31);
+            const int row = s < d.S ? (s < 32 ? a0 : a1) : -1;
+            const float* p = r.emb + (long)(row >= 0 ? row : 0) * r.lde;
+            float4 u[VPL];
+#pragma unroll
+            for (int q = 0; q < VPL; q++) u[q] = row >= 0 ? *reinterpret_cast<const float4*>(p + (q * LPR + lir) * 4) : zero4();
+            if (first) {
+#pragma unroll
+                for (int q = 0; q < VPL; q++) ny2 += dot4(v[q], v[q]);
+                ny2 = group_sum<LPR>(ny2);
+                ny = fsqrt_pos(ny2); rny = ny2 > 0.0f ? rsqrtf(ny2) : 0.0f;
+                first = false;
+            }
+            // du = c1*g + c2*v + c3*u ; dv += c4*u - (kv coefficient)*v
+            float c1 = invS, c2 = 0.0f, c3 = 0.0f, c4 = 0.0f;
+            if (MODEL != MODEL_YOUTUBE) {
+                const float att_s = s < d.S ? __ldg(att + s) : 0.0f;
+                float gu = 0.0f, dot = 0.0f, nx2 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < VPL; q++) {
+                    gu += dot4(g[q], u[q]);
+                    if (MODEL == MODEL_DIN_COS) { dot += dot4(u[q], v[q]); nx2 += dot4(u[q], u[q]); }
+                    else {
+                        const float4 e = make_float4(u[q].x - v[q].x, u[q].y - v[q].y, u[q].z - v[q].z, u[q].w - v[q].w);
+                        nx2 += dot4(e, e);
+                    }
+                }
+                gu = group_sum<LPR>(gu); nx2 = group_sum<LPR>(nx2);
+                if (MODEL == MODEL_DIN_COS) {
+                    dot = group_sum<LPR>(dot);
+                    const float nx = fsqrt_pos(nx2);
+                    const float iden = frcp(nx * ny + 1e-8f);
+                    const float cs = dot * iden;
+                    const float w = (cs + 1.0f) * 0.5f;
+                    const float a = sigmoid_fast(w * att_s);
+                    const float dz = gu * invS * a * (1.0f - a);
+                    if (lir == 0 && s < d.S) atomicAdd(&s_datt[s], dz * w);
+                    const float cc = 0.5f * dz * att_s;
+                    c1 = a * invS; c2 = cc * iden; c4 = c2;
+                    c3 = nx2 > 0.0f ? -cc * cs * ny * iden * rsqrtf(nx2) : 0.0f;     // -cc*cos*|v|/(|u| den)
+                    kvsum += cc * cs * nx * iden * rny;                               //  cc*cos*|u|/(|v| den)
+                } else {
+                    const float dist = fsqrt_pos(nx2);
+                    const float w = 1.0f - dist;
+                    const float a = sigmoid_fast(w * att_s);
+                    const float dz = gu * invS * a * (1.0f - a);
+                    if (lir == 0 && s < d.S) atomicAdd(&s_datt[s], dz * w);
+                    const float k = nx2 > 0.0f ? dz * att_s * rsqrtf(nx2) : 0.0f;    // dw/dist
+                    c1 = a * invS; c3 = -k; c2 = k;      // du = c1 g - k (u - v)
+                    c4 = s < d.S ? k : 0.0f;             // dv += k (u - v)
+                    kvsum += c4;
+                }
+            }
+            if (s < d.S) {
+                const float e1 = c1 * sc, e2 = c2 * sc, e3 = c3 * sc;
+                float* dst = (o.sgd && row >= 0) ? scatter_dst(r, d, o, row, rep) : nullptr;
+#pragma unroll
+                for (int q = 0; q < VPL; q++) {
+                    float4 du;
+                    du.x = fmaf(e3, u[q].x, fmaf(e2, v[q].x, e1 * g[q].x)); du.y = fmaf(e3, u[q].y, fmaf(e2, v[q].y, e1 * g[q].y));
+                    du.z = fmaf(e3, u[q].z, fmaf(e2, v[q].z, e1 * g[q].z)); du.w = fmaf(e3, u[q].w, fmaf(e2, v[q].w, e1 * g[q].w));
+                    dvu[q] = fma4(c4, u[q], dvu[q]);
+                    if (o.dUb) *reinterpret_cast<float4*>(o.dUb + ((long)b * d.S + s) * d.D + (q * LPR + lir) * 4) = du;
+                    if (dst) red_add4(dst + (q * LPR + lir) * 4, du);
+                }
+            }
+        }
+        // dv = gi + sum_subgroups(dvu) - (sum kv) * v
+#pragma unroll
+        for (int of = LPR; of < 32; of <<= 1) kvsum += __shfl_xor_sync(0xffffffffu, kvsum, of);
+#pragma unroll
+        for (int q = 0; q < VPL; q++) {
+#pragma unroll
+            for (int of = LPR; of < 32; of <<= 1) {
+                dvu[q].x += __shfl_xor_sync(0xffffffffu, dvu[q].x, of);
+                dvu[q].y += __shfl_xor_sync(0xffffffffu, dvu[q].y, of);
+                dvu[q].z += __shfl_xor_sync(0xffffffffu, dvu[q].z, of);
+                dvu[q].w += __shfl_xor_sync(0xffffffffu, dvu[q].w, of);
+            }
+        }
+        if (sub == 0) {
+            float* dst = (o.sgd && id.z >= 0) ? scatter_dst(r, d, o, id.z, rep) : nullptr;
+#pragma unroll
+            for (int q = 0; q < VPL; q++) {
+                const float4 gi = ldg4(dX + (long)b * lddx + d.D + (q * LPR + lir) * 4);
+                float4 dv;
+                dv.x = (gi.x + dvu[q].x - kvsum * v[q].x) * sc; dv.y = (gi.y + dvu[q].y - kvsum * v[q].y) * sc;
+                dv.z = (gi.z + dvu[q].z - kvsum * v[q].z) * sc; dv.w = (gi.w + dvu[q].w - kvsum * v[q].w) * sc;
+                if (o.dIt) *reinterpret_cast<float4*>(o.dIt + (long)b * d.D + (q * LPR + lir) * 4) = dv;
+                if (dst) red_add4(dst + (q * LPR + lir) * 4, dv);
+            }
+        }
+        b = bn;
+    }
+    __syncthreads();
+    if (MODEL != MODEL_YOUTUBE && o.datt && threadIdx.x < d.S && s_datt[threadIdx.x] != 0.0f) atomicAdd(o.datt + threadIdx.x, s_datt[threadIdx.x]);
 }
 
 // folds the hot-row replica accumulators into the table: row += scale * sum_rep acc ; acc = 0

@@ -81,6 +81,19 @@ __device__ __forceinline__ float4 fma4(float s, float4 a, float4 c) {
 }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+// 16-byte global→shared copy that does not occupy a register or stall the issuing warp (LDGSTS); valid == false
+// writes zeros without touching src
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Where one sample's rows come from.  index mode: the HBM tables + per-sample row ids
 // (GetSampleVector rcmd.go:462-536 done inside the kernel).  dense mode: a materialised X row and
 // SampleInfo column offsets (model.Train's tensor.Slice calls, model.go:129-171).

@@ -7,6 +7,7 @@
 #include "umma_gemm.cuh"
 #include "auc.cuh"
 #include "ubcache.cuh"
+#include "idmap.cuh"
 #include "item2vec.cuh"
 #include "comm.cuh"
 
@@ -18,6 +19,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -98,6 +100,11 @@ struct ctr_handle {
     // device-side ubcache (ubcache.cuh)
     long long *ub_off = nullptr, *ub_ts = nullptr; int* ub_items = nullptr; int64_t ub_users = 0, ub_n = 0;
 
+    // device id maps (idmap.cuh): [CTR_IDMAP_USER, CTR_IDMAP_ITEM]
+    unsigned long long* idm_keys[2] = {nullptr, nullptr}; int* idm_vals[2] = {nullptr, nullptr};
+    unsigned long long idm_cap[2] = {0, 0}; int64_t idm_n[2] = {0, 0};
+    long long *k_keys = nullptr, *k_host = nullptr; int* k_flags = nullptr;   // staging for ctr_batch_predict_keys (device, pinned host)
+
     unsigned long long* umma_dbg = nullptr;     // CTR_UMMA_TIMELINE=1: timeline buffer of the last umma launch
 
     Comm comm;
@@ -162,7 +169,7 @@ bool vec_ok(const ctr_handle* h, const RowSrc& r) {
 // bwd_probe.cu: occupancy beats deeper per-warp unrolling on B200).
 int grid_attn(const ctr_handle* h, int B) {
     int blocks = (B + 3) / 4;
-    return std::max(1, std::min(blocks, h->num_sms * 32));
+    return std::max(1, std::min(blocks, h->num_sms * 16));     // two waves of 8 resident blocks; 8..64 per SM measure within 1 %
 }
 template <int LPR, int VPL, int MINB>
 void launch_fwd_vec(ctr_handle* h, const RowSrc& r, int B) {
@@ -185,7 +192,46 @@ void launch_bwd_vec(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
     }
 }
 
+// index-mode fast kernels (k_attn_fwd_idx / k_attn_bwd_idx): conditions beyond vec_ok
+bool idx_fwd_ok(const ctr_handle* h, const RowSrc& r, int B) {
+    static const bool off = getenv("CTR_ATTN_OLD") != nullptr;
+    const ctr_config& c = h->cfg;
+    return !off && !r.dense && r.nvalid >= B && c.S <= 64 && c.uP % 4 == 0 && r.ldu % 4 == 0 && r.ldi % 4 == 0 && (h->Kp - 2 * c.D) / 4 <= 32 &&
+           r.ufeat && r.ifeat;
+}
+bool idx_bwd_ok(const ctr_handle* h, const RowSrc& r, int B) {
+    static const bool off = getenv("CTR_ATTN_OLD") != nullptr;
+    return !off && !r.dense && r.nvalid >= B && h->cfg.S <= 64;
+}
+template <int LPR, int VPL, int MINB>
+void launch_fwd_idx(ctr_handle* h, const RowSrc& r, int B) {
+    const int g = grid_attn(h, B);
+    switch (h->cfg.model) {
+        case CTR_MODEL_YOUTUBE: k_attn_fwd_idx<LPR, VPL, MODEL_YOUTUBE, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
+        case CTR_MODEL_DIN_COS: k_attn_fwd_idx<LPR, VPL, MODEL_DIN_COS, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
+        default:                k_attn_fwd_idx<LPR, VPL, MODEL_DIN_EUC, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
+    }
+}
+template <int LPR, int VPL, int MINB>
+void launch_bwd_idx(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
+    const int g = grid_attn(h, B);
+    switch (h->cfg.model) {
+        case CTR_MODEL_YOUTUBE: k_attn_bwd_idx<LPR, VPL, MODEL_YOUTUBE, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); break;
+        case CTR_MODEL_DIN_COS: k_attn_bwd_idx<LPR, VPL, MODEL_DIN_COS, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); break;
+        default:                k_attn_bwd_idx<LPR, VPL, MODEL_DIN_EUC, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); break;
+    }
+}
+
 int attn_forward(ctr_handle* h, const RowSrc& r, int B) {
+    if (vec_ok(h, r) && idx_fwd_ok(h, r, B)) {
+        return launch(h, "attn_fwd_vec", [&] {
+            switch (h->cfg.D / 4) {
+                case 4: launch_fwd_idx<4, 1, 8>(h, r, B); break;    case 8: launch_fwd_idx<4, 2, 8>(h, r, B); break;
+                case 16: launch_fwd_idx<4, 4, 8>(h, r, B); break;
+                default: launch_fwd_idx<8, 4, 8>(h, r, B); break;
+            }
+        });
+    }
     if (vec_ok(h, r)) {
         return launch(h, "attn_fwd_vec", [&] {
             switch (h->cfg.D / 4) {           // float4 per row
@@ -200,6 +246,15 @@ int attn_forward(ctr_handle* h, const RowSrc& r, int B) {
 }
 
 int attn_backward(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
+    if (vec_ok(h, r) && idx_bwd_ok(h, r, B)) {
+        return launch(h, "attn_bwd_vec", [&] {
+            switch (h->cfg.D / 4) {
+                case 4: launch_bwd_idx<4, 1, 8>(h, r, o, B); break;    case 8: launch_bwd_idx<4, 2, 8>(h, r, o, B); break;
+                case 16: launch_bwd_idx<8, 2, 8>(h, r, o, B); break;
+                default: launch_bwd_idx<16, 2, 8>(h, r, o, B); break;
+            }
+        });
+    }
     if (vec_ok(h, r)) {
         return launch(h, "attn_bwd_vec", [&] {
             switch (h->cfg.D / 4) {
@@ -750,6 +805,8 @@ void ctr_destroy(ctr_handle* h) {
     comm_destroy(h);
     for (int i = 0; i < 3; i++) if (h->tab[i]) cudaFree(h->tab[i]);
     for (void* p : {(void*)h->ub_off, (void*)h->ub_ts, (void*)h->ub_items}) if (p) cudaFree(p);
+    for (void* p : {(void*)h->idm_keys[0], (void*)h->idm_keys[1], (void*)h->idm_vals[0], (void*)h->idm_vals[1], (void*)h->k_keys, (void*)h->k_flags}) if (p) cudaFree(p);
+    if (h->k_host) cudaFreeHost(h->k_host);
     for (int i = 0; i < 2; i++) for (float* p : {h->um.Wt0[i], h->um.Wt1[i], h->um.W1s[i], h->um.W0s[i]}) if (p) cudaFree(p);
     for (int i = 0; i < 4; i++) for (float* p : {h->W[i], h->G[i], h->Mo[i], h->Vo[i]}) if (p) cudaFree(p);
     for (void* p : {(void*)h->X0, (void*)h->H0d, (void*)h->H1d, (void*)h->P, (void*)h->Z, (void*)h->dZ1, (void*)h->dZ0, (void*)h->dX,
@@ -1163,6 +1220,207 @@ int ctr_ubcache_window(ctr_handle* h, const int32_t* user_row, const int64_t* ma
                              cudaStreamSynchronize(h->stream) != cudaSuccess)) rc = set_err(h, CTR_ECUDA, "ubcache window copy: %s", cudaGetErrorString(cudaGetLastError()));
     }
     for (void* p : {(void*)du, (void*)dt, (void*)dh}) if (p) cudaFree(p);
+    return rc;
+}
+
+// ---- sparse ids, serving keys, checkpoint (rows f3 / f4) -------------------------------------------------
+int ctr_idmap_build(ctr_handle* h, int which, const int64_t* ids, int64_t n) {
+    if (!h || !ids || which < 0 || which > 1 || n < 1 || n > 0x7fffffff) return set_err(h, CTR_EINVAL, "bad idmap arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    for (void* p : {(void*)h->idm_keys[which], (void*)h->idm_vals[which]}) if (p) cudaFree(p);
+    h->idm_keys[which] = nullptr; h->idm_vals[which] = nullptr; h->idm_n[which] = 0;
+    unsigned long long cap = 64;
+    while (cap < 2ull * (unsigned long long)n) cap <<= 1;                 // load factor <= 0.5
+    RET(dalloc(h, &h->idm_keys[which], (size_t)cap, false)); RET(dalloc(h, &h->idm_vals[which], (size_t)cap, false));
+    if (!h->k_flags) RET(dalloc(h, &h->k_flags, 1));
+    long long* d_ids = nullptr;
+    CU(h, cudaMalloc(&d_ids, sizeof(long long) * (size_t)n));
+    int flags = 0, rc = CTR_OK;
+    cudaMemcpyAsync(d_ids, ids, sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+    cudaMemsetAsync(h->k_flags, 0, sizeof(int), h->stream);
+    rc = launch(h, "idmap_clear", [&] { k_idmap_clear<<<h->num_sms * 8, 256, 0, h->stream>>>(h->idm_keys[which], h->idm_vals[which], cap); });
+    if (rc == CTR_OK) rc = launch(h, "idmap_insert", [&] {
+        k_idmap_insert<<<h->num_sms * 8, 256, 0, h->stream>>>(h->idm_keys[which], h->idm_vals[which], cap - 1, d_ids, (long)n, h->k_flags);
+    });
+    if (rc == CTR_OK && (cudaMemcpyAsync(&flags, h->k_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                         cudaStreamSynchronize(h->stream) != cudaSuccess)) rc = set_err(h, CTR_ECUDA, "idmap build: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_ids);
+    RET(rc);
+    if (flags) {
+        cudaFree(h->idm_keys[which]); cudaFree(h->idm_vals[which]); h->idm_keys[which] = nullptr; h->idm_vals[which] = nullptr;
+        return set_err(h, CTR_EINVAL, flags & 2 ? "idmap: id INT64_MIN is reserved" : "idmap: duplicate ids");
+    }
+    h->idm_cap[which] = cap; h->idm_n[which] = n;
+    return CTR_OK;
+}
+
+int ctr_idmap_lookup_dev(ctr_handle* h, int which, const int64_t* d_ids, int64_t n, int32_t* d_rows) {
+    if (!h || !d_ids || !d_rows || which < 0 || which > 1 || n < 1) return set_err(h, CTR_EINVAL, "bad idmap lookup arguments");
+    if (!h->idm_keys[which]) return set_err(h, CTR_ESTATE, "idmap %d not built", which);
+    CU(h, cudaSetDevice(h->dev));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, h->num_sms * 8));
+    return launch(h, "idmap_lookup", [&] {
+        k_idmap_lookup<<<grid, 256, 0, h->stream>>>(h->idm_keys[which], h->idm_vals[which], h->idm_cap[which] - 1, (const long long*)d_ids, (long)n, d_rows);
+    });
+}
+
+int ctr_idmap_lookup(ctr_handle* h, int which, const int64_t* ids, int64_t n, int32_t* rows) {
+    if (!h || !ids || !rows || which < 0 || which > 1 || n < 1) return set_err(h, CTR_EINVAL, "bad idmap lookup arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    long long* d_ids = nullptr; int* d_rows = nullptr;
+    int rc = CTR_OK;
+    if (cudaMalloc(&d_ids, sizeof(long long) * (size_t)n) != cudaSuccess || cudaMalloc(&d_rows, sizeof(int) * (size_t)n) != cudaSuccess) rc = set_err(h, CTR_ENOMEM, "idmap lookup buffers");
+    if (rc == CTR_OK) {
+        cudaMemcpyAsync(d_ids, ids, sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+        rc = ctr_idmap_lookup_dev(h, which, (const int64_t*)d_ids, n, d_rows);
+        if (rc == CTR_OK && (cudaMemcpyAsync(rows, d_rows, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                             cudaStreamSynchronize(h->stream) != cudaSuccess)) rc = set_err(h, CTR_ECUDA, "idmap lookup copy: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    for (void* p : {(void*)d_ids, (void*)d_rows}) if (p) cudaFree(p);
+    return rc;
+}
+
+int ctr_batch_predict_keys(ctr_handle* h, const int64_t* user_ids, const int64_t* item_ids, const int64_t* ts, int64_t n, float* scores) {
+    if (!h || !user_ids || !item_ids || !ts || !scores || n < 1) return set_err(h, CTR_EINVAL, "bad batch predict arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    if (!h->idm_keys[0] || !h->idm_keys[1]) return set_err(h, CTR_ESTATE, "batch predict needs both id maps (ctr_idmap_build)");
+    const int B = h->cfg.pred_batch, S = h->cfg.S;
+    if (!h->k_keys) {       // device + pinned staging: [user ids | item ids | ts] and {first user row}
+        RET(dalloc(h, &h->k_keys, (size_t)3 * B, false));
+        CU(h, cudaMallocHost(&h->k_host, sizeof(long long) * (size_t)3 * B + sizeof(float) * (size_t)B + 16));
+    }
+    long long* hk = h->k_host;
+    float* hs = (float*)(hk + (size_t)3 * B);
+    int* hfirst = (int*)(hs + B);
+    for (int64_t s = 0; s < n; s += B) {
+        const int nb = (int)std::min<int64_t>(B, n - s);
+        memcpy(hk, user_ids + s, sizeof(long long) * (size_t)nb);
+        memcpy(hk + nb, item_ids + s, sizeof(long long) * (size_t)nb);
+        memcpy(hk + 2 * (size_t)nb, ts + s, sizeof(long long) * (size_t)nb);
+        CU(h, cudaMemcpyAsync(h->k_keys, hk, sizeof(long long) * (size_t)3 * nb, cudaMemcpyHostToDevice, h->stream));
+        RET(launch(h, "keys_resolve", [&] {
+            k_keys_resolve<<<grid_for_warps(h, nb), 256, 0, h->stream>>>(h->idm_keys[0], h->idm_vals[0], h->idm_cap[0] - 1, h->idm_keys[1], h->idm_vals[1], h->idm_cap[1] - 1,
+                                                                    h->ub_off, h->ub_ts, h->ub_items, (long)h->ub_users, h->k_keys, nb, S, h->s_user, h->s_item, h->s_hist);
+        }));
+        if (s == 0) CU(h, cudaMemcpyAsync(hfirst, h->s_user, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        RET(ctr_predict_idx_dev(h, h->s_user, h->s_item, h->s_hist, nb, nullptr));
+        CU(h, cudaMemcpyAsync(hs, h->P, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        // rcmd.go:297-300: an unresolvable FIRST key is an error, later ones become zero rows
+        if (s == 0 && *hfirst < 0) return set_err(h, CTR_ENOTFOUND, "get sample vector error: user %lld or item %lld has no features", (long long)user_ids[0], (long long)item_ids[0]);
+        memcpy(scores + s, hs, sizeof(float) * (size_t)nb);
+    }
+    return CTR_OK;
+}
+
+namespace {
+struct CkptHeader {
+    char magic[8];                 // "CTRB200\0"
+    int32_t version, model, uP, S, D, cF, H0, H1, rank, world;
+    uint32_t step;
+    int32_t has_table[3];
+    int64_t tab_rows[3], tab_local_rows[3];
+    int32_t tab_width[3];
+    int32_t pad;
+};
+constexpr size_t kCkptChunk = 32u << 20;
+
+// device [rows, ld] → file as compact [rows, width], through a pinned bounce buffer
+int ckpt_write_2d(ctr_handle* h, FILE* f, const float* d, long ld, int64_t rows, int width, float* bounce) {
+    const int64_t per = std::max<int64_t>(1, (int64_t)(kCkptChunk / sizeof(float)) / width);
+    for (int64_t r = 0; r < rows; r += per) {
+        const int64_t nr = std::min(per, rows - r);
+        CU(h, cudaMemcpy2DAsync(bounce, (size_t)width * sizeof(float), d + (size_t)r * ld, (size_t)ld * sizeof(float), (size_t)width * sizeof(float), (size_t)nr, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (fwrite(bounce, sizeof(float), (size_t)nr * width, f) != (size_t)nr * width) return set_err(h, CTR_EIO, "checkpoint: short write");
+    }
+    return CTR_OK;
+}
+int ckpt_read_2d(ctr_handle* h, FILE* f, float* d, long ld, int64_t rows, int width, float* bounce) {
+    const int64_t per = std::max<int64_t>(1, (int64_t)(kCkptChunk / sizeof(float)) / width);
+    for (int64_t r = 0; r < rows; r += per) {
+        const int64_t nr = std::min(per, rows - r);
+        if (fread(bounce, sizeof(float), (size_t)nr * width, f) != (size_t)nr * width) return set_err(h, CTR_EIO, "checkpoint: truncated file");
+        CU(h, cudaMemcpy2DAsync(d + (size_t)r * ld, (size_t)ld * sizeof(float), bounce, (size_t)width * sizeof(float), (size_t)width * sizeof(float), (size_t)nr, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    return CTR_OK;
+}
+// the four learnable tensors in their logical (reference JSON) shapes
+void dense_shape(const ctr_handle* h, int i, int64_t* rows, int* width, long* ld) {
+    const ctr_config& c = h->cfg;
+    if (i == 0) { *rows = h->in; *width = c.H0; *ld = h->H0p; }
+    else if (i == 1) { *rows = c.H0; *width = c.H1; *ld = h->H1p; }
+    else if (i == 2) { *rows = 1; *width = c.H1; *ld = h->H1p; }
+    else { *rows = 1; *width = c.S; *ld = h->Sp; }
+}
+}  // namespace
+
+int ctr_checkpoint_save(ctr_handle* h, const char* path) {
+    if (!h || !path) return set_err(h, CTR_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    CU(h, cudaStreamSynchronize(h->stream));
+    FILE* f = fopen(path, "wb");
+    if (!f) return set_err(h, CTR_EIO, "checkpoint: cannot open %s for writing", path);
+    float* bounce = nullptr;
+    if (cudaMallocHost(&bounce, kCkptChunk) != cudaSuccess) { fclose(f); return set_err(h, CTR_ENOMEM, "checkpoint bounce buffer"); }
+    const ctr_config& c = h->cfg;
+    CkptHeader hd{};
+    memcpy(hd.magic, "CTRB200", 8);
+    hd.version = 1; hd.model = c.model; hd.uP = c.uP; hd.S = c.S; hd.D = c.D; hd.cF = c.cF; hd.H0 = c.H0; hd.H1 = c.H1;
+    hd.rank = h->comm.rank; hd.world = h->comm.world; hd.step = h->step;
+    for (int t = 0; t < 3; t++) { hd.has_table[t] = h->tab[t] != nullptr; hd.tab_rows[t] = h->tab_rows[t]; hd.tab_local_rows[t] = h->tab_local_rows[t]; hd.tab_width[t] = h->tab_width[t]; }
+    int rc = fwrite(&hd, sizeof hd, 1, f) == 1 ? CTR_OK : set_err(h, CTR_EIO, "checkpoint: short write");
+    for (int i = 0; i < 4 && rc == CTR_OK; i++) {
+        int64_t rows; int width; long ld; dense_shape(h, i, &rows, &width, &ld);
+        for (float* src : {h->W[i], h->Mo[i], h->Vo[i]}) if (rc == CTR_OK) rc = ckpt_write_2d(h, f, src, ld, rows, width, bounce);
+    }
+    for (int t = 0; t < 3 && rc == CTR_OK; t++)
+        if (h->tab[t]) rc = ckpt_write_2d(h, f, h->tab[t], h->tab_ld[t], h->tab_local_rows[t], h->tab_width[t], bounce);
+    cudaFreeHost(bounce);
+    if (fclose(f) != 0 && rc == CTR_OK) rc = set_err(h, CTR_EIO, "checkpoint: close failed");
+    return rc;
+}
+
+int ctr_checkpoint_load(ctr_handle* h, const char* path) {
+    if (!h || !path) return set_err(h, CTR_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_err(h, CTR_EIO, "checkpoint: cannot open %s", path);
+    CkptHeader hd{};
+    const ctr_config& c = h->cfg;
+    int rc = CTR_OK;
+    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "CTRB200", 8) != 0 || hd.version != 1) rc = set_err(h, CTR_EIO, "checkpoint: %s is not a version-1 ctr-b200 snapshot", path);
+    else if (hd.model != c.model || hd.uP != c.uP || hd.S != c.S || hd.D != c.D || hd.cF != c.cF || hd.H0 != c.H0 || hd.H1 != c.H1)
+        rc = set_err(h, CTR_EINVAL, "checkpoint: model dims differ from this handle");
+    else if (hd.rank != h->comm.rank || hd.world != h->comm.world) rc = set_err(h, CTR_EINVAL, "checkpoint: written by rank %d/%d, this handle is %d/%d", hd.rank, hd.world, h->comm.rank, h->comm.world);
+    float* bounce = nullptr;
+    if (rc == CTR_OK && cudaMallocHost(&bounce, kCkptChunk) != cudaSuccess) rc = set_err(h, CTR_ENOMEM, "checkpoint bounce buffer");
+    for (int i = 0; i < 4 && rc == CTR_OK; i++) {
+        int64_t rows; int width; long ld; dense_shape(h, i, &rows, &width, &ld);
+        for (float* dst : {h->W[i], h->Mo[i], h->Vo[i]}) if (rc == CTR_OK) rc = ckpt_read_2d(h, f, dst, ld, rows, width, bounce);
+    }
+    for (int t = 0; t < 3 && rc == CTR_OK; t++) {
+        if (!hd.has_table[t]) continue;
+        const int want = t == CTR_TABLE_USER_FEAT ? c.uP : t == CTR_TABLE_ITEM_FEAT ? c.cF : c.D;
+        if (hd.tab_width[t] != want || hd.tab_rows[t] < 1 || hd.tab_local_rows[t] < 0) { rc = set_err(h, CTR_EIO, "checkpoint: bad table %d header", t); break; }
+        if (h->tab[t]) { cudaFree(h->tab[t]); h->tab[t] = nullptr; }
+        const long ld = round_up(hd.tab_width[t], 4);
+        const size_t bytes = (size_t)std::max<int64_t>(hd.tab_local_rows[t], 1) * ld * sizeof(float);
+        if (cudaMalloc(&h->tab[t], bytes) != cudaSuccess) { cudaGetLastError(); rc = set_err(h, CTR_ENOMEM, "checkpoint: table %d (%zu bytes)", t, bytes); break; }
+        cudaMemsetAsync(h->tab[t], 0, bytes, h->stream);
+        h->tab_ld[t] = ld; h->tab_rows[t] = hd.tab_rows[t]; h->tab_local_rows[t] = hd.tab_local_rows[t]; h->tab_width[t] = hd.tab_width[t];
+        rc = ckpt_read_2d(h, f, h->tab[t], ld, hd.tab_local_rows[t], hd.tab_width[t], bounce);
+        if (t == CTR_TABLE_ITEM_EMB && h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; h->hot_rows = 0; }
+    }
+    if (bounce) cudaFreeHost(bounce);
+    fclose(f);
+    if (rc == CTR_OK) { h->step = hd.step; h->um.dirty = true; cudaStreamSynchronize(h->stream); }
     return rc;
 }
 

@@ -11,12 +11,14 @@ from . import build as _build
 
 __all__ = ["Engine", "Config", "StepStats", "CtrError", "load_library", "MODEL_YOUTUBE", "MODEL_DIN_COS",
            "MODEL_DIN_EUC", "TABLE_USER_FEAT", "TABLE_ITEM_FEAT", "TABLE_ITEM_EMB", "TABLE_FROZEN", "TABLE_SGD",
-           "TABLE_SGD_DETERMINISTIC", "GEMM_AUTO", "GEMM_FP32", "GEMM_TCGEN05_3XTF32", "EXPORTS"]
+           "TABLE_SGD_DETERMINISTIC", "GEMM_AUTO", "GEMM_FP32", "GEMM_TCGEN05_3XTF32", "EXPORTS", "IDMAP_USER", "IDMAP_ITEM", "ENOTFOUND"]
 
 MODEL_YOUTUBE, MODEL_DIN_COS, MODEL_DIN_EUC = 0, 1, 2
 TABLE_USER_FEAT, TABLE_ITEM_FEAT, TABLE_ITEM_EMB = 0, 1, 2
 TABLE_FROZEN, TABLE_SGD, TABLE_SGD_DETERMINISTIC = 0, 1, 2
 GEMM_AUTO, GEMM_FP32, GEMM_TCGEN05_3XTF32 = 0, 1, 2
+IDMAP_USER, IDMAP_ITEM = 0, 1
+ENOTFOUND = 7
 
 # every symbol include/ctr_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ["ctr_abi_version", "ctr_config_default", "ctr_create", "ctr_destroy", "ctr_last_error",
@@ -24,7 +26,8 @@ EXPORTS = ["ctr_abi_version", "ctr_config_default", "ctr_create", "ctr_destroy",
            "ctr_gather_rows", "ctr_train_dense", "ctr_predict_dense", "ctr_train_step_idx", "ctr_train_idx", "ctr_predict_idx",
            "ctr_train_step_idx_dev", "ctr_predict_idx_dev", "ctr_last_cost", "ctr_sync", "ctr_get_stream",
            "ctr_set_stream", "ctr_launch_count", "ctr_profile_enable", "ctr_profile_get", "ctr_profile_reset",
-           "ctr_profile_dump", "ctr_debug_grads_idx", "ctr_ubcache_upload", "ctr_ubcache_window", "ctr_ubcache_window_dev", "ctr_roc_auc", "ctr_i2v_config_default", "ctr_i2v_paths", "ctr_i2v_train", "ctr_comm_unique_id", "ctr_comm_init"]
+           "ctr_profile_dump", "ctr_debug_grads_idx", "ctr_ubcache_upload", "ctr_ubcache_window", "ctr_ubcache_window_dev", "ctr_idmap_build", "ctr_idmap_lookup", "ctr_idmap_lookup_dev",
+           "ctr_batch_predict_keys", "ctr_checkpoint_save", "ctr_checkpoint_load", "ctr_roc_auc", "ctr_i2v_config_default", "ctr_i2v_paths", "ctr_i2v_train", "ctr_comm_unique_id", "ctr_comm_init"]
 
 
 class CtrError(RuntimeError):
@@ -48,6 +51,7 @@ class StepStats(C.Structure):
 
 _lib = None
 _fp = C.POINTER(C.c_float)
+_lp = C.POINTER(C.c_int64)
 _ip = C.POINTER(C.c_int32)
 
 
@@ -287,6 +291,31 @@ class Engine:
         out = np.empty((u.size, self.cfg.S), np.int32)
         self._ck(self.L.ctr_ubcache_window(self.h, up, t.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int32(u.size), out.ctypes.data_as(_ip)))
         return out
+
+    def idmap_build(self, which, ids):
+        a = np.ascontiguousarray(ids, np.int64)
+        self._ck(self.L.ctr_idmap_build(self.h, C.c_int(which), a.ctypes.data_as(_lp), C.c_int64(a.size)))
+
+    def idmap_lookup(self, which, ids):
+        a = np.ascontiguousarray(ids, np.int64)
+        out = np.empty(a.size, np.int32)
+        self._ck(self.L.ctr_idmap_lookup(self.h, C.c_int(which), a.ctypes.data_as(_lp), C.c_int64(a.size), out.ctypes.data_as(_ip)))
+        return out
+
+    def batch_predict_keys(self, user_ids, item_ids, ts):
+        """recommend.BatchPredict (rcmd.go:282-337) over Sample keys."""
+        u = np.ascontiguousarray(user_ids, np.int64); i = np.ascontiguousarray(item_ids, np.int64); t = np.ascontiguousarray(ts, np.int64)
+        assert u.size == i.size == t.size
+        out = np.empty(u.size, np.float32)
+        self._ck(self.L.ctr_batch_predict_keys(self.h, u.ctypes.data_as(_lp), i.ctypes.data_as(_lp), t.ctypes.data_as(_lp), C.c_int64(u.size),
+                                                out.ctypes.data_as(_fp)))
+        return out
+
+    def checkpoint_save(self, path):
+        self._ck(self.L.ctr_checkpoint_save(self.h, C.c_char_p(str(path).encode())))
+
+    def checkpoint_load(self, path):
+        self._ck(self.L.ctr_checkpoint_load(self.h, C.c_char_p(str(path).encode())))
 
     def roc_auc(self, pred, y):
         p, pp = _f(pred); t, tp = _f(y)

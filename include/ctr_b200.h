@@ -23,7 +23,7 @@ extern "C" {
 
 #define CTR_B200_ABI_VERSION 1
 
-enum { CTR_OK = 0, CTR_EINVAL = 1, CTR_ENODEV = 2, CTR_ECUDA = 3, CTR_ENOMEM = 4, CTR_ESTATE = 5, CTR_ECOMM = 6 };
+enum { CTR_OK = 0, CTR_EINVAL = 1, CTR_ENODEV = 2, CTR_ECUDA = 3, CTR_ENOMEM = 4, CTR_ESTATE = 5, CTR_ECOMM = 6, CTR_ENOTFOUND = 7, CTR_EIO = 8 };
 
 /* which graph: model/youtube/dnn.go:162-184 | model/din/din.go:219-323 (cosine, live) |
  * din.go:230 + model/activation.go:23-50 (euclidean ActivationUnit variant) */
@@ -174,6 +174,34 @@ int ctr_debug_grads_idx(ctr_handle* h, const int32_t* user_row, const int32_t* i
 int ctr_ubcache_upload(ctr_handle* h, const int64_t* offsets, const int64_t* ts, const int32_t* item_rows, int64_t n_users, int64_t n);
 int ctr_ubcache_window(ctr_handle* h, const int32_t* user_row, const int64_t* max_ts, int32_t B, int32_t* hist_rows);
 int ctr_ubcache_window_dev(ctr_handle* h, const int32_t* d_user_row, const int64_t* d_max_ts, int32_t B, int32_t* d_hist_rows);
+
+/* ---- sparse ids, serving keys, checkpoint ------------------------------------
+ * The reference keys its caches by the decimal string of a Go int (rcmd.go:472,484,502,520); the engine's
+ * tables are dense.  ctr_idmap_build puts `ids[i] → row i` into a device hash table (which: CTR_IDMAP_*);
+ * duplicate ids or INT64_MIN are rejected (CTR_EINVAL).  lookup writes the row, or -1 for an unknown id —
+ * which the gather reads as a zero row, the reference's "not found → zeros" (rcmd.go:501-505,520-522). */
+enum { CTR_IDMAP_USER = 0, CTR_IDMAP_ITEM = 1 };
+int ctr_idmap_build(ctr_handle* h, int which, const int64_t* ids, int64_t n);
+int ctr_idmap_lookup(ctr_handle* h, int which, const int64_t* ids, int64_t n, int32_t* rows);
+int ctr_idmap_lookup_dev(ctr_handle* h, int which, const int64_t* d_ids, int64_t n, int32_t* d_rows);
+
+/* recommend.BatchPredict (rcmd.go:282-337) over sample keys {UserId, ItemId, Timestamp} (rcmd.go:50-54),
+ * entirely on the device: id maps → rows, ubcache window at the sample's timestamp → history rows,
+ * forward → scores [n].  Needs both id maps; without an uploaded ubcache the history is empty (the
+ * reference's "UserBehavior not implemented → zeros", rcmd.go:498,507).  A key whose user or item is
+ * unknown scores as an all-zero X row (rcmd.go:296-306) — unless it is key 0, which fails the call with
+ * CTR_ENOTFOUND as the reference returns the error (rcmd.go:297-300).  recommend.Rank (rcmd.go:248-280) =
+ * this with one user id, the candidate item ids and ts = now. */
+int ctr_batch_predict_keys(ctr_handle* h, const int64_t* user_ids, const int64_t* item_ids, const int64_t* ts,
+                           int64_t n, float* scores);
+
+/* Binary snapshot of everything a resumed run needs: dims, optimiser step, dense weights with their Adam
+ * moments, and the three tables (this rank's shard of ITEM_EMB when world > 1 — use one path per rank).
+ * The reference has no checkpoint at all (JSON weights only, din.go:62); that JSON stays
+ * available through ctr_get_weights / ctr_set_weights.  load requires a handle created with the same
+ * dims, rank and world; tables are (re)allocated from the file. */
+int ctr_checkpoint_save(ctr_handle* h, const char* path);
+int ctr_checkpoint_load(ctr_handle* h, const char* path);
 
 /* utils.RocAuc32 (util.go:131-148 → nn/metrics/ranking.go:144): labels binarised at 0.5, tied
  * scores grouped, trapezoid. Sorted on the device. */

@@ -194,7 +194,8 @@ void orc_gather_rows(const float* user_feat, long ldu, const float* item_feat, l
 #pragma omp parallel for schedule(static)
     for (long b = 0; b < B; b++) {
         float* x = X + b * xc;
-        memcpy(x, user_feat + (long)user_row[b] * ldu, sizeof(float) * (size_t)uP);
+        if (user_row[b] >= 0) memcpy(x, user_feat + (long)user_row[b] * ldu, sizeof(float) * (size_t)uP);
+        else memset(x, 0, sizeof(float) * (size_t)uP);   /* BatchPredict's zero row, rcmd.go:296-306 */
         float* ub = x + uP;
         for (int s = 0; s < S; s++) {
             int32_t r = hist[b * S + s];

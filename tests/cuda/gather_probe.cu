@@ -198,6 +198,90 @@ __global__ void __launch_bounds__(NT, MINB) k_gate(const float* __restrict__ emb
     }
 }
 
+// ---- same math, rows staged through a per-warp shared-memory ring with cp.async (LDGSTS): NST-1 groups of
+// 8 rows stay in flight per warp at no register cost, and the pipeline runs across sample boundaries.
+// Sequence per sample: position 0 = item row, 1..50 = history rows; group g = positions 8g..8g+7 (7 groups).
+__device__ __forceinline__ void cp16(void* dst, const void* src, int bytes) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+template <int NST, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_gate_ring(const float* __restrict__ emb, const int* __restrict__ idx, const int* __restrict__ item,
+                                                      const float* __restrict__ att, float* __restrict__ out, int B) {
+    extern __shared__ float4 ring[];
+    constexpr int NG = 7;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lir = lane & 3, sub = lane >> 2;
+    const int nw = gridDim.x * (NT / 32), w = blockIdx.x * (NT / 32) + wib;
+    float4* wb = ring + wib * NST * 128;
+    const float invS = 1.0f / 50.0f;
+    auto load_ids = [&](int b, int& p0, int& p1) {
+        p0 = p1 = -1;
+        if (b < B) { p0 = lane == 0 ? item[b] : idx[(long)b * S + lane - 1]; if (lane + 32 <= 50) p1 = idx[(long)b * S + lane + 31]; }
+    };
+    const int nsamp = w < B ? (B - w + nw - 1) / nw : 0;
+    const int T = nsamp * NG;
+    int i0, i1, n0, n1;                       // ids of the sample being issued, and of the one after it
+    load_ids(w, i0, i1); load_ids(w + nw, n0, n1);
+    int ib = w, ig = 0, kiss = 0;             // issue cursor
+    auto issue = [&]() {
+        if (kiss < T) {
+            const int slot = kiss % NST;
+            const int src = ig < 4 ? i0 : i1;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int rg = 2 * j + (lane >> 4), p = 8 * ig + rg;
+                const int id = __shfl_sync(0xffffffffu, src, p & 31);
+                const int c = lane & 15;
+                cp16(wb + slot * 128 + rg * 16 + (c ^ ((rg & 1) << 2)), emb + (long)(id >= 0 ? id : 0) * D + c * 4, id >= 0 ? 16 : 0);
+            }
+            if (++ig == NG) { ig = 0; ib += nw; i0 = n0; i1 = n1; load_ids(ib + nw, n0, n1); }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        kiss++;
+    };
+#pragma unroll
+    for (int j = 0; j < NST - 1; j++) issue();
+    float4 v[4], acc[4]; float ny = 0.f;
+    int cb = w, cg = 0;
+    for (int k = 0; k < T; k++) {
+        issue();
+        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");
+        __syncwarp();
+        const float4* sl = wb + (k % NST) * 128;
+        if (cg == 0) {
+            float ny2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { v[q] = sl[q * 4 + lir]; ny2 += d4(v[q], v[q]); acc[q] = make_float4(0, 0, 0, 0); }
+            ny = fsq(gsum<4>(ny2));
+        }
+        {
+            const int p = 8 * cg + sub, s = p - 1;
+            float4 u[4]; float dot = 0.f, nx2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { u[q] = sl[sub * 16 + ((q * 4 + lir) ^ ((sub & 1) << 2))]; dot += d4(u[q], v[q]); nx2 += d4(u[q], u[q]); }
+            dot = gsum<4>(dot); nx2 = gsum<4>(nx2);
+            const float cs = dot * frcp(fsq(nx2) * ny + 1e-8f);
+            float a = sigf((cs + 1.0f) * 0.5f * ((s >= 0 && s < 50) ? __ldg(att + s) : 0.0f));
+            if (s < 0 || s >= 50) a = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { acc[q].x = fmaf(a, u[q].x, acc[q].x); acc[q].y = fmaf(a, u[q].y, acc[q].y); acc[q].z = fmaf(a, u[q].z, acc[q].z); acc[q].w = fmaf(a, u[q].w, acc[q].w); }
+        }
+        if (++cg == NG) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o); acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+                    acc[q].z += __shfl_xor_sync(0xffffffffu, acc[q].z, o); acc[q].w += __shfl_xor_sync(0xffffffffu, acc[q].w, o);
+                }
+                if (sub == 0) *reinterpret_cast<float4*>(out + (long)cb * D + (q * 4 + lir) * 4) = make_float4(acc[q].x * invS, acc[q].y * invS, acc[q].z * invS, acc[q].w * invS);
+            }
+            cg = 0; cb += nw;
+        }
+        __syncwarp();
+    }
+}
+
 int main(int argc, char** argv) {
     long I = argc > 1 ? atol(argv[1]) : 12500000; int B = 65536;
     float* emb; int* idx; float* out;
@@ -254,6 +338,21 @@ int main(int argc, char** argv) {
         run("g 8x2 unr4 nopipe 128/6", [&] { k_gate<8, 2, 4, 0, 128, 6><<<148 * 16, 128>>>(emb, idx, item, att, out, B); });
         run("g 4x4 unr1 nopipe 128/8", [&] { k_gate<4, 4, 1, 0, 128, 8><<<148 * 16, 128>>>(emb, idx, item, att, out, B); });
         run("g 16x1 unr4 nopipe 128/8", [&] { k_gate<16, 1, 4, 0, 128, 8><<<148 * 16, 128>>>(emb, idx, item, att, out, B); });
+        {
+            auto ringrun = [&](const char* name, auto kern, int nst, int nt, int blocks_per_sm) {
+                size_t sm = (size_t)(nt / 32) * nst * 2048;
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                run(name, [&] { kern<<<148 * blocks_per_sm, nt, sm>>>(emb, idx, item, att, out, B); });
+            };
+            ringrun("ring nst3 128/8", k_gate_ring<3, 128, 8>, 3, 128, 8);
+            ringrun("ring nst4 128/6", k_gate_ring<4, 128, 6>, 4, 128, 6);
+            ringrun("ring nst2 128/8", k_gate_ring<2, 128, 8>, 2, 128, 8);
+            ringrun("ring nst3 128/6", k_gate_ring<3, 128, 6>, 3, 128, 6);
+            ringrun("ring nst6 128/4", k_gate_ring<6, 128, 4>, 6, 128, 4);
+            ringrun("ring nst3 256/4", k_gate_ring<3, 256, 4>, 3, 256, 4);
+            ringrun("ring nst3 128/7", k_gate_ring<3, 128, 7>, 3, 128, 7);
+            ringrun("ring nst4 128/7", k_gate_ring<4, 128, 7>, 4, 128, 7);
+        }
         run("g 2x8 pipe 128/4", [&] { k_gate<2, 8, 1, 1, 128, 4><<<148 * 16, 128>>>(emb, idx, item, att, out, B); });
     }
     return 0;
