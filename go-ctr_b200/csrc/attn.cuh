@@ -56,16 +56,20 @@ __device__ __forceinline__ const float* ub_ptr(const RowSrc& r, const Dims& d, c
     return ub_ref(r, d, hi, use_hi, b, s).p;
 }
 
-// fast reciprocal / sigmoid for the attention gate (MUFU.RCP / MUFU.EX2; relative error ~1e-6,
-// two orders below the 1e-4 parity bar)
-__device__ __forceinline__ float frcp(float x) { return __fdividef(1.0f, x); }
+// MUFU-based reciprocal / sigmoid / sqrt for the attention gate, flush-to-zero forms (no denormal fix-up code
+// around the MUFU): relative error ~1e-6, two orders below the 1e-4 parity bar
+__device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_ftz(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float frcp(float x) { return rcp_ftz(x); }
+// gorgonia's float32 sigmoid saturates outside [-88, 15]; below -88 the formula itself yields 1/(1+inf) = 0
 __device__ __forceinline__ float sigmoid_fast(float x) {
-    if (x < -88.0f) return 0.0f;
-    if (x > 15.0f) return 1.0f;
-    return frcp(1.0f + __expf(-x));
+    const float r = rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x));
+    return x > 15.0f ? 1.0f : r;
 }
-// sqrt(x) for x >= 0 through MUFU.RSQ
-__device__ __forceinline__ float fsqrt_pos(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
+// sqrt(x) for x >= 0 through MUFU.RSQ; squared norms below 1e-30 count as zero (they sit under the 1e-8 the
+// cosine denominator adds anyway, activation.go:80)
+__device__ __forceinline__ float fsqrt_pos(float x) { return x > 1e-30f ? x * rsqrt_ftz(x) : 0.0f; }
 
 // attention gate of one row given the group-reduced dot products (generic kernels)
 __device__ __forceinline__ float gate_cos(float dot, float nx2, float ny, float att_s) {
@@ -235,22 +239,23 @@ k_attn_fwd_idx(RowSrc r, Dims d, const float* __restrict__ att, float* __restric
         const float* ip = r.emb + (long)(id.z >= 0 ? id.z : 0) * r.lde;
 #pragma unroll
         for (int q = 0; q < VPL; q++) { v[q] = id.z >= 0 ? ldg4(ip + (q * LPR + lir) * 4) : zero4(); acc[q] = zero4(); }
-        bool first = true;
-        float ny = 0.0f;
-        for (int s0 = 0; s0 < d.S; s0 += RPW) {
+        // history rows: the loads of a group are issued, then (first group only) the item row's norm is formed
+        // while they are in flight, then the group is consumed
+        auto load_rows = [&](float4 (&u)[VPL], int s0) {
             const int s = s0 + sub;
             const int a0 = __shfl_sync(0xffffffffu, id.x, s & 31), a1 = __shfl_sync(0xffffffffu, id.y, s & 31);
             const int row = s < d.S ? (s < 32 ? a0 : a1) : -1;
-            float4 u[VPL];
-            const float* p = r.emb + (long)(row >= 0 ? row : 0) * r.lde;
+            const float* p = r.emb + (long)(row >= 0 ? row : 0) * r.lde + lir * 4;
 #pragma unroll
-            for (int q = 0; q < VPL; q++) u[q] = row >= 0 ? ldg4_stream(p + (q * LPR + lir) * 4) : zero4();
-            if (first) {         // the item row's norm is not needed before the first history rows are in flight
+            for (int q = 0; q < VPL; q++) u[q] = row >= 0 ? ldg4_stream(p + q * LPR * 4) : zero4();
+        };
+        float4 u[VPL];
+        load_rows(u, 0);
 #pragma unroll
-                for (int q = 0; q < VPL; q++) ny2 += dot4(v[q], v[q]);
-                ny = fsqrt_pos(group_sum<LPR>(ny2));
-                first = false;
-            }
+        for (int q = 0; q < VPL; q++) ny2 += dot4(v[q], v[q]);
+        const float ny = fsqrt_pos(group_sum<LPR>(ny2));
+        for (int s0 = 0;;) {
+            const int s = s0 + sub;
             float a = 1.0f;
             if (MODEL == MODEL_DIN_COS) {
                 float dot = 0.0f, nx2 = 0.0f;
@@ -270,6 +275,9 @@ k_attn_fwd_idx(RowSrc r, Dims d, const float* __restrict__ att, float* __restric
             }
 #pragma unroll
             for (int q = 0; q < VPL; q++) acc[q] = fma4(a, u[q], acc[q]);      // slots beyond S / missing rows carry u == 0
+            s0 += RPW;
+            if (s0 >= d.S) break;
+            load_rows(u, s0);
         }
 #pragma unroll
         for (int q = 0; q < VPL; q++) {
@@ -424,7 +432,7 @@ k_attn_bwd_vec(RowSrc r, Dims d, const float* __restrict__ att,
         }
         ny2 = group_sum<LPR>(ny2);
         const float ny = fsqrt_pos(ny2);
-        const float rny = ny2 > 0.0f ? rsqrtf(ny2) : 0.0f;
+        const float rny = ny2 > 1e-30f ? rsqrt_ftz(ny2) : 0.0f;
         float kvsum = 0.0f;                               // coefficient of -v in dv
         for (int s0 = 0; s0 < d.S; s0 += UNR * RPW) {
             float4 u[UNR][VPL]; int idx[UNR]; bool have[UNR];
@@ -464,7 +472,7 @@ k_attn_bwd_vec(RowSrc r, Dims d, const float* __restrict__ att,
                         if (lir == 0 && s < d.S) atomicAdd(&smem[s], dz * w);
                         const float cc = 0.5f * dz * att_s;
                         c1 = a * invS; c2 = cc * iden; c4 = c2;
-                        c3 = nx2 > 0.0f ? -cc * cs * ny * iden * rsqrtf(nx2) : 0.0f;     // -cc*cos*|v|/(|u| den)
+                        c3 = nx2 > 1e-30f ? -cc * cs * ny * iden * rsqrt_ftz(nx2) : 0.0f;     // -cc*cos*|v|/(|u| den)
                         kvsum += cc * cs * nx * iden * rny;                               //  cc*cos*|u|/(|v| den)
                     } else {
                         const float dist = fsqrt_pos(nx2);
@@ -472,7 +480,7 @@ k_attn_bwd_vec(RowSrc r, Dims d, const float* __restrict__ att,
                         const float a = sigmoid_fast(w * att_s);
                         const float dz = gu * invS * a * (1.0f - a);
                         if (lir == 0 && s < d.S) atomicAdd(&smem[s], dz * w);
-                        const float k = nx2 > 0.0f ? dz * att_s * rsqrtf(nx2) : 0.0f;    // dw/dist
+                        const float k = nx2 > 1e-30f ? dz * att_s * rsqrt_ftz(nx2) : 0.0f;    // dw/dist
                         c1 = a * invS; c3 = -k; c2 = k;      // du = c1 g - k (u - v)
                         c4 = s < d.S ? k : 0.0f;             // dv += k (u - v)
                         kvsum += c4;
@@ -526,21 +534,28 @@ k_attn_bwd_vec(RowSrc r, Dims d, const float* __restrict__ att,
             if (smem[j] != 0.0f) atomicAdd(o.datt + j, smem[j]);
 }
 
-// backward, index path: k_attn_bwd_vec's math with the dense-X route compiled out and the next sample's ids
-// prefetched through lane-private shared-memory slots (see k_attn_fwd_idx).  Requires S <= 64.
-template <int LPR, int VPL, int MODEL, int NT, int MINB>
+// backward, index path: k_attn_bwd_vec's math with the dense-X route compiled out, the next sample's ids
+// prefetched through lane-private shared-memory slots (see k_attn_fwd_idx), and the two per-sample vectors
+// every row needs — g = d cost/d pooled and the item row v — parked in shared memory instead of registers.
+// That frees the registers for the forward kernel's wide lane mapping (LPR lanes x VPL float4 per row, 32/LPR
+// rows per step), which halves the per-row share of the gate's scalar/shuffle/MUFU work against the
+// 8-lanes-per-row mapping the register-resident version was limited to.  FUSED: scatter-add + SGD straight into
+// the table / hot-row replicas (red.global.add.v4.f32); otherwise gradients go to the dUb / dIt buffers.
+// Requires S <= 64.
+template <int LPR, int VPL, int MODEL, bool FUSED, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
                const float* __restrict__ dX, long lddx, BwdOut o, int B) {
-    constexpr int RPW = 32 / LPR;
+    constexpr int RPW = 32 / LPR, CH = LPR * VPL;
     __shared__ float s_datt[64];
     __shared__ __align__(16) int4 s_ids[NT];
-    const int lane = threadIdx.x & 31, lir = lane % LPR, sub = lane / LPR;
-    const int gwarp = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    __shared__ __align__(16) float4 s_g[NT / 32][CH], s_v[NT / 32][CH];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, lir = lane % LPR, sub = lane / LPR;
+    const int gwarp = blockIdx.x * (NT / 32) + wib;
     const int nwarps = gridDim.x * (NT / 32);
     const int rep = o.hot_reps > 0 ? gwarp % o.hot_reps : 0;
     const float invS = 1.0f / (float)d.S;
-    const float sc = o.sgd ? o.neg_lr : 1.0f;         // fused SGD: gradients leave pre-scaled by -lr
+    const float sc = FUSED ? o.neg_lr : 1.0f;         // fused SGD: gradients leave pre-scaled by -lr
     if (threadIdx.x < 64) s_datt[threadIdx.x] = 0.0f;
     int* my_ids = reinterpret_cast<int*>(&s_ids[threadIdx.x]);
     *reinterpret_cast<int4*>(my_ids) = make_int4(-1, -1, -1, -1);
@@ -552,6 +567,8 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
         cp_async4(my_ids + 2, r.item_row + bb);
         cp_async_commit();
     };
+    const float4* gs = s_g[wib];
+    const float4* vs = s_v[wib];
     int b = gwarp;
     if (b < B) fetch_ids(b);
     while (b < B) {
@@ -559,33 +576,31 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
         const int4 id = *reinterpret_cast<const int4*>(my_ids);
         const int bn = b + nwarps;
         if (bn < B) fetch_ids(bn);
-        const float* ip = r.emb + (long)(id.z >= 0 ? id.z : 0) * r.lde;
-        float4 g[VPL], v[VPL], dvu[VPL];
-        float ny2 = 0.0f;
-#pragma unroll
-        for (int q = 0; q < VPL; q++) {
-            g[q] = ldg4(dX + (long)b * lddx + (q * LPR + lir) * 4);
-            // the table is written by this kernel (sgd mode): coherent loads, no .nc
-            v[q] = id.z >= 0 ? *reinterpret_cast<const float4*>(ip + (q * LPR + lir) * 4) : zero4();
-            dvu[q] = zero4();
+        // stage g and v (one float4 per lane; the table is written by this kernel in FUSED mode: coherent load)
+        if (lane < CH) {
+            s_g[wib][lane] = ldg4(dX + (long)b * lddx + 4 * lane);
+            s_v[wib][lane] = id.z >= 0 ? *reinterpret_cast<const float4*>(r.emb + (long)id.z * r.lde + 4 * lane) : zero4();
         }
-        float ny = 0.0f, rny = 0.0f, kvsum = 0.0f;        // kvsum: coefficient of -v in dv
-        bool first = true;
-        for (int s0 = 0; s0 < d.S; s0 += RPW) {
+        auto load_rows = [&](float4 (&u)[VPL], int& row, int s0) {
             const int s = s0 + sub;
             const int a0 = __shfl_sync(0xffffffffu, id.x, s & 31), a1 = __shfl_sync(0xffffffffu, id.y, s & 31);
-            const int row = s < d.S ? (s < 32 ? a0 : a1) : -1;
-            const float* p = r.emb + (long)(row >= 0 ? row : 0) * r.lde;
-            float4 u[VPL];
+            row = s < d.S ? (s < 32 ? a0 : a1) : -1;
+            const float* p = r.emb + (long)(row >= 0 ? row : 0) * r.lde + lir * 4;
 #pragma unroll
-            for (int q = 0; q < VPL; q++) u[q] = row >= 0 ? *reinterpret_cast<const float4*>(p + (q * LPR + lir) * 4) : zero4();
-            if (first) {
+            for (int q = 0; q < VPL; q++) u[q] = row >= 0 ? *reinterpret_cast<const float4*>(p + q * LPR * 4) : zero4();
+        };
+        float4 u[VPL], dvu[VPL];
+        int row;
+        load_rows(u, row, 0);
+        __syncwarp();
+        float ny2 = 0.0f;
 #pragma unroll
-                for (int q = 0; q < VPL; q++) ny2 += dot4(v[q], v[q]);
-                ny2 = group_sum<LPR>(ny2);
-                ny = fsqrt_pos(ny2); rny = ny2 > 0.0f ? rsqrtf(ny2) : 0.0f;
-                first = false;
-            }
+        for (int q = 0; q < VPL; q++) { const float4 t = vs[q * LPR + lir]; ny2 += dot4(t, t); dvu[q] = zero4(); }
+        ny2 = group_sum<LPR>(ny2);
+        const float ny = fsqrt_pos(ny2), rny = ny2 > 1e-30f ? rsqrt_ftz(ny2) : 0.0f;
+        float kvsum = 0.0f;                               // coefficient of -v in dv
+        for (int s0 = 0;;) {
+            const int s = s0 + sub;
             // du = c1*g + c2*v + c3*u ; dv += c4*u - (kv coefficient)*v
             float c1 = invS, c2 = 0.0f, c3 = 0.0f, c4 = 0.0f;
             if (MODEL != MODEL_YOUTUBE) {
@@ -593,10 +608,11 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
                 float gu = 0.0f, dot = 0.0f, nx2 = 0.0f;
 #pragma unroll
                 for (int q = 0; q < VPL; q++) {
-                    gu += dot4(g[q], u[q]);
-                    if (MODEL == MODEL_DIN_COS) { dot += dot4(u[q], v[q]); nx2 += dot4(u[q], u[q]); }
+                    const float4 gq = gs[q * LPR + lir], vq = vs[q * LPR + lir];
+                    gu += dot4(gq, u[q]);
+                    if (MODEL == MODEL_DIN_COS) { dot += dot4(u[q], vq); nx2 += dot4(u[q], u[q]); }
                     else {
-                        const float4 e = make_float4(u[q].x - v[q].x, u[q].y - v[q].y, u[q].z - v[q].z, u[q].w - v[q].w);
+                        const float4 e = make_float4(u[q].x - vq.x, u[q].y - vq.y, u[q].z - vq.z, u[q].w - vq.w);
                         nx2 += dot4(e, e);
                     }
                 }
@@ -612,7 +628,7 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
                     if (lir == 0 && s < d.S) atomicAdd(&s_datt[s], dz * w);
                     const float cc = 0.5f * dz * att_s;
                     c1 = a * invS; c2 = cc * iden; c4 = c2;
-                    c3 = nx2 > 0.0f ? -cc * cs * ny * iden * rsqrtf(nx2) : 0.0f;     // -cc*cos*|v|/(|u| den)
+                    c3 = nx2 > 1e-30f ? -cc * cs * ny * iden * rsqrt_ftz(nx2) : 0.0f;   // -cc*cos*|v|/(|u| den)
                     kvsum += cc * cs * nx * iden * rny;                               //  cc*cos*|u|/(|v| den)
                 } else {
                     const float dist = fsqrt_pos(nx2);
@@ -620,7 +636,7 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
                     const float a = sigmoid_fast(w * att_s);
                     const float dz = gu * invS * a * (1.0f - a);
                     if (lir == 0 && s < d.S) atomicAdd(&s_datt[s], dz * w);
-                    const float k = nx2 > 0.0f ? dz * att_s * rsqrtf(nx2) : 0.0f;    // dw/dist
+                    const float k = nx2 > 1e-30f ? dz * att_s * rsqrt_ftz(nx2) : 0.0f;  // dw/dist
                     c1 = a * invS; c3 = -k; c2 = k;      // du = c1 g - k (u - v)
                     c4 = s < d.S ? k : 0.0f;             // dv += k (u - v)
                     kvsum += c4;
@@ -628,17 +644,22 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
             }
             if (s < d.S) {
                 const float e1 = c1 * sc, e2 = c2 * sc, e3 = c3 * sc;
-                float* dst = (o.sgd && row >= 0) ? scatter_dst(r, d, o, row, rep) : nullptr;
+                float* dst = nullptr;
+                if (FUSED) { if (row >= 0) dst = scatter_dst(r, d, o, row, rep) + lir * 4; }
+                else if (o.dUb) dst = o.dUb + ((long)b * d.S + s) * d.D + lir * 4;
 #pragma unroll
                 for (int q = 0; q < VPL; q++) {
+                    const float4 gq = gs[q * LPR + lir], vq = vs[q * LPR + lir];
                     float4 du;
-                    du.x = fmaf(e3, u[q].x, fmaf(e2, v[q].x, e1 * g[q].x)); du.y = fmaf(e3, u[q].y, fmaf(e2, v[q].y, e1 * g[q].y));
-                    du.z = fmaf(e3, u[q].z, fmaf(e2, v[q].z, e1 * g[q].z)); du.w = fmaf(e3, u[q].w, fmaf(e2, v[q].w, e1 * g[q].w));
+                    du.x = fmaf(e3, u[q].x, fmaf(e2, vq.x, e1 * gq.x)); du.y = fmaf(e3, u[q].y, fmaf(e2, vq.y, e1 * gq.y));
+                    du.z = fmaf(e3, u[q].z, fmaf(e2, vq.z, e1 * gq.z)); du.w = fmaf(e3, u[q].w, fmaf(e2, vq.w, e1 * gq.w));
                     dvu[q] = fma4(c4, u[q], dvu[q]);
-                    if (o.dUb) *reinterpret_cast<float4*>(o.dUb + ((long)b * d.S + s) * d.D + (q * LPR + lir) * 4) = du;
-                    if (dst) red_add4(dst + (q * LPR + lir) * 4, du);
+                    if (dst) { if (FUSED) red_add4(dst + q * LPR * 4, du); else *reinterpret_cast<float4*>(dst + q * LPR * 4) = du; }
                 }
             }
+            s0 += RPW;
+            if (s0 >= d.S) break;
+            load_rows(u, row, s0);
         }
         // dv = gi + sum_subgroups(dvu) - (sum kv) * v
 #pragma unroll
@@ -654,17 +675,20 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
             }
         }
         if (sub == 0) {
-            float* dst = (o.sgd && id.z >= 0) ? scatter_dst(r, d, o, id.z, rep) : nullptr;
+            float* dst = nullptr;
+            if (FUSED) { if (id.z >= 0) dst = scatter_dst(r, d, o, id.z, rep) + lir * 4; }
+            else if (o.dIt) dst = o.dIt + (long)b * d.D + lir * 4;
 #pragma unroll
             for (int q = 0; q < VPL; q++) {
                 const float4 gi = ldg4(dX + (long)b * lddx + d.D + (q * LPR + lir) * 4);
+                const float4 vq = vs[q * LPR + lir];
                 float4 dv;
-                dv.x = (gi.x + dvu[q].x - kvsum * v[q].x) * sc; dv.y = (gi.y + dvu[q].y - kvsum * v[q].y) * sc;
-                dv.z = (gi.z + dvu[q].z - kvsum * v[q].z) * sc; dv.w = (gi.w + dvu[q].w - kvsum * v[q].w) * sc;
-                if (o.dIt) *reinterpret_cast<float4*>(o.dIt + (long)b * d.D + (q * LPR + lir) * 4) = dv;
-                if (dst) red_add4(dst + (q * LPR + lir) * 4, dv);
+                dv.x = (gi.x + dvu[q].x - kvsum * vq.x) * sc; dv.y = (gi.y + dvu[q].y - kvsum * vq.y) * sc;
+                dv.z = (gi.z + dvu[q].z - kvsum * vq.z) * sc; dv.w = (gi.w + dvu[q].w - kvsum * vq.w) * sc;
+                if (dst) { if (FUSED) red_add4(dst + q * LPR * 4, dv); else *reinterpret_cast<float4*>(dst + q * LPR * 4) = dv; }
             }
         }
+        __syncwarp();          // s_g / s_v are rewritten for the next sample
         b = bn;
     }
     __syncthreads();

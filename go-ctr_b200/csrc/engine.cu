@@ -215,11 +215,14 @@ void launch_fwd_idx(ctr_handle* h, const RowSrc& r, int B) {
 template <int LPR, int VPL, int MINB>
 void launch_bwd_idx(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
     const int g = grid_attn(h, B);
+#define BWD_CASE(M) { if (o.sgd) k_attn_bwd_idx<LPR, VPL, M, true, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); \
+                      else       k_attn_bwd_idx<LPR, VPL, M, false, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); }
     switch (h->cfg.model) {
-        case CTR_MODEL_YOUTUBE: k_attn_bwd_idx<LPR, VPL, MODEL_YOUTUBE, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); break;
-        case CTR_MODEL_DIN_COS: k_attn_bwd_idx<LPR, VPL, MODEL_DIN_COS, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); break;
-        default:                k_attn_bwd_idx<LPR, VPL, MODEL_DIN_EUC, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); break;
+        case CTR_MODEL_YOUTUBE: BWD_CASE(MODEL_YOUTUBE) break;
+        case CTR_MODEL_DIN_COS: BWD_CASE(MODEL_DIN_COS) break;
+        default:                BWD_CASE(MODEL_DIN_EUC) break;
     }
+#undef BWD_CASE
 }
 
 int attn_forward(ctr_handle* h, const RowSrc& r, int B) {
@@ -250,6 +253,8 @@ int attn_backward(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
         return launch(h, "attn_bwd_vec", [&] {
             switch (h->cfg.D / 4) {
                 case 4: launch_bwd_idx<4, 1, 8>(h, r, o, B); break;    case 8: launch_bwd_idx<4, 2, 8>(h, r, o, B); break;
+                // D = 64: 8 lanes x 2 float4 (128-byte contiguous red.add / load segments per row) measured faster than
+                // 4 x 4 (64-byte segments, 0.39 vs 0.34 ms) although the latter executes a third fewer instructions
                 case 16: launch_bwd_idx<8, 2, 8>(h, r, o, B); break;
                 default: launch_bwd_idx<16, 2, 8>(h, r, o, B); break;
             }
@@ -365,12 +370,12 @@ int umma_split_weights(ctr_handle* h) {
     auto& u = h->um;
     if (!u.dirty) return CTR_OK;
     const ctr_config& c = h->cfg;
-    RET(launch(h, "split_weights_tf32", [&] {
-        umma::k_split_weights<<<64, 256, 0, h->stream>>>(h->W[0], h->H0p, h->in, c.H0, 1, u.Wt0[0], u.Wt0[1], h->Kp);          // W0ᵀ [H0, in]
-        umma::k_split_weights<<<32, 256, 0, h->stream>>>(h->W[1], h->H1p, c.H0, c.H1, 1, u.Wt1[0], u.Wt1[1], h->H0p);        // W1ᵀ [H1, H0]
-        umma::k_split_weights<<<32, 256, 0, h->stream>>>(h->W[1], h->H1p, c.H0, c.H1, 0, u.W1s[0], u.W1s[1], h->H1p);        // W1  [H0, H1]
-        umma::k_split_weights<<<64, 256, 0, h->stream>>>(h->W[0] + (long)c.uP * h->H0p, h->H0p, 2 * c.D, c.H0, 0, u.W0s[0], u.W0s[1], h->H0p);   // W0[uP:uP+2D, :]
-    }));
+    umma::SplitJobs jobs;
+    jobs.j[0] = {h->W[0], h->H0p, h->in, c.H0, 1, u.Wt0[0], u.Wt0[1], h->Kp};                                      // W0ᵀ [H0, in]
+    jobs.j[1] = {h->W[1], h->H1p, c.H0, c.H1, 1, u.Wt1[0], u.Wt1[1], h->H0p};                                     // W1ᵀ [H1, H0]
+    jobs.j[2] = {h->W[1], h->H1p, c.H0, c.H1, 0, u.W1s[0], u.W1s[1], h->H1p};                                     // W1  [H0, H1]
+    jobs.j[3] = {h->W[0] + (long)c.uP * h->H0p, h->H0p, 2 * c.D, c.H0, 0, u.W0s[0], u.W0s[1], h->H0p};            // W0[uP:uP+2D, :]
+    RET(launch(h, "split_weights_tf32", [&] { umma::k_split_weights<<<dim3(48, 4), 256, 0, h->stream>>>(jobs); }));
     u.dirty = false;
     return CTR_OK;
 }

@@ -330,17 +330,20 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 // W (logical [rows, cols], stride ld) → hi / lo TF32 split, optionally transposed, into padded
-// K-major operand buffers [orows_pad, ocols_pad] (stride old); padding stays zero.
+// K-major operand buffers [orows_pad, ocols_pad] (stride old); padding stays zero.  All operand copies of a
+// step are produced by ONE launch (blockIdx.y = job): the work is tiny, launch gaps would dominate.
+struct SplitJob { const float* W; long ld; int rows, cols, transpose; float* hi; float* lo; long old; };
+struct SplitJobs { SplitJob j[4]; };
 __global__ void __launch_bounds__(256)
-k_split_weights(const float* __restrict__ W, long ld, int rows, int cols, int transpose,
-                float* __restrict__ hi, float* __restrict__ lo, long old) {
-    const long n = (long)rows * cols;
+k_split_weights(SplitJobs jobs) {
+    const SplitJob& jb = jobs.j[blockIdx.y];
+    const long n = (long)jb.rows * jb.cols;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / cols), c = (int)(i % cols);
-        const float x = W[(long)r * ld + c];
+        const int r = (int)(i / jb.cols), c = (int)(i % jb.cols);
+        const float x = jb.W[(long)r * jb.ld + c];
         const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-        const long o = transpose ? (long)c * old + r : (long)r * old + c;
-        hi[o] = h; lo[o] = x - h;
+        const long o = jb.transpose ? (long)c * jb.old + r : (long)r * jb.old + c;
+        jb.hi[o] = h; jb.lo[o] = x - h;
     }
 }
 
