@@ -49,18 +49,22 @@ def load_peaks():
 
 
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi polled every 10 ms from before the warm-up; stop() keeps the samples whose timestamp falls inside
+    [t0, t1] = the timed region plus a short untimed tail of the same load (the timed region alone is often shorter
+    than nvidia-smi's start-up + polling latency)."""
+    Q = "timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "10"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
@@ -70,21 +74,27 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush(); self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 8:
+            if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[2]), float(c[3]), c[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+        os.unlink(self.f.name)
+        inside = [r for r in rows if t0 is None or (t0 - 0.005 <= r[0] <= t1 + 0.005)]
+        sm, mx, reasons = [], [], set()
+        for ts, a, m, flags in inside:
+            sm.append(a); mx.append(m)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.f.name)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       window="timed region + untimed tail of the same steps, %.2f s" % (t1 - t0) if t0 is not None else "whole run")
         return out
 
 
@@ -305,6 +315,7 @@ def main():
                 if e: e[0].record(st)
                 eng.train_step_idx_dev(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B)
                 if e: e[1].record(st)
+        sampler = ClockSampler(local) if not profile else None      # polls from before the warm-up
         for i in range(warmup):
             one(i)
         eng.sync(); torch.cuda.synchronize()
@@ -314,8 +325,7 @@ def main():
         l1 = eng.launch_count()
         if profile:
             eng.profile_reset(); eng.profile(True)
-        sampler = ClockSampler(local) if not profile else None
-        t0 = time.perf_counter()
+        t0 = time.perf_counter(); c0 = time.time()
         for i in range(steps):
             one(warmup + i, ev[i])
         eng.sync(); torch.cuda.synchronize()
@@ -323,7 +333,17 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        clocks = sampler.stop() if sampler else None
+        l2 = eng.launch_count()
+        clocks = None
+        if sampler:      # untimed tail: the same steps keep the load up until nvidia-smi has had >= 0.3 s to sample it
+            k = 0
+            # multi-rank steps contain collectives: every rank must run the same number of tail steps
+            while (k < 300) if world > 1 else (time.time() - c0 < 0.3 and k < 400):
+                one(k); k += 1
+                if k % 8 == 0:
+                    eng.sync()
+            eng.sync(); torch.cuda.synchronize()
+            clocks = sampler.stop(c0, time.time())
         if profile:
             eng.profile(False)
         ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -331,7 +351,7 @@ def main():
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        launches = (eng.launch_count() - l1)
+        launches = (l2 - l1)        # kernels launched inside the timed region only
         cost = eng.last_cost()
         return dict(ms=ms, wall=wall, clocks=clocks, launches=launches, host=host, cost=cost, prof=eng.profile_dump() if profile else None)
 
@@ -422,11 +442,13 @@ def main():
                        "uP": w["uP"], "cF": w["cF"], "per_gpu_batch": B, "global_batch": B * world, "table_opt": args.table_opt,
                        "gemm": args.gemm, "ids": "zipf(1.05)" if w["zipf"] else "uniform", "history_padding": "20% of samples have a -1 padded tail",
                        "l2": "256 MiB buffer written before every timed step (outside the event pair); per-step event pairs are summed",
-                       "parallelism": "1 process per GPU; ITEM_EMB rows sharded row%%world" if world > 1 else "single GPU"},
+                       "parallelism": ("single GPU" if world == 1 else
+                                       "1 process per GPU; ITEM_EMB (%.0f MB) replicated, row + dense gradients all-reduced (NCCL)" % (w["I"] * w["D"] * 4 / 1e6)
+                                       if w["I"] * w["D"] * 4 <= 32 * 2**20 else "1 process per GPU; ITEM_EMB rows sharded row%world, de-duplicated all-to-all exchange (NCCL)")},
             "clocks": leg["clocks"], "e2e": {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
             "e2e_ms_per_step": e2e["ms_per_step"], "gpu_launches": int(leg["launches"]), "last_cost": leg["cost"],
             "wall_s_timed_region": leg["wall"], "roofline": rl, "kernels": kern}
-    if rl is not None and w["I"] * w["D"] * 4 / world < 126e6:
+    if rl is not None and w["I"] * w["D"] * 4 / (1 if w["I"] * w["D"] * 4 <= 32 * 2**20 else world) < 126e6:
         rl["note"] = "table is L2-resident in the timed workload (DRAM traffic << algorithmic bytes): not an HBM reading"
     if rank == 0 and world == 1 and not args.no_hbm_leg and wname != "din_100m_shard":
         # HBM-fair reading of the same kernels: a table far larger than L2

@@ -721,6 +721,20 @@ k_hot_apply(float* __restrict__ emb, long lde, float* __restrict__ hot_acc, int 
     }
 }
 
+// replicated-table step: table += grad (already -lr/world scaled and summed over ranks); grad = 0
+__global__ void __launch_bounds__(256)
+k_apply_table_grad(float* __restrict__ tab, float* __restrict__ grad, long n4) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 g = reinterpret_cast<float4*>(grad)[i];
+        if (g.x != 0.0f || g.y != 0.0f || g.z != 0.0f || g.w != 0.0f) {
+            float4 t = reinterpret_cast<float4*>(tab)[i];
+            t.x += g.x; t.y += g.y; t.z += g.z; t.w += g.w;
+            reinterpret_cast<float4*>(tab)[i] = t;
+            reinterpret_cast<float4*>(grad)[i] = zero4();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_attn_bwd_gen(RowSrc r, Dims d, int model, const float* __restrict__ att,
                const float* __restrict__ dX, long lddx, BwdOut o, int B) {

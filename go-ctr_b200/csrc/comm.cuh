@@ -39,11 +39,17 @@ struct Comm {
     void* scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
     float* rep_acc = nullptr;     // [reps, cap_U, D] replica accumulators of the per-row gradients
     int reps = 0; size_t cap_U = 0;
+    // small ITEM_EMB tables (<= kReplicateBytes) are not sharded at all: every rank keeps the whole table, the
+    // batch's row gradients are summed into table_grad [rows, ld], all-reduced together with the dense
+    // gradients and applied identically everywhere — no per-step exchange plan, no host sync
+    bool replicate = false;
+    float* table_grad = nullptr; size_t table_grad_n = 0;
 };
+constexpr size_t kReplicateBytes = (size_t)32 << 20;
 
 }  // namespace ctr
 
-static int comm_allreduce_grads(ctr_handle* h);
+static int comm_allreduce_grads(ctr_handle* h, float* extra, size_t extra_n);
 static int comm_train_step(ctr_handle* h, const int32_t* d_user, const int32_t* d_item, const int32_t* d_hist, const float* d_label, int32_t B);
 static int comm_predict(ctr_handle* h, const int32_t* d_user, const int32_t* d_item, const int32_t* d_hist, int32_t B, float* d_out);
 static int comm_unique_id(void* id_out, int32_t* id_bytes);

@@ -249,9 +249,11 @@ int comm_check(ctr_handle* h) {
 }  // namespace
 
 // dense gradients + the batch cost: sum over ranks (every rank then takes the identical Adam step)
-static int comm_allreduce_grads(ctr_handle* h) {
+static int comm_allreduce_grads(ctr_handle* h, float* extra, size_t extra_n) {
     Comm& cm = h->comm;
+    if (!cm.ready) return set_err(h, CTR_ESTATE, "world=%d but ctr_comm_init was not called", cm.world);
     NC(h, g_nccl.GroupStart());
+    if (extra && extra_n) NC(h, g_nccl.AllReduce(extra, extra, extra_n, kNcclFloat32, kNcclSum, cm.nccl, h->stream));
     const int nt = h->cfg.model == CTR_MODEL_YOUTUBE ? 3 : 4;
     for (int i = 0; i < nt; i++) NC(h, g_nccl.AllReduce(h->G[i], h->G[i], h->wsize[i], kNcclFloat32, kNcclSum, cm.nccl, h->stream));
     NC(h, g_nccl.AllReduce(h->d_cost, h->d_cost, 1, kNcclFloat64, kNcclSum, cm.nccl, h->stream));
@@ -327,7 +329,7 @@ static void comm_destroy(ctr_handle* h) {
     Comm& cm = h->comm;
     for (void* p : {(void*)cm.flags, (void*)cm.pos, cm.scan_tmp, (void*)cm.rep_acc}) if (p) cudaFree(p);
     for (void* p : {(void*)cm.d_cnt, (void*)cm.d_cursor, (void*)cm.d_rcnt, (void*)cm.send_rows, (void*)cm.slot_hist, (void*)cm.slot_item,
-                    (void*)cm.recv_rows, (void*)cm.rows_out, (void*)cm.rows_local, (void*)cm.grad_local}) if (p) cudaFree(p);
+                    (void*)cm.recv_rows, (void*)cm.rows_out, (void*)cm.rows_local, (void*)cm.grad_local, (void*)cm.table_grad}) if (p) cudaFree(p);
     if (cm.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(cm.nccl);
     cm.nccl = nullptr; cm.ready = false;
 }

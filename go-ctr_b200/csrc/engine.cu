@@ -432,6 +432,9 @@ struct StepOpts {
     // global mean and the dense gradients are all-reduced before Adam
     bool comm = false; float* scatter_base = nullptr; float grad_scale = 1.0f; int adam_batch = 0;
     float* rep_acc = nullptr; int rep_rows = 0, rep_n = 0;      // replica accumulators over the batch's distinct rows
+    // replicated-table step: row gradients are summed into table_grad (layout of the table), all-reduced with the
+    // dense gradients and applied on every rank
+    float* table_grad = nullptr; size_t table_grad_n = 0;
 };
 
 int ensure_rowgrad_buffers(ctr_handle* h, int B) {
@@ -569,11 +572,12 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
             g.C = h->dX; g.ldc = h->lddx; g.M = B; g.N = 2 * c.D; g.K = c.H0; g.Nz = h->lddx;
             RET((gemm_big<false, true, EPI_STORE>(h, "sgemm_dX", g)));
         }
-        const bool buffers = o.want_rows || (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC && !o.comm);
+        const bool fused_only = o.comm || o.table_grad;        // multi-GPU steps always scatter with red.add
+        const bool buffers = o.want_rows || (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC && !fused_only);
         if (buffers) RET(ensure_rowgrad_buffers(h, B));
         BwdOut bo{}; bo.datt = h->G[3]; bo.dUb = buffers ? h->dUb : nullptr; bo.dIt = buffers ? h->dIt : nullptr;
-        bo.sgd = (learn_rows && (c.table_opt == CTR_TABLE_SGD || o.comm)) ? 1 : 0; bo.neg_lr = -c.table_lr * o.grad_scale;
-        bo.scatter_base = o.scatter_base ? o.scatter_base : h->tab[CTR_TABLE_ITEM_EMB];
+        bo.sgd = (learn_rows && (c.table_opt == CTR_TABLE_SGD || fused_only)) ? 1 : 0; bo.neg_lr = -c.table_lr * o.grad_scale;
+        bo.scatter_base = o.scatter_base ? o.scatter_base : o.table_grad ? o.table_grad : h->tab[CTR_TABLE_ITEM_EMB];
         const bool hot = bo.sgd && vec_ok(h, r) && !o.comm;
         if (hot) { RET(ensure_hot(h)); bo.hot_acc = h->hot_acc; bo.hot_rows = h->hot_rows; bo.hot_reps = h->hot_reps; }
         if (o.comm && o.rep_acc && bo.sgd) { bo.hot_acc = o.rep_acc; bo.hot_rows = o.rep_rows; bo.hot_reps = o.rep_n; }
@@ -584,13 +588,18 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
             }));
         if (hot && h->hot_rows > 0)
             RET(launch(h, "hot_rows_apply", [&] {
-                k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(h->tab[CTR_TABLE_ITEM_EMB], h->tab_ld[CTR_TABLE_ITEM_EMB], h->hot_acc,
+                k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(bo.scatter_base, h->tab_ld[CTR_TABLE_ITEM_EMB], h->hot_acc,
                                                                 h->hot_rows, h->hot_reps, c.D, 1.0f);
             }));
-        if (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC && !o.comm) RET(deterministic_table_update(h, r, B));
+        if (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC && !fused_only) RET(deterministic_table_update(h, r, B));
     }
     if (o.update) {
-        if (o.comm) RET(comm_allreduce_grads(h));
+        const bool tg = o.table_grad && c.table_opt != CTR_TABLE_FROZEN;
+        if (o.comm || o.table_grad) RET(comm_allreduce_grads(h, tg ? o.table_grad : nullptr, tg ? o.table_grad_n : 0));
+        if (tg)
+            RET(launch(h, "apply_table_grad", [&] {
+                k_apply_table_grad<<<h->num_sms * 8, 256, 0, h->stream>>>(h->tab[CTR_TABLE_ITEM_EMB], o.table_grad, (long)(o.table_grad_n / 4));
+            }));
         AdamArgs a{};
         const int in = h->in;
         a.t[0] = AdamTensor{h->W[0], h->G[0], h->Mo[0], h->Vo[0], in, c.H0, h->H0p};
@@ -616,6 +625,16 @@ int zero_grads(ctr_handle* h) {
     return CTR_OK;
 }
 
+// ITEM_EMB placement under world > 1: sharded by row % world, or (small tables) replicated on every rank.
+// cfg.reserved[1]: 0 = by size, 1 = always shard, 2 = always replicate.
+bool emb_replicated(const ctr_handle* h, int64_t nrows, int32_t width) {
+    if (h->comm.world <= 1) return false;
+    const int pol = h->cfg.reserved[1];
+    if (pol == 1) return false;
+    if (pol == 2) return true;
+    return (size_t)nrows * round_up(width, 4) * sizeof(float) <= kReplicateBytes;
+}
+
 RowSrc idx_src(const ctr_handle* h, const int* d_user, const int* d_item, const int* d_hist, int B) {
     RowSrc r{};
     r.emb = h->tab[CTR_TABLE_ITEM_EMB]; r.lde = h->tab_ld[CTR_TABLE_ITEM_EMB];
@@ -634,7 +653,7 @@ int check_tables(const ctr_handle* h) {
         return set_err(h, CTR_ESTATE, "USER_FEAT table not uploaded with width uP=%d", c.uP);
     if (c.cF > 0 && (!h->tab[CTR_TABLE_ITEM_FEAT] || h->tab_width[CTR_TABLE_ITEM_FEAT] != c.cF))
         return set_err(h, CTR_ESTATE, "ITEM_FEAT table not uploaded with width cF=%d", c.cF);
-    if (h->comm.world > 1) return set_err(h, CTR_ESTATE, "sharded tables: use the comm step path");
+    if (h->comm.world > 1 && !h->comm.replicate) return set_err(h, CTR_ESTATE, "sharded tables: use the comm step path");
     return CTR_OK;
 }
 
@@ -879,7 +898,8 @@ int ctr_table_upload(ctr_handle* h, int which, const float* rows, int64_t nrows,
     CU(h, cudaSetDevice(h->dev));
     if (h->tab[which]) { cudaFree(h->tab[which]); h->tab[which] = nullptr; }
     const long ld = round_up(width, 4);                       // 16-byte aligned rows for 128-bit loads
-    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1;
+    if (which == CTR_TABLE_ITEM_EMB) h->comm.replicate = emb_replicated(h, nrows, width);
+    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1 && !h->comm.replicate;
     const int64_t local = shard ? (nrows - h->comm.rank + h->comm.world - 1) / h->comm.world : nrows;
     CU(h, cudaMalloc(&h->tab[which], (size_t)std::max<int64_t>(local, 1) * ld * sizeof(float)));
     CU(h, cudaMemsetAsync(h->tab[which], 0, (size_t)std::max<int64_t>(local, 1) * ld * sizeof(float), h->stream));
@@ -904,7 +924,8 @@ int ctr_table_fill(ctr_handle* h, int which, int64_t nrows, int32_t width, uint3
     CU(h, cudaSetDevice(h->dev));
     if (h->tab[which]) { cudaFree(h->tab[which]); h->tab[which] = nullptr; }
     const long ld = round_up(width, 4);
-    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1;
+    if (which == CTR_TABLE_ITEM_EMB) h->comm.replicate = emb_replicated(h, nrows, width);
+    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1 && !h->comm.replicate;
     const int64_t local = shard ? (nrows - h->comm.rank + h->comm.world - 1) / h->comm.world : nrows;
     const size_t bytes = (size_t)std::max<int64_t>(local, 1) * ld * sizeof(float);
     CU(h, cudaMalloc(&h->tab[which], bytes));
@@ -924,7 +945,7 @@ int ctr_table_download(ctr_handle* h, int which, float* rows, int64_t nrows, int
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->tab[which] || nrows != h->tab_rows[which] || width != h->tab_width[which]) return set_err(h, CTR_EINVAL, "table %d shape mismatch", which);
     CU(h, cudaSetDevice(h->dev));
-    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1;
+    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1 && !h->comm.replicate;
     if (!shard) {
         CU(h, cudaMemcpy2DAsync(rows, (size_t)width * sizeof(float), h->tab[which], h->tab_ld[which] * sizeof(float), (size_t)width * sizeof(float), (size_t)nrows, cudaMemcpyDeviceToHost, h->stream));
     } else if (h->tab_local_rows[which] > 0) {   // fills only this rank's rows (row % world == rank)
@@ -1011,13 +1032,34 @@ int ctr_predict_dense(ctr_handle* h, const float* X, int64_t n, int32_t xcols, c
     return CTR_OK;
 }
 
+namespace {
+// options of one local-gather train step; with world > 1 (replicated ITEM_EMB) the row gradients go through
+// comm.table_grad and everything is all-reduced before the update
+int train_opts(ctr_handle* h, const float* d_label, int B, StepOpts* out) {
+    StepOpts o; o.training = true; o.update = true; o.d_label = d_label;
+    if (h->comm.world > 1) {
+        Comm& cm = h->comm;
+        const size_t n = (size_t)h->tab_rows[CTR_TABLE_ITEM_EMB] * h->tab_ld[CTR_TABLE_ITEM_EMB];
+        if (cm.table_grad_n != n) {
+            if (cm.table_grad) cudaFree(cm.table_grad);
+            cm.table_grad = nullptr; cm.table_grad_n = 0;
+            RET(dalloc(h, &cm.table_grad, n)); cm.table_grad_n = n;
+        }
+        o.table_grad = cm.table_grad; o.table_grad_n = n; o.grad_scale = 1.0f / (float)cm.world; o.adam_batch = B * cm.world;
+    }
+    *out = o;
+    return CTR_OK;
+}
+}  // namespace
+
 int ctr_train_step_idx_dev(ctr_handle* h, const int32_t* d_user, const int32_t* d_item, const int32_t* d_hist, const float* d_label, int32_t B) {
     if (!h || !d_user || !d_item || !d_hist || !d_label) return set_err(h, CTR_EINVAL, "null argument");
     if (B != h->cfg.batch) return set_err(h, CTR_EINVAL, "B=%d != configured batch %d", B, h->cfg.batch);
-    if (h->comm.world > 1) return comm_train_step(h, d_user, d_item, d_hist, d_label, B);
+    if (h->comm.world > 1 && !h->comm.replicate) return comm_train_step(h, d_user, d_item, d_hist, d_label, B);
     RET(check_tables(h));
     RowSrc r = idx_src(h, d_user, d_item, d_hist, B);
-    StepOpts o; o.training = true; o.update = true; o.d_label = d_label;
+    StepOpts o;
+    RET(train_opts(h, d_label, B, &o));
     return step_core(h, r, B, o);
 }
 
@@ -1040,7 +1082,7 @@ int ctr_train_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_ro
     if (!h || !user_row || !item_row || !hist || !label || n < 1) return set_err(h, CTR_EINVAL, "bad train arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     CU(h, cudaSetDevice(h->dev));
-    if (h->comm.world > 1) return set_err(h, CTR_ESTATE, "ctr_train_idx: sharded tables use ctr_train_step_idx per batch");
+    if (h->comm.world > 1 && !h->comm.replicate) return set_err(h, CTR_ESTATE, "ctr_train_idx: sharded tables use ctr_train_step_idx per batch");
     RET(check_tables(h));
     const int B = h->cfg.batch, S = h->cfg.S;
     const int64_t nb = (n + B - 1) / B;                      // model.go:96-99
@@ -1067,7 +1109,8 @@ int ctr_train_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_ro
         CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
         RowSrc r = idx_src(h, su[slot], si[slot], sh[slot], B);
         r.nvalid = nv;                                       // ragged tail → zero rows with label 0 (model.go:357-371)
-        StepOpts o; o.training = true; o.update = true; o.d_label = sl[slot];
+        StepOpts o;
+        RET(train_opts(h, sl[slot], B, &o));
         RET(step_core(h, r, B, o));
         CU(h, cudaMemcpyAsync(h->d_costs + b, h->d_cost, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         CU(h, cudaEventRecord(h->ev_consumed[slot], h->stream));
@@ -1076,13 +1119,13 @@ int ctr_train_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_ro
     CU(h, cudaMemcpyAsync(hc.data(), h->d_costs, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaStreamSynchronize(h->copy_stream));
-    if (costs) for (int64_t b = 0; b < nb; b++) costs[b] = -(float)(hc[(size_t)b] / (double)B);
+    if (costs) for (int64_t b = 0; b < nb; b++) costs[b] = -(float)(hc[(size_t)b] / ((double)B * h->comm.world));   // d_cost is summed over the ranks
     return CTR_OK;
 }
 
 int ctr_predict_idx_dev(ctr_handle* h, const int32_t* d_user, const int32_t* d_item, const int32_t* d_hist, int32_t B, float* d_out) {
     if (!h || !d_user || !d_item || !d_hist) return set_err(h, CTR_EINVAL, "null argument");
-    if (h->comm.world > 1) return comm_predict(h, d_user, d_item, d_hist, B, d_out);
+    if (h->comm.world > 1 && !h->comm.replicate) return comm_predict(h, d_user, d_item, d_hist, B, d_out);
     RET(check_tables(h));
     RowSrc r = idx_src(h, d_user, d_item, d_hist, B);
     StepOpts o;

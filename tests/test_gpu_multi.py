@@ -1,4 +1,5 @@
-"""Two-rank NCCL test of the sharded-table path (needs >= 2 GPUs: `gpurun --gpus 2`): a step on 2 GPUs with
+"""Two-rank NCCL test of both ITEM_EMB placements (row-sharded with the all-to-all exchange; replicated with
+gradient all-reduce)  (needs >= 2 GPUs: `gpurun --gpus 2`): a step on 2 GPUs with
 per-GPU batch B == a step on 1 GPU with batch 2B (same samples), for scores, cost, dense weights and the
 updated embedding table."""
 import os
@@ -28,7 +29,7 @@ def _data():
     return uf, itf, emb, batches
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, policy):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -36,6 +37,7 @@ def _worker(rank, world, port, out_dir):
     uf, itf, emb, batches = _data()
     cfg = g.engine.default_config(g.MODEL_DIN_COS, batch=B, pred_batch=B, table_opt=g.TABLE_SGD, table_lr=0.7, dropout0=0.0, dropout1=0.0,
                                   seed=3, device=rank, rank=rank, world=world, **DIMS)
+    cfg.reserved[1] = policy                  # 1 = shard rows, 2 = replicate the table (auto would replicate: 13 KB)
     eng = g.Engine(cfg)
     ids = [eng.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
@@ -56,12 +58,13 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_step_equals_single_gpu_global_batch(tmp_path):
+@pytest.mark.parametrize("policy", [1, 2], ids=["sharded", "replicated"])
+def test_two_gpu_step_equals_single_gpu_global_batch(tmp_path, policy):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), policy), nprocs=world, join=True)
     uf, itf, emb, batches = _data()
     cfg = g.engine.default_config(g.MODEL_DIN_COS, batch=2 * B, pred_batch=2 * B, table_opt=g.TABLE_SGD_DETERMINISTIC, table_lr=0.7,
                                   dropout0=0.0, dropout1=0.0, seed=3, **DIMS)
@@ -78,6 +81,9 @@ def test_two_gpu_sharded_step_equals_single_gpu_global_batch(tmp_path):
     got_emb = np.zeros_like(emb)
     for r in range(world):
         got_emb[r::world] = np.load(tmp_path / ("emb%d.npy" % r))[r::world]
+    if policy == 2:      # every rank holds the whole, identical table
+        assert np.load(tmp_path / "emb0.npy").tobytes() == np.load(tmp_path / "emb1.npy").tobytes()
+        got_emb = np.load(tmp_path / "emb0.npy")
     want_emb = ref.table_download(g.TABLE_ITEM_EMB, I, DIMS["D"])
     assert np.abs(want_emb - emb).max() > 1e-5
     np.testing.assert_allclose(got_emb, want_emb, rtol=2e-3, atol=2e-5)
