@@ -271,12 +271,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hbm_peak, peak_src = load_peaks()
 
-    def build_engine(w, B):
+    def build_engine(w, B, placement=0):
         model = g.MODEL_DIN_COS if w["model"] == "din" else g.MODEL_YOUTUBE
         topt = {"sgd": g.TABLE_SGD, "det": g.TABLE_SGD_DETERMINISTIC, "frozen": g.TABLE_FROZEN}[args.table_opt]
         gm = {"auto": g.GEMM_AUTO, "fp32": g.GEMM_FP32, "tcgen05": g.GEMM_TCGEN05_3XTF32}[args.gemm]
         cfg = g.engine.default_config(model, uP=w["uP"], S=w["S"], D=w["D"], cF=w["cF"], batch=B, pred_batch=B,
                                       table_opt=topt, table_lr=0.05, gemm=gm, device=local, rank=rank, world=world, seed=1)
+        cfg.reserved[1] = placement          # ITEM_EMB under world > 1: 0 = by size, 1 = row-sharded, 2 = replicated
         eng = g.Engine(cfg)
         if world > 1:
             ids = [None]
@@ -300,7 +301,7 @@ def main():
     dev = torch.device("cuda", local)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    def timed_leg(eng, w, B, steps, warmup, profile=False):
+    def timed_leg(eng, w, B, steps, warmup, profile=False, clocks=True):
         """K timed steps, inputs resident in HBM, L2 flushed before every step (outside the events)."""
         host = make_batches(w, B, 4, 100)
         devb = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in host]
@@ -315,7 +316,7 @@ def main():
                 if e: e[0].record(st)
                 eng.train_step_idx_dev(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B)
                 if e: e[1].record(st)
-        sampler = ClockSampler(local) if not profile else None      # polls from before the warm-up
+        sampler = ClockSampler(local) if (clocks and not profile) else None      # polls from before the warm-up
         for i in range(warmup):
             one(i)
         eng.sync(); torch.cuda.synchronize()
@@ -362,7 +363,7 @@ def main():
         back D2H before the call returns.  Single-GPU; with sharded tables (world > 1) the per-batch entry
         point ctr_train_step_idx is timed instead."""
         host = make_batches(w, B, 4, 200)
-        if world > 1:
+        if world > 1 and w["I"] * w["D"] * 4 > 32 * 2**20:     # row-sharded tables: per-batch entry point
             pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
             st = g.StepStats()
             for i in range(warmup):
@@ -384,9 +385,15 @@ def main():
             costs = torch.empty(steps, dtype=torch.float32).pin_memory()
             eng.train_idx_ptr(cat[0].data_ptr(), cat[1].data_ptr(), cat[2].data_ptr(), cat[3].data_ptr(), B * min(steps, max(warmup, 2)), costs.data_ptr())
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
             eng.train_idx_ptr(cat[0].data_ptr(), cat[1].data_ptr(), cat[2].data_ptr(), cat[3].data_ptr(), B * steps, costs.data_ptr())
             dt = time.perf_counter() - t0
+            if world > 1:       # slowest rank
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
             last = float(costs[-1])
             h2d = sum(a.numel() * a.element_size() for a in cat) // steps
         return dict(value=B * world * steps / dt, unit="samples/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=8,
@@ -450,6 +457,18 @@ def main():
             "wall_s_timed_region": leg["wall"], "roofline": rl, "kernels": kern}
     if rl is not None and w["I"] * w["D"] * 4 / (1 if w["I"] * w["D"] * 4 <= 32 * 2**20 else world) < 126e6:
         rl["note"] = "table is L2-resident in the timed workload (DRAM traffic << algorithmic bytes): not an HBM reading"
+    if world > 1 and w["I"] * w["D"] * 4 <= 32 * 2**20 and not args.no_hbm_leg:
+        # the timed workload's table is small enough to be replicated; the same steps with the table forced onto
+        # the row-sharded NCCL all-to-all path (BASELINE north_star's placement for large tables) — all ranks, collective
+        del eng
+        torch.cuda.empty_cache()
+        eng_s = build_engine(w, B, placement=1)
+        ks = max(5, args.steps // 4)
+        leg_s = timed_leg(eng_s, w, B, ks, 3, clocks=False)
+        if rank == 0:
+            line["sharded_exchange"] = {"what": "same workload, ITEM_EMB forced row-sharded (row % world) with the de-duplicated all-to-all exchange",
+                                        "value": B * world * ks / (leg_s["ms"] * 1e-3), "unit": "samples/s", "ms_per_step": leg_s["ms"] / ks}
+        del eng_s
     if rank == 0 and world == 1 and not args.no_hbm_leg and wname != "din_100m_shard":
         # HBM-fair reading of the same kernels: a table far larger than L2
         del eng

@@ -124,6 +124,57 @@ func (e *Engine) PredictIdx(userRow, itemRow, histRows []int32) ([]float32, erro
 	return y, e.err(rc)
 }
 
+// TrainIdx is one model.Train pass (one epoch) over n samples given as row ids in host memory: batches are
+// copied H2D on a second stream while the previous batch computes; costs receives one BCE per batch.
+func (e *Engine) TrainIdx(userRow, itemRow, histRows []int32, label []float32, costs []float32) error {
+	var cp *C.float
+	if len(costs) > 0 {
+		cp = f32(costs)
+	}
+	return e.err(C.ctr_train_idx(e.h, i32(userRow), i32(itemRow), i32(histRows), f32(label), C.int64_t(len(userRow)), cp))
+}
+
+func i64(p []int64) *C.int64_t { return (*C.int64_t)(unsafe.Pointer(&p[0])) }
+
+// LoadIDMaps replaces the strconv.Itoa-keyed caches (rcmd.go:472,484,502): userIds[r] / itemIds[r] is the
+// external id of table row r.
+func (e *Engine) LoadIDMaps(userIds, itemIds []int64) error {
+	if err := e.err(C.ctr_idmap_build(e.h, C.CTR_IDMAP_USER, i64(userIds), C.int64_t(len(userIds)))); err != nil {
+		return err
+	}
+	return e.err(C.ctr_idmap_build(e.h, C.CTR_IDMAP_ITEM, i64(itemIds), C.int64_t(len(itemIds))))
+}
+
+// UploadUserBehavior puts every user's (time-descending) behaviour sequence in HBM (feature/ubcache,
+// prepare.go:13-38): offsets [nUsers+1], ts and itemRows [n].
+func (e *Engine) UploadUserBehavior(offsets, ts []int64, itemRows []int32) error {
+	return e.err(C.ctr_ubcache_upload(e.h, i64(offsets), i64(ts), i32(itemRows), C.int64_t(len(offsets)-1), C.int64_t(len(ts))))
+}
+
+// BatchPredict is recommend.BatchPredict (rcmd.go:282-337) over sample keys, entirely on the device.
+func (e *Engine) BatchPredict(sampleKeys []rcmd.Sample) ([]float32, error) {
+	n := len(sampleKeys)
+	u, it, ts := make([]int64, n), make([]int64, n), make([]int64, n)
+	for i, k := range sampleKeys {
+		u[i], it[i], ts[i] = int64(k.UserId), int64(k.ItemId), k.Timestamp
+	}
+	y := make([]float32, n)
+	rc := C.ctr_batch_predict_keys(e.h, i64(u), i64(it), i64(ts), C.int64_t(n), f32(y))
+	return y, e.err(rc)
+}
+
+// SaveCheckpoint / LoadCheckpoint: binary snapshot of weights, Adam moments, step counter and tables.
+func (e *Engine) SaveCheckpoint(path string) error {
+	cs := C.CString(path)
+	defer C.free(unsafe.Pointer(cs))
+	return e.err(C.ctr_checkpoint_save(e.h, cs))
+}
+func (e *Engine) LoadCheckpoint(path string) error {
+	cs := C.CString(path)
+	defer C.free(unsafe.Pointer(cs))
+	return e.err(C.ctr_checkpoint_load(e.h, cs))
+}
+
 // dinModel is the reference's JSON schema (din.go:41-52; dnn.go:38-47 without att0).
 type dinModel struct {
 	UProfileDim   int       `json:"uProfileDim"`
