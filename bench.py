@@ -437,7 +437,7 @@ def main():
     leg = timed_leg(eng, w, B, args.steps, args.warmup)
     prof_leg = timed_leg(eng, w, B, args.steps, 1, profile=True)
     rl, kern = roofline_of(w, prof_leg, prof_leg["prof"], B)
-    e2e = e2e_leg(eng, w, B, max(3, min(args.steps, 40)), 2)
+    e2e = e2e_leg(eng, w, B, max(3, min(args.steps, 64)), 2)
     value = B * world * args.steps / (leg["ms"] * 1e-3)
     step_ms = sum(v["ms_per_launch"] * v["launches_per_step"] for v in kern.values())
     for v in kern.values():

@@ -1572,11 +1572,14 @@ int ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, i
             I2vArgs a{}; a.doc = d_doc; a.nd = nd; a.z = d_z; a.poff = d_poff; a.pnode = d_pnode; a.pcode = d_pcode; a.syn0 = d_syn0; a.syn1 = d_syn1;
             a.D = D; a.W = W; a.lr_tab = d_lr; a.upd = c.update_lr_batch; a.seed = c.seed; a.iter = it; a.counters = d_cnt;
             a.node_scale = d_nsc; a.word_scale = d_wsc;
+            static const bool no_hot = getenv("CTR_I2V_NO_HOT") != nullptr;
+            a.hot_n = no_hot ? 0 : std::min(kI2vHot, V - 1); a.hot_base = V - 1 - a.hot_n;
+            const size_t sm = (size_t)std::max(a.hot_n, 1) * D * sizeof(float);
             CI(cudaEventRecord(e0, st));
             switch (D / 4) {
-                case 1: k_i2v_skipgram_hs<1><<<grid, 256, 0, st>>>(a); break;   case 2: k_i2v_skipgram_hs<2><<<grid, 256, 0, st>>>(a); break;
-                case 4: k_i2v_skipgram_hs<4><<<grid, 256, 0, st>>>(a); break;   case 8: k_i2v_skipgram_hs<8><<<grid, 256, 0, st>>>(a); break;
-                case 16: k_i2v_skipgram_hs<16><<<grid, 256, 0, st>>>(a); break; default: k_i2v_skipgram_hs<32><<<grid, 256, 0, st>>>(a); break;
+                case 1: k_i2v_skipgram_hs<1><<<grid, 256, sm, st>>>(a); break;   case 2: k_i2v_skipgram_hs<2><<<grid, 256, sm, st>>>(a); break;
+                case 4: k_i2v_skipgram_hs<4><<<grid, 256, sm, st>>>(a); break;   case 8: k_i2v_skipgram_hs<8><<<grid, 256, sm, st>>>(a); break;
+                case 16: k_i2v_skipgram_hs<16><<<grid, 256, sm, st>>>(a); break; default: k_i2v_skipgram_hs<32><<<grid, 256, sm, st>>>(a); break;
             }
             launches++;
             CI(cudaGetLastError());

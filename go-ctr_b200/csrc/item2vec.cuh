@@ -35,55 +35,89 @@ struct I2vArgs {
     const float* word_scale;              // [V]   1/max(1, C*p_word)
     uint32_t seed; int iter;
     unsigned long long* counters;         // [0] trained positions, [1] (centre, context) pairs, [2] node visits
+    int hot_base, hot_n;                  // inner nodes [hot_base, hot_base + hot_n) = the top of the Huffman tree
 };
+
+// The top of the tree is on every path: the root alone would take one red.add per (pair, 16 bytes) on the same
+// 16 L2 addresses.  Huffman nodes are numbered in creation order = non-decreasing subtree count, so the last
+// kI2vHot nodes ARE the hottest ones: their updates are summed per block in shared memory (native f32 shared
+// atomics) and flushed to HBM every kI2vFlush positions per warp — one global add per block instead of one per pair.
+constexpr int kI2vHot = 64;
+constexpr int kI2vFlush = 8;
 
 template <int LPR>
 __global__ void __launch_bounds__(256)
 k_i2v_skipgram_hs(I2vArgs a) {
-    constexpr int RPW = 32 / LPR;
+    constexpr int RPW = 32 / LPR, D = 4 * LPR;
+    extern __shared__ float s_acc[];           // [hot_n, D] this block's pending updates of the hot nodes
     const int lane = threadIdx.x & 31, lir = lane % LPR, sub = lane / LPR;
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const long gwarp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long niter = (a.nd + nwarps - 1) / nwarps;
     unsigned long long n_tr = 0, n_pair = 0, n_node = 0;
-    for (long pos = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pos < a.nd; pos += nwarps) {
-        const int id = a.doc[pos];
-        // Subsampler.Trial (subsample.go:45-52): train when z[id] > U[0,1)
-        const double u = (double)(mix64(a.seed, 200u + (uint32_t)a.iter, (uint64_t)pos) >> 11) * (1.0 / 9007199254740992.0);
-        if (!(a.z[id] > u)) continue;
-        const int del = (int)(mix64(a.seed, 300u + (uint32_t)a.iter, (uint64_t)pos) % (uint64_t)a.W);   // modelutil.NextRandom(window)
-        const float lr = a.lr_tab[pos / a.upd];
-        const long long p0 = a.poff[id]; const int np = (int)(a.poff[id + 1] - p0);
-        const int nctx = 2 * (a.W - del);                                   // a in [del, 2W+1-del), a != W
-        n_tr++;
-        for (int k0 = 0; k0 < nctx; k0 += RPW) {
-            const int k = k0 + sub;
-            int aa = del + k; if (aa >= a.W) aa++;
-            const long cpos = pos - a.W + aa;
-            const bool active = k < nctx && cpos >= 0 && cpos < a.nd;       // model.go:63-66
-            const int cid = active ? a.doc[cpos] : 0;
-            float* cptr = a.syn0 + (long)cid * a.D + lir * 4;
-            const float4 c = active ? *reinterpret_cast<const float4*>(cptr) : zero4();
-            float4 tmp = zero4();
-            bool alive = active;
-            if (active && lir == 0) n_pair++;
-            for (int i = 0; i < np; i++) {                                  // optimizer.go:113-128
-                if (__ballot_sync(0xffffffffu, alive) == 0u) break;
-                const int node = a.pnode[p0 + i];
-                float* nptr = a.syn1 + (long)node * a.D + lir * 4;
-                const float4 nv = *reinterpret_cast<const float4*>(nptr);
-                const float f = group_sum<LPR>(dot4(c, nv));
-                if (alive && (f <= -6.0f || f >= 6.0f)) alive = false;      // `return`: the rest of the path is abandoned
-                if (alive) {
-                    const float g = (1.0f - (float)a.pcode[p0 + i] - c_i2v_lut[(int)((f + 6.0f) * (1000.0f / 6.0f / 2.0f))]) * lr;
-                    tmp = fma4(g, nv, tmp);
-                    const float gs = g * __ldg(a.node_scale + node);
-                    red_add4(nptr, make_float4(gs * c.x, gs * c.y, gs * c.z, gs * c.w));
-                    if (lir == 0) n_node++;
+    for (int i = threadIdx.x; i < a.hot_n * D; i += blockDim.x) s_acc[i] = 0.0f;
+    __syncthreads();
+    for (long it = 0; it < niter; it++) {
+        const long pos = it * nwarps + gwarp;
+        bool train = pos < a.nd;
+        int id = 0;
+        if (train) {
+            id = a.doc[pos];
+            // Subsampler.Trial (subsample.go:45-52): train when z[id] > U[0,1)
+            const double u = (double)(mix64(a.seed, 200u + (uint32_t)a.iter, (uint64_t)pos) >> 11) * (1.0 / 9007199254740992.0);
+            train = a.z[id] > u;
+        }
+        if (train) {
+            const int del = (int)(mix64(a.seed, 300u + (uint32_t)a.iter, (uint64_t)pos) % (uint64_t)a.W);   // modelutil.NextRandom(window)
+            const float lr = a.lr_tab[pos / a.upd];
+            const long long p0 = a.poff[id]; const int np = (int)(a.poff[id + 1] - p0);
+            const int nctx = 2 * (a.W - del);                                   // a in [del, 2W+1-del), a != W
+            n_tr++;
+            for (int k0 = 0; k0 < nctx; k0 += RPW) {
+                const int k = k0 + sub;
+                int aa = del + k; if (aa >= a.W) aa++;
+                const long cpos = pos - a.W + aa;
+                const bool active = k < nctx && cpos >= 0 && cpos < a.nd;       // model.go:63-66
+                const int cid = active ? a.doc[cpos] : 0;
+                float* cptr = a.syn0 + (long)cid * D + lir * 4;
+                const float4 c = active ? *reinterpret_cast<const float4*>(cptr) : zero4();
+                float4 tmp = zero4();
+                bool alive = active;
+                if (active && lir == 0) n_pair++;
+                for (int i = 0; i < np; i++) {                                  // optimizer.go:113-128
+                    if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+                    const int node = a.pnode[p0 + i];
+                    float* nptr = a.syn1 + (long)node * D + lir * 4;
+                    const float4 nv = *reinterpret_cast<const float4*>(nptr);
+                    const float f = group_sum<LPR>(dot4(c, nv));
+                    if (alive && (f <= -6.0f || f >= 6.0f)) alive = false;      // `return`: the rest of the path is abandoned
+                    if (alive) {
+                        const float g = (1.0f - (float)a.pcode[p0 + i] - c_i2v_lut[(int)((f + 6.0f) * (1000.0f / 6.0f / 2.0f))]) * lr;
+                        tmp = fma4(g, nv, tmp);
+                        const float gs = g * __ldg(a.node_scale + node);
+                        const int hs = node - a.hot_base;
+                        if (hs >= 0) {
+                            float* sp = s_acc + hs * D + lir * 4;
+                            atomicAdd(sp + 0, gs * c.x); atomicAdd(sp + 1, gs * c.y); atomicAdd(sp + 2, gs * c.z); atomicAdd(sp + 3, gs * c.w);
+                        } else {
+                            red_add4(nptr, make_float4(gs * c.x, gs * c.y, gs * c.z, gs * c.w));
+                        }
+                        if (lir == 0) n_node++;
+                    }
+                }
+                if (active) {                                                   // model.go:74-76
+                    const float ws = __ldg(a.word_scale + cid);
+                    red_add4(cptr, make_float4(ws * tmp.x, ws * tmp.y, ws * tmp.z, ws * tmp.w));
                 }
             }
-            if (active) {                                                   // model.go:74-76
-                const float ws = __ldg(a.word_scale + cid);
-                red_add4(cptr, make_float4(ws * tmp.x, ws * tmp.y, ws * tmp.z, ws * tmp.w));
+        }
+        if (a.hot_n > 0 && ((it % kI2vFlush) == kI2vFlush - 1 || it == niter - 1)) {       // uniform across the block
+            __syncthreads();
+            for (int i = threadIdx.x; i < a.hot_n * D; i += blockDim.x) {
+                const float v = s_acc[i];
+                if (v != 0.0f) { atomicAdd(a.syn1 + (long)a.hot_base * D + i, v); s_acc[i] = 0.0f; }
             }
+            __syncthreads();
         }
     }
     n_tr = (lane == 0) ? n_tr : 0;
