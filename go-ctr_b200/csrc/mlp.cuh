@@ -177,23 +177,47 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
     for (int j = 0; j < 4; j++) { int k = lane + 32 * j; w2r[j] = k < a.H1 ? __ldg(a.w2 + k) : 0.0f; dw2r[j] = 0.0f; }
     double cost = 0.0;
     const float invB = 1.0f / (float)a.B;
-    for (int b = blockIdx.x * (blockDim.x >> 5) + wib; b < a.B; b += nwarps) {
-        float h[4]; float z = 0.0f;
+    // R consecutive rows per warp and step: their loads are issued together and the R reductions interleave
+    // (one row at a time left a single 384-byte request in flight per warp: latency-bound at ~30 us)
+    constexpr int R = 4;
+    for (int b0 = (blockIdx.x * (blockDim.x >> 5) + wib) * R; b0 < a.B; b0 += nwarps * R) {
+        float h[R][4], z[R];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { int k = lane + 32 * j; h[j] = k < a.H1 ? __ldg(a.H1d + (long)b * a.ldh + k) : 0.0f; z = fmaf(h[j], w2r[j], z); }
-        z = warp_sum(z);
-        const float p = sigmoid32(z);
-        if (lane == 0) { a.p[b] = p; if (a.logit) a.logit[b] = z; }
-        if (!train) continue;
-        const float y = (b < a.nvalid) ? __ldg(a.y + b) : 0.0f;
-        if (lane == 0) cost += (double)(logf(p) * y + logf(1.0f - p) * (1.0f - y));
-        const float dz2 = (p - y) * invB;
+        for (int i = 0; i < R; i++) {
+            z[i] = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int k = lane + 32 * j;
-            if (k < a.H1) a.dZ1[(long)b * a.lddz + k] = dz2 * w2r[j] * dsigmoid_drop(h[j], a.drop_p);
-            else if (k < a.H1p) a.dZ1[(long)b * a.lddz + k] = 0.0f;
-            dw2r[j] = fmaf(h[j], dz2, dw2r[j]);
+            for (int j = 0; j < 4; j++) {
+                const int k = lane + 32 * j;
+                h[i][j] = (k < a.H1 && b0 + i < a.B) ? __ldg(a.H1d + (long)(b0 + i) * a.ldh + k) : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) z[i] = fmaf(h[i][j], w2r[j], z[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < R; i++) z[i] += __shfl_xor_sync(0xffffffffu, z[i], o);
+        }
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            const int b = b0 + i;
+            if (b >= a.B) break;
+            const float p = sigmoid32(z[i]);
+            if (lane == 0) { a.p[b] = p; if (a.logit) a.logit[b] = z[i]; }
+            if (!train) continue;
+            const float y = (b < a.nvalid) ? __ldg(a.y + b) : 0.0f;
+            if (lane == 0) cost += (double)(logf(p) * y + logf(1.0f - p) * (1.0f - y));
+            const float dz2 = (p - y) * invB;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int k = lane + 32 * j;
+                if (k < a.H1) a.dZ1[(long)b * a.lddz + k] = dz2 * w2r[j] * dsigmoid_drop(h[i][j], a.drop_p);
+                else if (k < a.H1p) a.dZ1[(long)b * a.lddz + k] = 0.0f;
+                dw2r[j] = fmaf(h[i][j], dz2, dw2r[j]);
+            }
         }
     }
     if (!train) return;
