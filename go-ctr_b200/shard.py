@@ -69,3 +69,14 @@ def return_grads(dist, torch, shard, grad_local, plan):
     g = _all_to_all(dist, torch, grad_local, scnt, rcnt)
     np.add.at(shard, recv_rows, g)
     return shard
+
+
+def allreduce_replicated(dist, torch, dense_grads, table_grad, cost_sum):
+    """The replicated placement's one collective (comm_allreduce_grads with the table-shaped buffer, comm_impl.cuh):
+    dense gradients, the row-gradient buffer [I, D] and the cost sum, summed over the ranks, in place."""
+    bufs = [torch.from_numpy(g) for g in dense_grads] + [torch.from_numpy(table_grad)]
+    for t in bufs:
+        dist.all_reduce(t)
+    c = torch.tensor([cost_sum], dtype=torch.float64)
+    dist.all_reduce(c)
+    return float(c.item())
