@@ -219,7 +219,10 @@ def run_item2vec(args):
             "gpu_launches": int(st.launches),
             "roofline": {"bound": "hbm", "kernel": "k_i2v_skipgram_hs", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": st.algorithmic_bytes, "ms_per_launch": st.ms_device,
-                         "pairs": int(st.pairs), "node_visits": int(st.node_visits)},
+                         "pairs": int(st.pairs), "node_visits": int(st.node_visits),
+                         "note": "Zipf item popularity: most node/context rows are served by L2 and the top Huffman nodes by shared memory "
+                                 "(ncu: DRAM traffic << algorithmic bytes, profiles/r01/ncu_item2vec_v2.md) - this is SURVEY 8(d)'s algorithmic-bytes figure, "
+                                 "not a DRAM reading; the kernel is L2-latency / issue bound"},
             "stats": {"doc_len": int(st.doc_len), "trained_positions": int(st.trained_positions)}}
     if not args.no_cpu_baseline:
         m = min(n, args.i2v_cpu_tokens)
