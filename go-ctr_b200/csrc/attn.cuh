@@ -7,10 +7,15 @@
 // (din.go:301, dnn.go:170).  HBM-bound: (S+1) rows of D floats per sample, one pass forward, one
 // pass backward (+ the L2-side red.add that writes each touched row back once).
 //
-// Mapping: one warp per sample.  Vector kernels: a row of D=4*LPR floats is covered by LPR lanes
-// with one 128-bit load each, so a warp issues 32/LPR rows per load instruction, UNR of them back
-// to back (UNR*32/LPR rows in flight per warp) before any arithmetic; the dot products reduce
-// inside the LPR-lane group with __shfl_xor.  Generic kernels: any D<=256, scalar loads.
+// Mapping: one warp per sample; a row of D = 4*LPR*VPL floats is covered by LPR lanes x VPL 128-bit loads,
+// so a warp carries 32/LPR rows per step and the dot products reduce inside the LPR-lane group with
+// __shfl_xor.  Three kernel families:
+//   k_attn_{fwd,bwd}_idx  index mode (rows come from the HBM tables), D in {16,32,64,128}, S <= 64: the
+//                         fast path — next-sample ids and the dense features travel through lane-private
+//                         shared-memory slots (cp.async), see the comments at the kernels;
+//   k_attn_{fwd,bwd}_vec  the same lane mapping for the dense-X compatibility route and S > 64;
+//   k_attn_{fwd,bwd}_gen  any D <= 256, unaligned sources (the reference test's D = 7), scalar loads.
+// Set CTR_ATTN_OLD=1 to route index-mode batches through the *_vec kernels (A/B checks).
 #pragma once
 #include "common.cuh"
 
