@@ -984,6 +984,8 @@ int ctr_gather_rows(ctr_handle* h, const int32_t* user_row, const int32_t* item_
 int ctr_train_dense(ctr_handle* h, const float* X, const float* Y, int64_t n, int32_t xcols, const int32_t ranges[8],
                     int32_t epochs, int32_t early_stop, float* last_cost, int32_t* epochs_run) {
     if (!h || !X || !Y || !ranges || n < 1 || xcols < 1 || epochs < 0) return set_err(h, CTR_EINVAL, "bad train arguments");
+    // the dense-X compatibility route has no gradient exchange: refusing beats training world replicas that silently diverge
+    if (h->comm.world > 1) return set_err(h, CTR_ESTATE, "ctr_train_dense is single-GPU; with world=%d train through the index entry points", h->comm.world);
     std::lock_guard<std::mutex> lk(h->mu);
     CU(h, cudaSetDevice(h->dev));
     RowSrc base{};
@@ -1372,7 +1374,7 @@ struct CkptHeader {
     int32_t has_table[3];
     int64_t tab_rows[3], tab_local_rows[3];
     int32_t tab_width[3];
-    int32_t pad;
+    int32_t replicated;            // ITEM_EMB placement under world > 1 (1 = every rank holds the whole table)
 };
 constexpr size_t kCkptChunk = 32u << 20;
 
@@ -1420,7 +1422,7 @@ int ctr_checkpoint_save(ctr_handle* h, const char* path) {
     CkptHeader hd{};
     memcpy(hd.magic, "CTRB200", 8);
     hd.version = 1; hd.model = c.model; hd.uP = c.uP; hd.S = c.S; hd.D = c.D; hd.cF = c.cF; hd.H0 = c.H0; hd.H1 = c.H1;
-    hd.rank = h->comm.rank; hd.world = h->comm.world; hd.step = h->step;
+    hd.rank = h->comm.rank; hd.world = h->comm.world; hd.step = h->step; hd.replicated = h->comm.replicate ? 1 : 0;
     for (int t = 0; t < 3; t++) { hd.has_table[t] = h->tab[t] != nullptr; hd.tab_rows[t] = h->tab_rows[t]; hd.tab_local_rows[t] = h->tab_local_rows[t]; hd.tab_width[t] = h->tab_width[t]; }
     int rc = fwrite(&hd, sizeof hd, 1, f) == 1 ? CTR_OK : set_err(h, CTR_EIO, "checkpoint: short write");
     for (int i = 0; i < 4 && rc == CTR_OK; i++) {
@@ -1463,6 +1465,8 @@ int ctr_checkpoint_load(ctr_handle* h, const char* path) {
         if (cudaMalloc(&h->tab[t], bytes) != cudaSuccess) { cudaGetLastError(); rc = set_err(h, CTR_ENOMEM, "checkpoint: table %d (%zu bytes)", t, bytes); break; }
         cudaMemsetAsync(h->tab[t], 0, bytes, h->stream);
         h->tab_ld[t] = ld; h->tab_rows[t] = hd.tab_rows[t]; h->tab_local_rows[t] = hd.tab_local_rows[t]; h->tab_width[t] = hd.tab_width[t];
+        // placement travels with the snapshot
+        if (t == CTR_TABLE_ITEM_EMB) h->comm.replicate = h->comm.world > 1 && hd.replicated == 1;
         rc = ckpt_read_2d(h, f, h->tab[t], ld, hd.tab_local_rows[t], hd.tab_width[t], bounce);
         if (t == CTR_TABLE_ITEM_EMB && h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; h->hot_rows = 0; }
     }

@@ -110,7 +110,8 @@ int ctr_gather_rows(ctr_handle* h, const int32_t* user_row, const int32_t* item_
  * (rcmd.go:339-460).  ranges = SampleInfo {UserProfile, UserBehavior, ItemFeature, CtxFeature} as
  * 4 [start,end) pairs (rcmd.go:132-137).  Zero-pads the ragged last batch and trains on it with
  * label 0 (model.go:132-184,357-371); *last_cost = cost of the last batch (model.go:198);
- * early_stop = no-improvement epochs (0 = off, model.go:199-209). */
+ * early_stop = no-improvement epochs (0 = off, model.go:199-209).  Single-GPU route (the reference's own shape of
+ * use); with world > 1 it returns CTR_ESTATE — multi-GPU training goes through the index entry points. */
 int ctr_train_dense(ctr_handle* h, const float* X, const float* Y, int64_t n, int32_t xcols,
                     const int32_t ranges[8], int32_t epochs, int32_t early_stop,
                     float* last_cost, int32_t* epochs_run);
