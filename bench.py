@@ -144,7 +144,7 @@ def run_reference(args, w, wname):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wname, "sample": "each step = %d samples of the workload (bounded CPU sample)" % Bc,
-                       "model": w["model"], "S": w["S"], "D": w["D"], "items": wc["I"]},
+                       "graph": w["model"], "S": w["S"], "D": w["D"], "items": wc["I"]},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": "%d steps x %d samples, OpenMP %d threads, C port of go-ctr semantics (Go reference unbuildable here)" % (args.steps, Bc, cores)},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -448,11 +448,11 @@ def main():
     line = {"metric": "ctr_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": leg["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wname, "note": w["note"], "model": w["model"], "users": w["U"], "items": w["I"], "D": w["D"], "S": w["S"],
+            "config": {"workload": wname, "note": w["note"], "graph": w["model"], "users": w["U"], "items": w["I"], "D": w["D"], "S": w["S"],
                        "uP": w["uP"], "cF": w["cF"], "per_gpu_batch": B, "global_batch": B * world, "table_opt": args.table_opt,
                        "gemm": args.gemm, "ids": "zipf(1.05)" if w["zipf"] else "uniform", "history_padding": "20% of samples have a -1 padded tail",
                        "l2": "256 MiB buffer written before every timed step (outside the event pair); per-step event pairs are summed",
-                       "parallelism": ("single GPU" if world == 1 else
+                       "placement": ("single GPU" if world == 1 else
                                        "1 process per GPU; ITEM_EMB (%.0f MB) replicated, row + dense gradients all-reduced (NCCL)" % (w["I"] * w["D"] * 4 / 1e6)
                                        if w["I"] * w["D"] * 4 <= 32 * 2**20 else "1 process per GPU; ITEM_EMB rows sharded row%world, de-duplicated all-to-all exchange (NCCL)")},
             "clocks": leg["clocks"], "e2e": {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
