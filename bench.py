@@ -143,8 +143,10 @@ def run_reference(args, w, wname):
     line = {"impl": "reference", "metric": "ctr_train_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wname, "sample": "each step = %d samples of the workload (bounded CPU sample)" % Bc,
-                       "graph": w["model"], "S": w["S"], "D": w["D"], "items": wc["I"]},
+            "config": {"workload": wname, "note": w["note"], "graph": w["model"], "users": w["U"], "items": w["I"], "D": w["D"], "S": w["S"],
+                       "uP": w["uP"], "cF": w["cF"], "per_gpu_batch": w["B"], "global_batch": w["B"] * args.gpus,
+                       "ids": "zipf(1.05)" if w["zipf"] else "uniform", "history_padding": "20% of samples have a -1 padded tail",
+                       "sample": "each step = %d samples of this workload on the host cores (bounded CPU sample; item table capped at %d rows)" % (Bc, wc["I"])},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": "%d steps x %d samples, OpenMP %d threads, C port of go-ctr semantics (Go reference unbuildable here)" % (args.steps, Bc, cores)},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
