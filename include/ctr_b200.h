@@ -62,8 +62,10 @@ typedef struct {
     float   table_lr;         /* SGD step for embedding rows (engine extension) */
     int32_t gemm;             /* CTR_GEMM_* */
     int32_t device;           /* CUDA device ordinal */
-    int32_t rank, world;      /* row-sharding of ITEM_EMB across `world` GPUs: owner(row) = row % world */
-    int32_t reserved[8];
+    int32_t rank, world;      /* one handle per GPU; ITEM_EMB is row-sharded (owner(row) = row % world) or, when small, replicated */
+    int32_t reserved[8];      /* tuning knobs, 0 = automatic: [0] hot rows with replica accumulators (< 0: none);
+                                 [1] ITEM_EMB placement under world > 1: 1 = always shard, 2 = always replicate
+                                 (default: replicate tables <= 32 MB, shard larger ones) */
 } ctr_config;
 
 typedef struct {
