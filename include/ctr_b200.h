@@ -95,7 +95,8 @@ int ctr_get_weights(ctr_handle* h, float* mlp0, float* mlp1, float* mlp2, float*
 
 /* Feature / embedding tables resident in HBM: replaces UserFeatureCache / ItemFeatureCache /
  * itemEmbeddingMap (rcmd.go:30-36, 473-505).  rows is [nrows, width] row-major.  With world > 1,
- * ITEM_EMB upload takes the FULL table on every rank and keeps rows r % world == rank. */
+ * ITEM_EMB upload takes the FULL table on every rank and keeps rows r % world == rank — or all of them when the
+ * table is small enough to be replicated (<= 32 MB, see ctr_config.reserved[1]); download mirrors that. */
 int ctr_table_upload(ctr_handle* h, int which, const float* rows, int64_t nrows, int32_t width);
 int ctr_table_download(ctr_handle* h, int which, float* rows, int64_t nrows, int32_t width);
 /* Synthetic table generated on the device with the counter RNG (benchmarks with 10M-100M rows,
