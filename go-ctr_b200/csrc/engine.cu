@@ -1359,7 +1359,7 @@ int ctr_batch_predict_keys(ctr_handle* h, const int64_t* user_ids, const int64_t
         RET(ctr_predict_idx_dev(h, h->s_user, h->s_item, h->s_hist, nb, nullptr));
         CU(h, cudaMemcpyAsync(hs, h->P, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
-        // rcmd.go:297-300: an unresolvable FIRST key is an error, later ones become zero rows
+        // rcmd.go:300-303: an unresolvable FIRST key is an error, later ones become zero rows
         if (s == 0 && *hfirst < 0) return set_err(h, CTR_ENOTFOUND, "get sample vector error: user %lld or item %lld has no features", (long long)user_ids[0], (long long)item_ids[0]);
         memcpy(scores + s, hs, sizeof(float) * (size_t)nb);
     }

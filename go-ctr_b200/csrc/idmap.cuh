@@ -1,9 +1,9 @@
 // idmap.cuh — sparse external id → dense table row, on the device.
 // The reference keys every cache by the decimal string of a Go int (`strconv.Itoa(sampleKey.UserId)`,
-// rcmd.go:472,484,502; `itemEmbeddingMap.Get`, :502,520) — MovieLens ids are sparse, the tables here are
+// rcmd.go:472,483,502; `itemEmbeddingMap.Get`, :502,519) — MovieLens ids are sparse, the tables here are
 // dense.  An open-addressing table (linear probing, load factor <= 0.5) in HBM maps int64 ids to int32
 // rows; a missing id yields -1, which the gather turns into a zero row exactly like the reference's
-// "embedding not found → zeros" (rcmd.go:501-505,520-522).
+// "embedding not found → zeros" (rcmd.go:501-505,519-521).
 #pragma once
 #include "common.cuh"
 
@@ -71,10 +71,10 @@ __device__ __forceinline__ int idmap_find(const unsigned long long* __restrict__
     }
 }
 
-// The whole key → index step of recommend.BatchPredict (rcmd.go:282-337) in one launch, one warp per key:
+// The whole key → index step of recommend.BatchPredict (rcmd.go:277-337) in one launch, one warp per key:
 // lanes 0/1 resolve the user / item id, the warp then evaluates TimeSeq.Filter (cache.go:71-94) for the
 // user's behaviour CSR (ub_off == nullptr: no UserBehavior provider → empty history) and writes hist [B,S].
-// BatchPredict's per-sample failure rule (rcmd.go:296-306): a key whose user or item feature cannot be
+// BatchPredict's per-sample failure rule (rcmd.go:299-307): a key whose user or item feature cannot be
 // fetched becomes an all-zero X row — user, item and every history slot are dropped together.
 // keys3 = [user ids | item ids | timestamps], each B long.
 __global__ void __launch_bounds__(256)

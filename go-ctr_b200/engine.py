@@ -303,7 +303,7 @@ class Engine:
         return out
 
     def batch_predict_keys(self, user_ids, item_ids, ts):
-        """recommend.BatchPredict (rcmd.go:282-337) over Sample keys."""
+        """recommend.BatchPredict (rcmd.go:277-337) over Sample keys."""
         u = np.ascontiguousarray(user_ids, np.int64); i = np.ascontiguousarray(item_ids, np.int64); t = np.ascontiguousarray(ts, np.int64)
         assert u.size == i.size == t.size
         out = np.empty(u.size, np.float32)

@@ -12,7 +12,7 @@ from . import engine as _e
 
 
 @dataclass
-class Sample:                      # rcmd.go:50-54
+class Sample:                      # rcmd.go:189-194
     UserId: int
     ItemId: int
     Timestamp: int = 0
@@ -20,13 +20,13 @@ class Sample:                      # rcmd.go:50-54
 
 
 @dataclass
-class ItemScore:                   # rcmd.go:65-68
+class ItemScore:                   # rcmd.go:184-187
     ItemId: int
     Score: float
 
 
 def BatchPredict(recSys, sampleKeys):
-    """rcmd.go:282-337.  Returns float32 [n, 1] like the tensor the reference hands back.  An unknown
+    """rcmd.go:277-337.  Returns float32 [n, 1] like the tensor the reference hands back.  An unknown
     user/item in key 0 raises (CtrError code ENOTFOUND), in later keys it scores as a zero X row."""
     if len(sampleKeys) == 0:
         raise ValueError("no sample keys")
@@ -37,7 +37,7 @@ def BatchPredict(recSys, sampleKeys):
 
 
 def Rank(recSys, userId, itemIds, now=None):
-    """rcmd.go:248-280: score `itemIds` for one user at the current time; order is the caller's."""
+    """rcmd.go:248-275: score `itemIds` for one user at the current time; order is the caller's."""
     ts = int(time.time()) if now is None else int(now)
     y = BatchPredict(recSys, [Sample(userId, it, ts) for it in itemIds])
     return [ItemScore(int(it), float(y[k, 0])) for k, it in enumerate(itemIds)]

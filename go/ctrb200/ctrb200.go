@@ -136,7 +136,7 @@ func (e *Engine) TrainIdx(userRow, itemRow, histRows []int32, label []float32, c
 
 func i64(p []int64) *C.int64_t { return (*C.int64_t)(unsafe.Pointer(&p[0])) }
 
-// LoadIDMaps replaces the strconv.Itoa-keyed caches (rcmd.go:472,484,502): userIds[r] / itemIds[r] is the
+// LoadIDMaps replaces the strconv.Itoa-keyed caches (rcmd.go:472,483,502): userIds[r] / itemIds[r] is the
 // external id of table row r.
 func (e *Engine) LoadIDMaps(userIds, itemIds []int64) error {
 	if err := e.err(C.ctr_idmap_build(e.h, C.CTR_IDMAP_USER, i64(userIds), C.int64_t(len(userIds)))); err != nil {
@@ -151,7 +151,7 @@ func (e *Engine) UploadUserBehavior(offsets, ts []int64, itemRows []int32) error
 	return e.err(C.ctr_ubcache_upload(e.h, i64(offsets), i64(ts), i32(itemRows), C.int64_t(len(offsets)-1), C.int64_t(len(ts))))
 }
 
-// BatchPredict is recommend.BatchPredict (rcmd.go:282-337) over sample keys, entirely on the device.
+// BatchPredict is recommend.BatchPredict (rcmd.go:277-337) over sample keys, entirely on the device.
 func (e *Engine) BatchPredict(sampleKeys []rcmd.Sample) ([]float32, error) {
 	n := len(sampleKeys)
 	u, it, ts := make([]int64, n), make([]int64, n), make([]int64, n)

@@ -180,21 +180,21 @@ int ctr_ubcache_window(ctr_handle* h, const int32_t* user_row, const int64_t* ma
 int ctr_ubcache_window_dev(ctr_handle* h, const int32_t* d_user_row, const int64_t* d_max_ts, int32_t B, int32_t* d_hist_rows);
 
 /* ---- sparse ids, serving keys, checkpoint ------------------------------------
- * The reference keys its caches by the decimal string of a Go int (rcmd.go:472,484,502,520); the engine's
+ * The reference keys its caches by the decimal string of a Go int (rcmd.go:472,483,502,519); the engine's
  * tables are dense.  ctr_idmap_build puts `ids[i] → row i` into a device hash table (which: CTR_IDMAP_*);
  * duplicate ids or INT64_MIN are rejected (CTR_EINVAL).  lookup writes the row, or -1 for an unknown id —
- * which the gather reads as a zero row, the reference's "not found → zeros" (rcmd.go:501-505,520-522). */
+ * which the gather reads as a zero row, the reference's "not found → zeros" (rcmd.go:501-505,519-521). */
 enum { CTR_IDMAP_USER = 0, CTR_IDMAP_ITEM = 1 };
 int ctr_idmap_build(ctr_handle* h, int which, const int64_t* ids, int64_t n);
 int ctr_idmap_lookup(ctr_handle* h, int which, const int64_t* ids, int64_t n, int32_t* rows);
 int ctr_idmap_lookup_dev(ctr_handle* h, int which, const int64_t* d_ids, int64_t n, int32_t* d_rows);
 
-/* recommend.BatchPredict (rcmd.go:282-337) over sample keys {UserId, ItemId, Timestamp} (rcmd.go:50-54),
+/* recommend.BatchPredict (rcmd.go:277-337) over sample keys {UserId, ItemId, Timestamp} (rcmd.go:189-194),
  * entirely on the device: id maps → rows, ubcache window at the sample's timestamp → history rows,
  * forward → scores [n].  Needs both id maps; without an uploaded ubcache the history is empty (the
- * reference's "UserBehavior not implemented → zeros", rcmd.go:498,507).  A key whose user or item is
- * unknown scores as an all-zero X row (rcmd.go:296-306) — unless it is key 0, which fails the call with
- * CTR_ENOTFOUND as the reference returns the error (rcmd.go:297-300).  recommend.Rank (rcmd.go:248-280) =
+ * reference's "UserBehavior not implemented → zeros", rcmd.go:498,509).  A key whose user or item is
+ * unknown scores as an all-zero X row (rcmd.go:299-307) — unless it is key 0, which fails the call with
+ * CTR_ENOTFOUND as the reference returns the error (rcmd.go:300-303).  recommend.Rank (rcmd.go:248-275) =
  * this with one user id, the candidate item ids and ts = now. */
 int ctr_batch_predict_keys(ctr_handle* h, const int64_t* user_ids, const int64_t* item_ids, const int64_t* ts,
                            int64_t n, float* scores);

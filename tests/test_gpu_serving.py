@@ -1,5 +1,5 @@
 """Rows f3/f4: sparse-id maps, BatchPredict/Rank over sample keys, and the binary checkpoint,
-through the C ABI, against the oracle / a plain dict restatement of rcmd.go:282-337,462-536."""
+through the C ABI, against the oracle / a plain dict restatement of rcmd.go:277-337,462-536."""
 import numpy as np
 import pytest
 
@@ -50,7 +50,7 @@ def _serving_engine(model, seed=0, U=60, I=150, uP=9, S=6, D=16, cF=7, pred_batc
 
 
 def _expected_scores(ocfg, W, tabs, ids, ub, keys, with_ub=True):
-    """rcmd.go:282-337 + 462-536 restated with dicts: rows (or a zero row), history window, oracle forward."""
+    """rcmd.go:277-337 + 462-536 restated with dicts: rows (or a zero row), history window, oracle forward."""
     uf, itf, emb = tabs; uid, iid = ids; off, ts, items, lens = ub
     umap = {int(v): r for r, v in enumerate(uid)}; imap = {int(v): r for r, v in enumerate(iid)}
     S = ocfg.S
@@ -59,7 +59,7 @@ def _expected_scores(ocfg, W, tabs, ids, ub, keys, with_ub=True):
     for k, (u, i, t) in enumerate(keys):
         r, c = umap.get(int(u), -1), imap.get(int(i), -1)
         if r < 0 or c < 0:
-            continue                                         # GetSampleVector error → zero X row (rcmd.go:296-306)
+            continue                                         # GetSampleVector error → zero X row (rcmd.go:299-307)
         ur[k], ir[k] = r, c
         if with_ub and lens[r] > 0:
             start, cnt = orc.ub_filter(ts[off[r]:off[r + 1]], int(t), S)
@@ -77,7 +77,7 @@ def test_batch_predict_over_sample_keys(model):
     ku = uid[rng.integers(0, uid.size, n)]; ki = iid[rng.integers(0, iid.size, n)]; kt = rng.integers(0, 1100, n).astype(np.int64)
     ku[5] = 999_999_999_999; ki[9] = -4; ku[200] = 0         # unknown user / item → zero rows (not key 0)
     keys = list(zip(ku, ki, kt))
-    # without an uploaded ubcache the history is empty (UserBehavior not implemented → zeros, rcmd.go:498,507)
+    # without an uploaded ubcache the history is empty (UserBehavior not implemented → zeros, rcmd.go:498,509)
     want, X = _expected_scores(ocfg, W, tabs, ids, ub, keys, with_ub=False)
     got = serving.BatchPredict(eng, [serving.Sample(int(u), int(i), int(t)) for u, i, t in keys])
     assert got.shape == (n, 1) and got.dtype == np.float32
@@ -88,7 +88,7 @@ def test_batch_predict_over_sample_keys(model):
     got = eng.batch_predict_keys(ku, ki, kt)
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-7)
     assert got[5] == got[9] == got[200]                      # the score of an all-zero row
-    # key 0 unresolvable → the call fails like the reference (rcmd.go:297-300)
+    # key 0 unresolvable → the call fails like the reference (rcmd.go:300-303)
     with pytest.raises(g.CtrError) as e:
         eng.batch_predict_keys(np.array([123456789012, uid[0]]), np.array([iid[0], iid[1]]), np.array([5, 5]))
     assert e.value.code == g.ENOTFOUND and "get sample vector error" in str(e.value)
