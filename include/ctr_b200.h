@@ -132,7 +132,9 @@ int ctr_train_step_idx(ctr_handle* h, const int32_t* user_row, const int32_t* it
 /* model.Train's batch loop for one pass over n samples (model.go:107-196) fed by row ids: batches of
  * cfg.batch are consumed in order, the ragged tail is zero-padded with label 0 (model.go:357-371), and
  * the host→device copy of batch i+1 overlaps the compute of batch i (second stream).  One coarse call
- * per epoch is the shape a cgo caller wants.  costs (may be NULL) receives ceil(n/batch) batch costs. */
+ * per epoch is the shape a cgo caller wants.  costs (may be NULL) receives ceil(n/batch) batch costs.
+ * With world > 1 (replicated ITEM_EMB) every step contains collectives: all ranks must call with the same n;
+ * row-sharded tables use ctr_train_step_idx per batch. */
 int ctr_train_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row,
                   const int32_t* hist_rows, const float* label, int64_t n, float* costs);
 /* recommend.BatchPredict → model.Predict (rcmd.go:277-337) fed by indices. out is [n]. */
