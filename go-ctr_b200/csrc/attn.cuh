@@ -53,7 +53,7 @@ __device__ __forceinline__ RowRef ub_ref(const RowSrc& r, const Dims& d, const H
     if (s >= d.S || b >= r.nvalid) return o;
     if (r.dense) { o.p = r.X + (long)b * r.ldx + r.ub0 + (long)s * d.D; return o; }
     int idx = use_hi ? sidx : __ldg(r.hist + (long)b * d.S + s);
-    if (idx >= 0) { o.p = r.emb + (long)idx * r.lde; o.idx = idx; }
+    if (row_ok(idx, r.n_emb)) { o.p = emb_row(r, idx); o.idx = idx; }
     return o;
 }
 __device__ __forceinline__ const float* ub_ptr(const RowSrc& r, const Dims& d, const HistIdx& hi,
@@ -200,7 +200,23 @@ k_attn_fwd_vec(RowSrc r, Dims d, const float* __restrict__ att,
 //     the following lanes the ctx chunks and the zero pad, the sub-group-0 lanes pooled + item.
 // Requires S <= 64, uP % 4 == 0, 16-byte aligned table rows and (Kp - 2D)/4 <= 32 (one chunk per lane).
 // -------------------------------------------------------------------------------------------------
-template <int LPR, int VPL, int MODEL, int NT, int MINB>
+// streaming 128-bit load of a row that may live in a peer GPU's HBM (NVLink): plain ld.global, no L1 allocation
+__device__ __forceinline__ float4 ld4_peer(const float* p) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+template <bool PEER>
+__device__ __forceinline__ float* emb_ptr(const RowSrc& r, int idx) {
+    return PEER ? r.peer_emb[idx & r.wmask] + (long)(idx >> r.wshift) * r.lde : const_cast<float*>(r.emb) + (long)idx * r.lde;
+}
+
+// PEER: ITEM_EMB (and ITEM_FEAT when large) are row-sharded over the GPUs of the box and every shard is mapped into
+// this process (CUDA IPC): the gather reads the owner's HBM directly over NVLink — the transfer is the load itself, so
+// it overlaps the gate math of the other warps tile by tile — and keeps each fetched row in rows_cache for the
+// backward, so a row crosses NVLink once per step.
+template <int LPR, int VPL, int MODEL, bool PEER, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_attn_fwd_idx(RowSrc r, Dims d, const float* __restrict__ att, float* __restrict__ X0, long ldx0, int Kp, int B) {
     constexpr int RPW = 32 / LPR, DD = 4 * LPR * VPL;
@@ -216,49 +232,65 @@ k_attn_fwd_idx(RowSrc r, Dims d, const float* __restrict__ att, float* __restric
     const int fc = f_user ? lane : lane - nu4;
     const bool f_load = f_user || fc < nc4;
     const int f_off = f_user ? 4 * lane : d.uP + 2 * DD + 4 * fc;
-    const float* f_tab = f_user ? r.ufeat : r.ifeat;
-    const long f_ld = f_user ? r.ldu : r.ldi;
+    const int f_n = f_user ? r.n_user : r.n_ifeat;
     const int* f_ids = f_user ? r.user_row : (r.item_feat_row ? r.item_feat_row : r.item_row);
     int* my_ids = reinterpret_cast<int*>(&s_ids[threadIdx.x]);
     float4* my_feat = &s_feat[threadIdx.x];
 
-    auto fetch_ids = [&](int bb) {           // asynchronous: lands in my_ids
-        const int* h = r.hist + (long)bb * d.S;
-        if (lane < d.S) cp_async4(my_ids, h + lane);
-        if (lane + 32 < d.S) cp_async4(my_ids + 1, h + lane + 32);
-        cp_async4(my_ids + 2, r.item_row + bb);
-        cp_async4(my_ids + 3, f_ids + bb);
+    auto fetch_ids = [&](int bb) {           // asynchronous: lands in my_ids; the zero-padded tail (model.go:357-371) has no ids
+        if (bb < r.nvalid) {
+            const int* h = r.hist + (long)bb * d.S;
+            if (lane < d.S) cp_async4(my_ids, h + lane);
+            if (lane + 32 < d.S) cp_async4(my_ids + 1, h + lane + 32);
+            cp_async4(my_ids + 2, r.item_row + bb);
+            cp_async4(my_ids + 3, f_ids + bb);
+        } else *reinterpret_cast<int4*>(my_ids) = make_int4(-1, -1, -1, -1);
         cp_async_commit();
     };
     *reinterpret_cast<int4*>(my_ids) = make_int4(-1, -1, -1, -1);
     fetch_ids(b);
     for (;;) {
         cp_async_wait_all();
-        const int4 id = *reinterpret_cast<const int4*>(my_ids);        // x: hist[lane], y: hist[lane+32], z: item, w: feature row
+        int4 id = *reinterpret_cast<const int4*>(my_ids);        // x: hist[lane], y: hist[lane+32], z: item, w: feature row
+        id.x = row_ok(id.x, r.n_emb) ? id.x : -1; id.y = row_ok(id.y, r.n_emb) ? id.y : -1;
+        id.z = row_ok(id.z, r.n_emb) ? id.z : -1; id.w = row_ok(id.w, f_n) ? id.w : -1;
         const int bn = b + nwarps;
         if (bn < B) fetch_ids(bn);
-        if (f_load) cp_async16(my_feat, f_tab + (long)(id.w >= 0 ? id.w : 0) * f_ld + 4 * fc, id.w >= 0);
+        if (f_load) {
+            const int fw = id.w >= 0 ? id.w : 0;
+            const float* fp = f_user ? r.ufeat + (long)fw * r.ldu : (PEER ? ifeat_row(r, fw) : r.ifeat + (long)fw * r.ldi);
+            cp_async16(my_feat, fp + 4 * fc, id.w >= 0);
+        }
         cp_async_commit();
         float4 v[VPL], acc[VPL];
         float ny2 = 0.0f;
-        const float* ip = r.emb + (long)(id.z >= 0 ? id.z : 0) * r.lde;
+        const float* ip = emb_ptr<PEER>(r, id.z >= 0 ? id.z : 0);
+        float* cache_b = (PEER && r.rows_cache) ? r.rows_cache + (long)b * (d.S + 1) * DD : nullptr;    // predict keeps no rows
 #pragma unroll
-        for (int q = 0; q < VPL; q++) { v[q] = id.z >= 0 ? ldg4(ip + (q * LPR + lir) * 4) : zero4(); acc[q] = zero4(); }
+        for (int q = 0; q < VPL; q++) {
+            v[q] = id.z >= 0 ? (PEER ? ld4_peer(ip + (q * LPR + lir) * 4) : ldg4(ip + (q * LPR + lir) * 4)) : zero4();
+            acc[q] = zero4();
+        }
         // history rows: the loads of a group are issued, then (first group only) the item row's norm is formed
         // while they are in flight, then the group is consumed
+        int row;
         auto load_rows = [&](float4 (&u)[VPL], int s0) {
             const int s = s0 + sub;
             const int a0 = __shfl_sync(0xffffffffu, id.x, s & 31), a1 = __shfl_sync(0xffffffffu, id.y, s & 31);
-            const int row = s < d.S ? (s < 32 ? a0 : a1) : -1;
-            const float* p = r.emb + (long)(row >= 0 ? row : 0) * r.lde + lir * 4;
+            row = s < d.S ? (s < 32 ? a0 : a1) : -1;
+            const float* p = emb_ptr<PEER>(r, row >= 0 ? row : 0) + lir * 4;
 #pragma unroll
-            for (int q = 0; q < VPL; q++) u[q] = row >= 0 ? ldg4_stream(p + q * LPR * 4) : zero4();
+            for (int q = 0; q < VPL; q++) u[q] = row >= 0 ? (PEER ? ld4_peer(p + q * LPR * 4) : ldg4_stream(p + q * LPR * 4)) : zero4();
         };
         float4 u[VPL];
         load_rows(u, 0);
 #pragma unroll
         for (int q = 0; q < VPL; q++) ny2 += dot4(v[q], v[q]);
         const float ny = fsqrt_pos(group_sum<LPR>(ny2));
+        if (PEER && cache_b && sub == 0 && id.z >= 0) {
+#pragma unroll
+            for (int q = 0; q < VPL; q++) *reinterpret_cast<float4*>(cache_b + (long)d.S * DD + (q * LPR + lir) * 4) = v[q];
+        }
         for (int s0 = 0;;) {
             const int s = s0 + sub;
             float a = 1.0f;
@@ -280,6 +312,11 @@ k_attn_fwd_idx(RowSrc r, Dims d, const float* __restrict__ att, float* __restric
             }
 #pragma unroll
             for (int q = 0; q < VPL; q++) acc[q] = fma4(a, u[q], acc[q]);      // slots beyond S / missing rows carry u == 0
+            if (PEER && cache_b && row >= 0) {
+                float* c = cache_b + (long)s * DD + lir * 4;
+#pragma unroll
+                for (int q = 0; q < VPL; q++) *reinterpret_cast<float4*>(c + q * LPR * 4) = u[q];
+            }
             s0 += RPW;
             if (s0 >= d.S) break;
             load_rows(u, s0);
@@ -547,7 +584,10 @@ k_attn_bwd_vec(RowSrc r, Dims d, const float* __restrict__ att,
 // 8-lanes-per-row mapping the register-resident version was limited to.  FUSED: scatter-add + SGD straight into
 // the table / hot-row replicas (red.global.add.v4.f32); otherwise gradients go to the dUb / dIt buffers.
 // Requires S <= 64.
-template <int LPR, int VPL, int MODEL, bool FUSED, int NT, int MINB>
+// PEER (row-sharded tables over NVLink, see k_attn_fwd_idx): rows are re-read from rows_cache (what the forward
+// fetched — the gradient is taken at the step-start table values, and nothing crosses NVLink twice), and each row
+// gradient leaves as red.global.add.v4.f32 straight into the OWNER's table over NVLink, pre-scaled by -lr/world.
+template <int LPR, int VPL, int MODEL, bool FUSED, bool PEER, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
                const float* __restrict__ dX, long lddx, BwdOut o, int B) {
@@ -565,11 +605,13 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
     int* my_ids = reinterpret_cast<int*>(&s_ids[threadIdx.x]);
     *reinterpret_cast<int4*>(my_ids) = make_int4(-1, -1, -1, -1);
     __syncthreads();
-    auto fetch_ids = [&](int bb) {
-        const int* h = r.hist + (long)bb * d.S;
-        if (lane < d.S) cp_async4(my_ids, h + lane);
-        if (lane + 32 < d.S) cp_async4(my_ids + 1, h + lane + 32);
-        cp_async4(my_ids + 2, r.item_row + bb);
+    auto fetch_ids = [&](int bb) {           // the zero-padded tail (model.go:357-371) has no ids
+        if (bb < r.nvalid) {
+            const int* h = r.hist + (long)bb * d.S;
+            if (lane < d.S) cp_async4(my_ids, h + lane);
+            if (lane + 32 < d.S) cp_async4(my_ids + 1, h + lane + 32);
+            cp_async4(my_ids + 2, r.item_row + bb);
+        } else *reinterpret_cast<int4*>(my_ids) = make_int4(-1, -1, -1, -1);
         cp_async_commit();
     };
     const float4* gs = s_g[wib];
@@ -578,19 +620,22 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
     if (b < B) fetch_ids(b);
     while (b < B) {
         cp_async_wait_all();
-        const int4 id = *reinterpret_cast<const int4*>(my_ids);
+        int4 id = *reinterpret_cast<const int4*>(my_ids);
+        id.x = row_ok(id.x, r.n_emb) ? id.x : -1; id.y = row_ok(id.y, r.n_emb) ? id.y : -1; id.z = row_ok(id.z, r.n_emb) ? id.z : -1;
         const int bn = b + nwarps;
         if (bn < B) fetch_ids(bn);
+        const float* cache_b = PEER ? r.rows_cache + (long)b * (d.S + 1) * (4 * CH) : nullptr;
         // stage g and v (one float4 per lane; the table is written by this kernel in FUSED mode: coherent load)
         if (lane < CH) {
             s_g[wib][lane] = ldg4(dX + (long)b * lddx + 4 * lane);
-            s_v[wib][lane] = id.z >= 0 ? *reinterpret_cast<const float4*>(r.emb + (long)id.z * r.lde + 4 * lane) : zero4();
+            const float* vp = PEER ? cache_b + (long)d.S * (4 * CH) : r.emb + (long)(id.z >= 0 ? id.z : 0) * r.lde;
+            s_v[wib][lane] = id.z >= 0 ? *reinterpret_cast<const float4*>(vp + 4 * lane) : zero4();
         }
         auto load_rows = [&](float4 (&u)[VPL], int& row, int s0) {
             const int s = s0 + sub;
             const int a0 = __shfl_sync(0xffffffffu, id.x, s & 31), a1 = __shfl_sync(0xffffffffu, id.y, s & 31);
             row = s < d.S ? (s < 32 ? a0 : a1) : -1;
-            const float* p = r.emb + (long)(row >= 0 ? row : 0) * r.lde + lir * 4;
+            const float* p = (PEER ? cache_b + (long)(s < d.S ? s : 0) * (4 * CH) : r.emb + (long)(row >= 0 ? row : 0) * r.lde) + lir * 4;
 #pragma unroll
             for (int q = 0; q < VPL; q++) u[q] = row >= 0 ? *reinterpret_cast<const float4*>(p + q * LPR * 4) : zero4();
         };
@@ -650,7 +695,7 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
             if (s < d.S) {
                 const float e1 = c1 * sc, e2 = c2 * sc, e3 = c3 * sc;
                 float* dst = nullptr;
-                if (FUSED) { if (row >= 0) dst = scatter_dst(r, d, o, row, rep) + lir * 4; }
+                if (FUSED) { if (row >= 0) dst = (PEER ? emb_ptr<true>(r, row) : scatter_dst(r, d, o, row, rep)) + lir * 4; }
                 else if (o.dUb) dst = o.dUb + ((long)b * d.S + s) * d.D + lir * 4;
 #pragma unroll
                 for (int q = 0; q < VPL; q++) {
@@ -681,7 +726,7 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
         }
         if (sub == 0) {
             float* dst = nullptr;
-            if (FUSED) { if (id.z >= 0) dst = scatter_dst(r, d, o, id.z, rep) + lir * 4; }
+            if (FUSED) { if (id.z >= 0) dst = (PEER ? emb_ptr<true>(r, id.z) : scatter_dst(r, d, o, id.z, rep)) + lir * 4; }
             else if (o.dIt) dst = o.dIt + (long)b * d.D + lir * 4;
 #pragma unroll
             for (int q = 0; q < VPL; q++) {
@@ -864,12 +909,13 @@ k_gather_rows(RowSrc r, Dims d, float* __restrict__ X, long ldx, int B) {
 // ascending p (== (b, slot) order) accumulating in double, then applies row -= lr * sum once.
 // -------------------------------------------------------------------------------------------------
 __global__ void k_scatter_keys(const int* __restrict__ hist, const int* __restrict__ item_row,
-                               int S, int B, unsigned* __restrict__ keys, unsigned* __restrict__ pos) {
+                               int S, int B, int nvalid, int n_emb, unsigned* __restrict__ keys, unsigned* __restrict__ pos) {
     long n = (long)B * (S + 1);
     for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n; p += (long)gridDim.x * blockDim.x) {
         int b = (int)(p / (S + 1)), sl = (int)(p % (S + 1));
-        int row = sl < S ? hist[(long)b * S + sl] : item_row[b];
-        keys[p] = row >= 0 ? (unsigned)row : 0xFFFFFFFFu;
+        // rows of the zero-padded tail (b >= nvalid, model.go:357-371) have no ids: the staging slot holds stale ones
+        int row = b < nvalid ? (sl < S ? hist[(long)b * S + sl] : item_row[b]) : -1;
+        keys[p] = row_ok(row, n_emb) ? (unsigned)row : 0xFFFFFFFFu;
         pos[p] = (unsigned)p;
     }
 }
@@ -897,6 +943,64 @@ k_segment_sgd(const unsigned* __restrict__ keys, const unsigned* __restrict__ po
                 float* e = emb + (long)key * lde + k;
                 *e = (float)((double)*e - (double)lr * acc);
             }
+        }
+    }
+}
+
+// CTR_TABLE_ADAM: the dense solver's update (gorgonia AdamSolver.Step as model.go:88 configures it: g *= 1/batch;
+// m = b1 m + (1-b1) g; v = b2 v + (1-b2) g²; w -= lr · (m/c1) / (sqrt(v/c2) + eps)) applied to the embedding rows
+// the batch touched — once per distinct row with the row's summed gradient ("lazy" Adam: untouched rows keep their
+// moments; no L2 on embeddings).  c1 = 1-b1^t, c2 = 1-b2^t with the dense step counter t.
+struct RowAdam { float lr, b1, b2, eps, c1, c2, inv_batch; };
+__device__ __forceinline__ void row_adam_elem(float& w, float& m, float& v, float g, const RowAdam& a) {
+    g *= a.inv_batch;
+    m = a.b1 * m + (1.0f - a.b1) * g;
+    v = a.b2 * v + (1.0f - a.b2) * g * g;
+    w -= a.lr * (m / a.c1) / (sqrtf(v / a.c2) + a.eps);
+}
+__global__ void __launch_bounds__(256)
+k_segment_adam(const unsigned* __restrict__ keys, const unsigned* __restrict__ pos, long n,
+               const float* __restrict__ dUb, const float* __restrict__ dIt, int S, int D,
+               float* __restrict__ emb, float* __restrict__ mo, float* __restrict__ vo, long lde, RowAdam a) {
+    const int lane = threadIdx.x & 31;
+    long w = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    long nw = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long i = w; i < n; i += nw) {
+        unsigned key = keys[i];
+        if (key == 0xFFFFFFFFu) continue;
+        if (i > 0 && keys[i - 1] == key) continue;        // not a segment head
+        for (int k0 = 0; k0 < D; k0 += 32) {
+            int k = k0 + lane;
+            double acc = 0.0;
+            for (long j = i; j < n && keys[j] == key; j++) {
+                unsigned p = pos[j];
+                int b = (int)(p / (unsigned)(S + 1)), sl = (int)(p % (unsigned)(S + 1));
+                if (k < D) acc += (double)(sl < S ? dUb[((long)b * S + sl) * D + k] : dIt[(long)b * D + k]);
+            }
+            if (k < D) {
+                const long o = (long)key * lde + k;
+                float ww = emb[o], mm = mo[o], vv = vo[o];
+                row_adam_elem(ww, mm, vv, (float)acc, a);
+                emb[o] = ww; mo[o] = mm; vo[o] = vv;
+            }
+        }
+    }
+}
+// replicated-table step: grad holds the all-reduced 1/world * gradient sums; rows with any non-zero element were touched
+__global__ void __launch_bounds__(256)
+k_apply_table_adam(float* __restrict__ tab, float* __restrict__ grad, float* __restrict__ mo, float* __restrict__ vo, long rows, int ld, RowAdam a) {
+    const int lane = threadIdx.x & 31;
+    long w = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long r = w; r < rows; r += nw) {
+        bool any = false;
+        for (int k = lane; k < ld; k += 32) any |= grad[r * ld + k] != 0.0f;
+        if (!__any_sync(0xffffffffu, any)) continue;
+        for (int k = lane; k < ld; k += 32) {
+            const long o = r * ld + k;
+            float ww = tab[o], mm = mo[o], vv = vo[o];
+            row_adam_elem(ww, mm, vv, grad[o], a);
+            tab[o] = ww; mo[o] = mm; vo[o] = vv; grad[o] = 0.0f;
         }
     }
 }

@@ -97,42 +97,61 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Where one sample's rows come from.  index mode: the HBM tables + per-sample row ids
 // (GetSampleVector rcmd.go:462-536 done inside the kernel).  dense mode: a materialised X row and
 // SampleInfo column offsets (model.Train's tensor.Slice calls, model.go:129-171).
+// Row ids outside [0, n_*) read as "missing" (zeros), exactly like -1: a stale id from the host can never
+// address memory outside the table (the reference's "not found -> zeros", rcmd.go:501-505,519-521).
+constexpr int kMaxPeers = 8;         // one NVSwitch box
 struct RowSrc {
-    const float* emb;   long lde;     // ITEM_EMB  [I, D]
+    const float* emb;   long lde;     // ITEM_EMB  [I, D]   (this rank's shard when world > 1)
     const float* ufeat; long ldu;     // USER_FEAT [U, uP]
     const float* ifeat; long ldi;     // ITEM_FEAT [I, cF]
     const int* user_row; const int* item_row; const int* hist;   // [B] [B] [B,S]
-    const int* item_feat_row;    // row of ITEM_FEAT when it differs from item_row (sharded tables: item_row is a slot)
+    const int* item_feat_row;    // row of ITEM_FEAT when it differs from item_row
     const float* X; long ldx; int up0, ub0, it0, cx0;            // dense mode
     int dense;
     int nvalid;          // rows >= nvalid are the zero-padded tail (model.go:357-371)
+    int n_emb, n_user, n_ifeat;      // logical (global) row counts: ids outside [0, n) are missing rows
+    // row-sharded tables over NVLink peer memory (comm.cuh): owner(row) = row & wmask, local row = row >> wshift.
+    // peer_emb[j] / peer_ifeat[j] are rank j's shards mapped into this process (CUDA IPC); world == 1: unused.
+    int world, wmask, wshift, ifeat_sharded;
+    float* peer_emb[kMaxPeers];
+    const float* peer_ifeat[kMaxPeers];
+    float* rows_cache;   // [B, S+1, D]: the forward keeps every fetched row for the backward (one NVLink pull per row)
 };
 
 struct Dims { int uP, S, D, cF, in; };
+
+__device__ __forceinline__ bool row_ok(int idx, int n) { return (unsigned)idx < (unsigned)n; }
+// address of ITEM_EMB row idx (must be valid)
+__device__ __forceinline__ const float* emb_row(const RowSrc& r, int idx) {
+    return r.world > 1 ? r.peer_emb[idx & r.wmask] + (long)(idx >> r.wshift) * r.lde : r.emb + (long)idx * r.lde;
+}
+__device__ __forceinline__ const float* ifeat_row(const RowSrc& r, int idx) {
+    return r.ifeat_sharded ? r.peer_ifeat[idx & r.wmask] + (long)(idx >> r.wshift) * r.ldi : r.ifeat + (long)idx * r.ldi;
+}
 
 __device__ __forceinline__ const float* src_ub(const RowSrc& r, const Dims& d, int b, int s) {
     if (b >= r.nvalid) return nullptr;
     if (r.dense) return r.X + (long)b * r.ldx + r.ub0 + (long)s * d.D;
     int idx = r.hist[(long)b * d.S + s];
-    return idx >= 0 ? r.emb + (long)idx * r.lde : nullptr;
+    return row_ok(idx, r.n_emb) ? emb_row(r, idx) : nullptr;
 }
 __device__ __forceinline__ const float* src_it(const RowSrc& r, const Dims& d, int b) {
     if (b >= r.nvalid) return nullptr;
     if (r.dense) return r.X + (long)b * r.ldx + r.it0;
     int idx = r.item_row[b];
-    return idx >= 0 ? r.emb + (long)idx * r.lde : nullptr;
+    return row_ok(idx, r.n_emb) ? emb_row(r, idx) : nullptr;
 }
 __device__ __forceinline__ const float* src_up(const RowSrc& r, int b) {
     if (b >= r.nvalid) return nullptr;
     if (r.dense) return r.X + (long)b * r.ldx + r.up0;
     int idx = r.user_row[b];
-    return idx >= 0 ? r.ufeat + (long)idx * r.ldu : nullptr;
+    return row_ok(idx, r.n_user) ? r.ufeat + (long)idx * r.ldu : nullptr;
 }
 __device__ __forceinline__ const float* src_cx(const RowSrc& r, int b) {
     if (b >= r.nvalid) return nullptr;
     if (r.dense) return r.X + (long)b * r.ldx + r.cx0;
     int idx = r.item_feat_row ? r.item_feat_row[b] : r.item_row[b];
-    return idx >= 0 ? r.ifeat + (long)idx * r.ldi : nullptr;
+    return row_ok(idx, r.n_ifeat) ? ifeat_row(r, idx) : nullptr;
 }
 
 }  // namespace ctr

@@ -20,9 +20,12 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace ctr;
@@ -34,6 +37,47 @@ std::string g_create_error;
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct Prof { double ms = 0; long n = 0; };
+
+// Caller buffers are pageable (Go slices, numpy arrays): a cudaMemcpyAsync straight from them is staged
+// synchronously by the driver and kills the copy/compute overlap.  The epoch entry points therefore copy each batch
+// into a pinned ring first — with a few worker threads, a single memcpy stream tops out near 10 GB/s — and DMA from
+// there.  The library never keeps a caller pointer past the call (cgo rule).
+class CopyPool {
+public:
+    explicit CopyPool(int n) { for (int i = 0; i < n; i++) th_.emplace_back([this] { run(); }); }
+    ~CopyPool() { { std::lock_guard<std::mutex> l(m_); stop_ = true; } cv_.notify_all(); for (auto& t : th_) t.join(); }
+    // copies n bytes, split over the workers and the calling thread; returns when done
+    void copy(void* dst, const void* src, size_t n) {
+        const size_t kMin = (size_t)1 << 20;
+        const int parts = (int)std::min<size_t>(th_.size() + 1, std::max<size_t>(1, n / kMin));
+        if (parts <= 1) { memcpy(dst, src, n); return; }
+        const size_t chunk = (n / parts + 63) & ~(size_t)63;
+        { std::lock_guard<std::mutex> l(m_);
+          for (int i = 1; i < parts; i++) {
+              const size_t off = (size_t)i * chunk; if (off >= n) break;
+              jobs_.push_back({(char*)dst + off, (const char*)src + off, std::min(chunk, n - off)}); pending_++;
+          } }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(chunk, n));
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return pending_ == 0; });
+    }
+private:
+    struct Job { char* d; const char* s; size_t n; };
+    void run() {
+        for (;;) {
+            Job j;
+            { std::unique_lock<std::mutex> l(m_);
+              cv_.wait(l, [this] { return stop_ || !jobs_.empty(); });
+              if (stop_ && jobs_.empty()) return;
+              j = jobs_.back(); jobs_.pop_back(); }
+            memcpy(j.d, j.s, j.n);
+            { std::lock_guard<std::mutex> l(m_); if (--pending_ == 0) done_.notify_all(); }
+        }
+    }
+    std::vector<std::thread> th_; std::vector<Job> jobs_;
+    std::mutex m_; std::condition_variable cv_, done_; int pending_ = 0; bool stop_ = false;
+};
 
 }  // namespace
 
@@ -54,9 +98,13 @@ struct ctr_handle {
     int64_t tab_rows[3] = {0, 0, 0};      // logical (global) rows
     int64_t tab_local_rows[3] = {0, 0, 0};
     int tab_width[3] = {0, 0, 0};
+    bool tab_sharded[3] = {false, false, false};   // world > 1: rows r % world == rank live here, the rest on the peers
+    VmmBuf tab_vmm[3];                    // a sharded table lives in shareable (VMM) memory; tab[] points into it
+    uint64_t tab_gen = 1;                 // bumped whenever an ITEM_* table is (re)allocated: peers must re-map it
 
     // learnables, padded storage: W0 [Kp,H0p] W1 [H0p,H1p] W2 [H1p] att [Sp]; grads / Adam moments alike
     float *W[4] = {}, *G[4] = {}, *Mo[4] = {}, *Vo[4] = {};
+    float* Gflat = nullptr; size_t Gflat_n = 0;    // the four gradient tensors live in one buffer (one all-reduce, one memset)
     size_t wsize[4] = {};
     uint32_t step = 0;                    // optimiser steps taken (Adam t = step+1; dropout stream = step*4+layer)
 
@@ -69,13 +117,22 @@ struct ctr_handle {
     void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0; size_t keys_cap = 0;
     double* d_cost = nullptr;
     float* hot_acc = nullptr; int hot_rows = 0, hot_reps = 0;
+    float *emb_m = nullptr, *emb_v = nullptr;      // CTR_TABLE_ADAM: first / second moments of ITEM_EMB, same layout as the table
     // staging for host-pointer entry points
     int *s_user = nullptr, *s_item = nullptr, *s_hist = nullptr; float* s_label = nullptr;
-    // second staging set + copy stream for the pipelined epoch entry point (ctr_train_idx)
-    int *p_user = nullptr, *p_item = nullptr, *p_hist = nullptr; float* p_label = nullptr;
+    // epoch entry points (ctr_train_idx / ctr_train_keys): pinned host ring (filled by the copy pool from the caller's
+    // pageable buffers) → device slots on a copy stream, overlapping the compute of the previous batch
+    static constexpr int kPin = 3;
+    unsigned char* feed_pin[kPin] = {}; unsigned char* feed_dev[2] = {}; size_t feed_bytes = 0;
+    cudaEvent_t pin_free[kPin] = {};
+    CopyPool* pool = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     double* d_costs = nullptr; size_t d_costs_cap = 0;
+    // ctr_train_keys: resolved + compacted samples resident in HBM
+    int *kt_user = nullptr, *kt_item = nullptr; long long* kt_ts = nullptr; float* kt_label = nullptr; size_t kt_cap = 0;
+    int *kt_flag = nullptr, *kt_pos = nullptr; void* kt_scan_tmp = nullptr; size_t kt_scan_bytes = 0; size_t kt_chunk = 0;
+    unsigned long long* kt_count = nullptr;
     // dense-X residency
     float* dXd = nullptr; float* dYd = nullptr; size_t dXd_cap = 0, dYd_cap = 0;
 
@@ -196,27 +253,27 @@ void launch_bwd_vec(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
 bool idx_fwd_ok(const ctr_handle* h, const RowSrc& r, int B) {
     static const bool off = getenv("CTR_ATTN_OLD") != nullptr;
     const ctr_config& c = h->cfg;
-    return !off && !r.dense && r.nvalid >= B && c.S <= 64 && c.uP % 4 == 0 && r.ldu % 4 == 0 && r.ldi % 4 == 0 && (h->Kp - 2 * c.D) / 4 <= 32 &&
+    return !off && !r.dense && c.S <= 64 && c.uP % 4 == 0 && r.ldu % 4 == 0 && r.ldi % 4 == 0 && (h->Kp - 2 * c.D) / 4 <= 32 &&
            r.ufeat && r.ifeat;
 }
 bool idx_bwd_ok(const ctr_handle* h, const RowSrc& r, int B) {
     static const bool off = getenv("CTR_ATTN_OLD") != nullptr;
-    return !off && !r.dense && r.nvalid >= B && h->cfg.S <= 64;
+    return !off && !r.dense && h->cfg.S <= 64;
 }
-template <int LPR, int VPL, int MINB>
+template <int LPR, int VPL, int MINB, bool PEER>
 void launch_fwd_idx(ctr_handle* h, const RowSrc& r, int B) {
     const int g = grid_attn(h, B);
     switch (h->cfg.model) {
-        case CTR_MODEL_YOUTUBE: k_attn_fwd_idx<LPR, VPL, MODEL_YOUTUBE, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
-        case CTR_MODEL_DIN_COS: k_attn_fwd_idx<LPR, VPL, MODEL_DIN_COS, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
-        default:                k_attn_fwd_idx<LPR, VPL, MODEL_DIN_EUC, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
+        case CTR_MODEL_YOUTUBE: k_attn_fwd_idx<LPR, VPL, MODEL_YOUTUBE, PEER, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
+        case CTR_MODEL_DIN_COS: k_attn_fwd_idx<LPR, VPL, MODEL_DIN_COS, PEER, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
+        default:                k_attn_fwd_idx<LPR, VPL, MODEL_DIN_EUC, PEER, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->X0, h->Kp, h->Kp, B); break;
     }
 }
-template <int LPR, int VPL, int MINB>
+template <int LPR, int VPL, int MINB, bool PEER>
 void launch_bwd_idx(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
     const int g = grid_attn(h, B);
-#define BWD_CASE(M) { if (o.sgd) k_attn_bwd_idx<LPR, VPL, M, true, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); \
-                      else       k_attn_bwd_idx<LPR, VPL, M, false, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); }
+#define BWD_CASE(M) { if (o.sgd) k_attn_bwd_idx<LPR, VPL, M, true, PEER, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); \
+                      else       k_attn_bwd_idx<LPR, VPL, M, false, PEER, 128, MINB><<<g, 128, 0, h->stream>>>(r, dims_of(h), h->W[3], h->dX, h->lddx, o, B); }
     switch (h->cfg.model) {
         case CTR_MODEL_YOUTUBE: BWD_CASE(MODEL_YOUTUBE) break;
         case CTR_MODEL_DIN_COS: BWD_CASE(MODEL_DIN_COS) break;
@@ -224,17 +281,30 @@ void launch_bwd_idx(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
     }
 #undef BWD_CASE
 }
+template <bool PEER>
+void dispatch_fwd_idx(ctr_handle* h, const RowSrc& r, int B) {
+    switch (h->cfg.D / 4) {
+        case 4: launch_fwd_idx<4, 1, 8, PEER>(h, r, B); break;    case 8: launch_fwd_idx<4, 2, 8, PEER>(h, r, B); break;
+        case 16: launch_fwd_idx<4, 4, 8, PEER>(h, r, B); break;
+        default: launch_fwd_idx<8, 4, 8, PEER>(h, r, B); break;
+    }
+}
+template <bool PEER>
+void dispatch_bwd_idx(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
+    switch (h->cfg.D / 4) {
+        case 4: launch_bwd_idx<4, 1, 8, PEER>(h, r, o, B); break;    case 8: launch_bwd_idx<4, 2, 8, PEER>(h, r, o, B); break;
+        // D = 64: 8 lanes x 2 float4 (128-byte contiguous red.add / load segments per row) measured faster than
+        // 4 x 4 (64-byte segments, 0.39 vs 0.34 ms) although the latter executes a third fewer instructions
+        case 16: launch_bwd_idx<8, 2, 8, PEER>(h, r, o, B); break;
+        default: launch_bwd_idx<16, 2, 8, PEER>(h, r, o, B); break;
+    }
+}
 
 int attn_forward(ctr_handle* h, const RowSrc& r, int B) {
-    if (vec_ok(h, r) && idx_fwd_ok(h, r, B)) {
-        return launch(h, "attn_fwd_vec", [&] {
-            switch (h->cfg.D / 4) {
-                case 4: launch_fwd_idx<4, 1, 8>(h, r, B); break;    case 8: launch_fwd_idx<4, 2, 8>(h, r, B); break;
-                case 16: launch_fwd_idx<4, 4, 8>(h, r, B); break;
-                default: launch_fwd_idx<8, 4, 8>(h, r, B); break;
-            }
-        });
-    }
+    if (r.world > 1)        // row-sharded tables: the owner's HBM is read over NVLink (comm_check vetted the dims)
+        return launch(h, "attn_fwd_peer", [&] { dispatch_fwd_idx<true>(h, r, B); });
+    if (vec_ok(h, r) && idx_fwd_ok(h, r, B))
+        return launch(h, "attn_fwd_vec", [&] { dispatch_fwd_idx<false>(h, r, B); });
     if (vec_ok(h, r)) {
         return launch(h, "attn_fwd_vec", [&] {
             switch (h->cfg.D / 4) {           // float4 per row
@@ -249,17 +319,10 @@ int attn_forward(ctr_handle* h, const RowSrc& r, int B) {
 }
 
 int attn_backward(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
-    if (vec_ok(h, r) && idx_bwd_ok(h, r, B)) {
-        return launch(h, "attn_bwd_vec", [&] {
-            switch (h->cfg.D / 4) {
-                case 4: launch_bwd_idx<4, 1, 8>(h, r, o, B); break;    case 8: launch_bwd_idx<4, 2, 8>(h, r, o, B); break;
-                // D = 64: 8 lanes x 2 float4 (128-byte contiguous red.add / load segments per row) measured faster than
-                // 4 x 4 (64-byte segments, 0.39 vs 0.34 ms) although the latter executes a third fewer instructions
-                case 16: launch_bwd_idx<8, 2, 8>(h, r, o, B); break;
-                default: launch_bwd_idx<16, 2, 8>(h, r, o, B); break;
-            }
-        });
-    }
+    if (r.world > 1)
+        return launch(h, "attn_bwd_peer", [&] { dispatch_bwd_idx<true>(h, r, o, B); });
+    if (vec_ok(h, r) && idx_bwd_ok(h, r, B))
+        return launch(h, "attn_bwd_vec", [&] { dispatch_bwd_idx<false>(h, r, o, B); });
     if (vec_ok(h, r)) {
         return launch(h, "attn_bwd_vec", [&] {
             switch (h->cfg.D / 4) {
@@ -415,7 +478,8 @@ int umma_dw(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtens
 // the weight-gradient GEMMs run on tcgen05 when the padded widths fit 8 column blocks and the batch
 // is the configured training batch (the TMA maps zero-fill rows beyond it)
 bool use_umma_dw(const ctr_handle* h, int B) {
-    return B == h->cfg.batch && h->Kp <= 256 && h->H0p <= 256 && h->H1p <= 256 && !getenv("CTR_DW_FP32");
+    static const bool off = getenv("CTR_DW_FP32") != nullptr;
+    return B == h->cfg.batch && h->Kp <= 256 && h->H0p <= 256 && h->H1p <= 256 && !off;
 }
 
 bool use_umma(const ctr_handle* h) {
@@ -430,8 +494,8 @@ struct StepOpts {
     const float* d_label = nullptr;
     // sharded-table step (comm_impl.cuh): rows live in a per-lookup buffer, gradients are scaled to the
     // global mean and the dense gradients are all-reduced before Adam
-    bool comm = false; float* scatter_base = nullptr; float grad_scale = 1.0f; int adam_batch = 0;
-    float* rep_acc = nullptr; int rep_rows = 0, rep_n = 0;      // replica accumulators over the batch's distinct rows
+    bool comm = false; float grad_scale = 1.0f; int adam_batch = 0;
+    bool peer = false;                   // rows come from / go to the owners' shards over NVLink (RowSrc.world > 1)
     // replicated-table step: row gradients are summed into table_grad (layout of the table), all-reduced with the
     // dense gradients and applied on every rank
     float* table_grad = nullptr; size_t table_grad_n = 0;
@@ -468,7 +532,15 @@ int ensure_hot(ctr_handle* h) {
     return dalloc(h, &h->hot_acc, (size_t)reps * want * h->cfg.D);
 }
 
-int deterministic_table_update(ctr_handle* h, const RowSrc& r, int B) {
+// CTR_TABLE_ADAM: moments of the embedding rows (zero-initialised, like the solver's, model.go:88)
+int ensure_moments(ctr_handle* h) {
+    if (h->emb_m) return CTR_OK;
+    const size_t n = (size_t)std::max<int64_t>(h->tab_local_rows[CTR_TABLE_ITEM_EMB], 1) * h->tab_ld[CTR_TABLE_ITEM_EMB];
+    RET(dalloc(h, &h->emb_m, n)); RET(dalloc(h, &h->emb_v, n));
+    return CTR_OK;
+}
+
+int deterministic_table_update(ctr_handle* h, const RowSrc& r, int B, int adam_batch) {
     const int S = h->cfg.S, D = h->cfg.D;
     size_t n = (size_t)B * (S + 1);
     if (h->keys_cap < n) {
@@ -482,11 +554,22 @@ int deterministic_table_update(ctr_handle* h, const RowSrc& r, int B) {
         h->sort_tmp_bytes = bytes; h->keys_cap = n;
     }
     RET(launch(h, "scatter_keys", [&] {
-        k_scatter_keys<<<std::min<int>((int)((n + 255) / 256), h->num_sms * 8), 256, 0, h->stream>>>(r.hist, r.item_row, S, B, h->keys, h->pos);
+        k_scatter_keys<<<std::min<int>((int)((n + 255) / 256), h->num_sms * 8), 256, 0, h->stream>>>(r.hist, r.item_row, S, B, r.nvalid, r.n_emb, h->keys, h->pos);
     }));
     RET(launch(h, "cub_radix_sort_pairs", [&] {
         cub::DeviceRadixSort::SortPairs(h->sort_tmp, h->sort_tmp_bytes, h->keys, h->keys2, h->pos, h->pos2, (int)n, 0, 32, h->stream);
     }));
+    if (h->cfg.table_opt == CTR_TABLE_ADAM) {
+        RET(ensure_moments(h));
+        const ctr_config& c = h->cfg;
+        const int t = (int)h->step + 1;                    // the dense solver's step counter (k_adam runs after this)
+        RowAdam ra{c.table_lr, c.beta1, c.beta2, c.eps, (float)(1.0 - std::pow((double)c.beta1, (double)t)), (float)(1.0 - std::pow((double)c.beta2, (double)t)),
+                   adam_batch > 1 ? 1.0f / (float)adam_batch : 1.0f};
+        return launch(h, "segment_adam", [&] {
+            k_segment_adam<<<std::min<int>((int)((n * 32 + 255) / 256), h->num_sms * 16), 256, 0, h->stream>>>(
+                h->keys2, h->pos2, (long)n, h->dUb, h->dIt, S, D, h->tab[CTR_TABLE_ITEM_EMB], h->emb_m, h->emb_v, h->tab_ld[CTR_TABLE_ITEM_EMB], ra);
+        });
+    }
     RET(launch(h, "segment_sgd", [&] {
         k_segment_sgd<<<std::min<int>((int)((n * 32 + 255) / 256), h->num_sms * 16), 256, 0, h->stream>>>(
             h->keys2, h->pos2, (long)n, h->dUb, h->dIt, S, D, h->tab[CTR_TABLE_ITEM_EMB], h->tab_ld[CTR_TABLE_ITEM_EMB], h->cfg.table_lr);
@@ -573,30 +656,42 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
             RET((gemm_big<false, true, EPI_STORE>(h, "sgemm_dX", g)));
         }
         const bool fused_only = o.comm || o.table_grad;        // multi-GPU steps always scatter with red.add
-        const bool buffers = o.want_rows || (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC && !fused_only);
+        const bool sorted_rows = c.table_opt == CTR_TABLE_SGD_DETERMINISTIC || c.table_opt == CTR_TABLE_ADAM;   // per-unique-row update from sorted keys
+        const bool adam_rows = learn_rows && c.table_opt == CTR_TABLE_ADAM;
+        if (adam_rows && o.peer) return set_err(h, CTR_ESTATE, "CTR_TABLE_ADAM is not available with row-sharded tables (use CTR_TABLE_SGD, or a replicated table)");
+        const bool buffers = o.want_rows || (learn_rows && sorted_rows && !fused_only);
         if (buffers) RET(ensure_rowgrad_buffers(h, B));
         BwdOut bo{}; bo.datt = h->G[3]; bo.dUb = buffers ? h->dUb : nullptr; bo.dIt = buffers ? h->dIt : nullptr;
-        bo.sgd = (learn_rows && (c.table_opt == CTR_TABLE_SGD || fused_only)) ? 1 : 0; bo.neg_lr = -c.table_lr * o.grad_scale;
-        bo.scatter_base = o.scatter_base ? o.scatter_base : o.table_grad ? o.table_grad : h->tab[CTR_TABLE_ITEM_EMB];
+        bo.sgd = (learn_rows && (c.table_opt == CTR_TABLE_SGD || fused_only)) ? 1 : 0;
+        // what leaves the kernel: -lr/world * gradient (SGD: added straight into rows), or 1/world * gradient (Adam on a
+        // replicated table: the all-reduced sum is the global-batch gradient the row solver consumes)
+        bo.neg_lr = (adam_rows ? 1.0f : -c.table_lr) * o.grad_scale;
+        bo.scatter_base = o.table_grad ? o.table_grad : h->tab[CTR_TABLE_ITEM_EMB];
         const bool hot = bo.sgd && vec_ok(h, r) && !o.comm;
         if (hot) { RET(ensure_hot(h)); bo.hot_acc = h->hot_acc; bo.hot_rows = h->hot_rows; bo.hot_reps = h->hot_reps; }
-        if (o.comm && o.rep_acc && bo.sgd) { bo.hot_acc = o.rep_acc; bo.hot_rows = o.rep_rows; bo.hot_reps = o.rep_n; }
+        // sharded tables: nobody's red.add may land in a row before every rank's forward has read it
+        if (o.peer && bo.sgd) RET(comm_barrier(h));
         RET(attn_backward(h, r, bo, B));
-        if (o.comm && o.rep_acc && bo.sgd && o.rep_rows > 0)
-            RET(launch(h, "shard_fold_replicas", [&] {
-                k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(o.scatter_base, c.D, o.rep_acc, o.rep_rows, o.rep_n, c.D, 1.0f);
-            }));
         if (hot && h->hot_rows > 0)
             RET(launch(h, "hot_rows_apply", [&] {
                 k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(bo.scatter_base, h->tab_ld[CTR_TABLE_ITEM_EMB], h->hot_acc,
                                                                 h->hot_rows, h->hot_reps, c.D, 1.0f);
             }));
-        if (learn_rows && c.table_opt == CTR_TABLE_SGD_DETERMINISTIC && !fused_only) RET(deterministic_table_update(h, r, B));
+        if (learn_rows && sorted_rows && !fused_only) RET(deterministic_table_update(h, r, B, o.adam_batch > 0 ? o.adam_batch : B));
     }
     if (o.update) {
         const bool tg = o.table_grad && c.table_opt != CTR_TABLE_FROZEN;
         if (o.comm || o.table_grad) RET(comm_allreduce_grads(h, tg ? o.table_grad : nullptr, tg ? o.table_grad_n : 0));
-        if (tg)
+        if (tg && c.table_opt == CTR_TABLE_ADAM) {
+            RET(ensure_moments(h));
+            const int t = (int)h->step + 1; const int ab = o.adam_batch > 0 ? o.adam_batch : B;
+            RowAdam ra{c.table_lr, c.beta1, c.beta2, c.eps, (float)(1.0 - std::pow((double)c.beta1, (double)t)), (float)(1.0 - std::pow((double)c.beta2, (double)t)),
+                       ab > 1 ? 1.0f / (float)ab : 1.0f};
+            RET(launch(h, "apply_table_adam", [&] {
+                k_apply_table_adam<<<h->num_sms * 8, 256, 0, h->stream>>>(h->tab[CTR_TABLE_ITEM_EMB], o.table_grad, h->emb_m, h->emb_v,
+                                                                         (long)h->tab_rows[CTR_TABLE_ITEM_EMB], (int)h->tab_ld[CTR_TABLE_ITEM_EMB], ra);
+            }));
+        } else if (tg)
             RET(launch(h, "apply_table_grad", [&] {
                 k_apply_table_grad<<<h->num_sms * 8, 256, 0, h->stream>>>(h->tab[CTR_TABLE_ITEM_EMB], o.table_grad, (long)(o.table_grad_n / 4));
             }));
@@ -621,18 +716,53 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
 }
 
 int zero_grads(ctr_handle* h) {
-    for (int i = 0; i < 4; i++) CU(h, cudaMemsetAsync(h->G[i], 0, h->wsize[i] * sizeof(float), h->stream));
+    CU(h, cudaMemsetAsync(h->Gflat, 0, h->Gflat_n * sizeof(float), h->stream));
     return CTR_OK;
 }
 
-// ITEM_EMB placement under world > 1: sharded by row % world, or (small tables) replicated on every rank.
-// cfg.reserved[1]: 0 = by size, 1 = always shard, 2 = always replicate.
-bool emb_replicated(const ctr_handle* h, int64_t nrows, int32_t width) {
-    if (h->comm.world <= 1) return false;
+// Placement of the ITEM_* tables under world > 1: sharded by row % world (large tables), or replicated on every
+// rank.  cfg.reserved[1]: 0 = by size (> 32 MB shards), 1 = always shard, 2 = always replicate.  USER_FEAT is
+// always replicated.
+bool table_sharded(const ctr_handle* h, int which, int64_t nrows, int32_t width) {
+    if (h->comm.world <= 1 || which == CTR_TABLE_USER_FEAT) return false;
     const int pol = h->cfg.reserved[1];
-    if (pol == 1) return false;
-    if (pol == 2) return true;
-    return (size_t)nrows * round_up(width, 4) * sizeof(float) <= kReplicateBytes;
+    if (pol == 1) return true;
+    if (pol == 2) return false;
+    return (size_t)nrows * round_up(width, 4) * sizeof(float) > kReplicateBytes;
+}
+
+// (re)allocates table `which` for nrows logical rows; decides the placement; leaves the rows zeroed
+void table_free(ctr_handle* h, int which) {
+    if (h->tab_vmm[which].live) { cudaStreamSynchronize(h->stream); vmm_free(&h->tab_vmm[which]); }
+    else if (h->tab[which]) cudaFree(h->tab[which]);
+    h->tab[which] = nullptr;
+}
+// device memory of a table: shareable VMM memory when the table is sharded (peers map it), cudaMalloc otherwise
+int table_mem(ctr_handle* h, int which, bool shard, size_t bytes) {
+    table_free(h, which);
+    if (shard) {
+        std::string err;
+        if (!vmm_alloc(bytes, h->dev, &h->tab_vmm[which], &err)) return set_err(h, CTR_ENOMEM, "table %d (%zu bytes): %s", which, bytes, err.c_str());
+        h->tab[which] = (float*)h->tab_vmm[which].ptr;
+    } else CU(h, cudaMalloc(&h->tab[which], bytes));
+    CU(h, cudaMemsetAsync(h->tab[which], 0, bytes, h->stream));
+    return CTR_OK;
+}
+int table_alloc(ctr_handle* h, int which, int64_t nrows, int32_t width) {
+    const long ld = round_up(width, 4);                       // 16-byte aligned rows for 128-bit loads
+    const bool shard = table_sharded(h, which, nrows, width);
+    const int64_t local = shard ? (nrows - h->comm.rank + h->comm.world - 1) / h->comm.world : nrows;
+    const size_t bytes = (size_t)std::max<int64_t>(local, 1) * ld * sizeof(float);
+    RET(table_mem(h, which, shard, bytes));
+    h->tab_ld[which] = ld; h->tab_rows[which] = nrows; h->tab_local_rows[which] = local; h->tab_width[which] = width;
+    h->tab_sharded[which] = shard;
+    if (which == CTR_TABLE_ITEM_EMB) {
+        h->comm.replicate = h->comm.world > 1 && !shard;
+        if (h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; h->hot_rows = 0; }
+        for (float** p : {&h->emb_m, &h->emb_v}) if (*p) { cudaFree(*p); *p = nullptr; }       // a new table starts a new solver state
+    }
+    if (which != CTR_TABLE_USER_FEAT) h->tab_gen++;           // peers hold mappings of the old allocation
+    return CTR_OK;
 }
 
 RowSrc idx_src(const ctr_handle* h, const int* d_user, const int* d_item, const int* d_hist, int B) {
@@ -642,6 +772,10 @@ RowSrc idx_src(const ctr_handle* h, const int* d_user, const int* d_item, const 
     r.ifeat = h->tab[CTR_TABLE_ITEM_FEAT]; r.ldi = h->tab_ld[CTR_TABLE_ITEM_FEAT];
     r.user_row = d_user; r.item_row = d_item; r.hist = d_hist;
     r.dense = 0; r.nvalid = B;
+    r.n_emb = (int)std::min<int64_t>(h->tab_rows[CTR_TABLE_ITEM_EMB], 0x7fffffff);
+    r.n_user = (int)std::min<int64_t>(h->tab_rows[CTR_TABLE_USER_FEAT], 0x7fffffff);
+    r.n_ifeat = (int)std::min<int64_t>(h->tab_rows[CTR_TABLE_ITEM_FEAT], 0x7fffffff);
+    r.world = 1;
     return r;
 }
 
@@ -653,7 +787,8 @@ int check_tables(const ctr_handle* h) {
         return set_err(h, CTR_ESTATE, "USER_FEAT table not uploaded with width uP=%d", c.uP);
     if (c.cF > 0 && (!h->tab[CTR_TABLE_ITEM_FEAT] || h->tab_width[CTR_TABLE_ITEM_FEAT] != c.cF))
         return set_err(h, CTR_ESTATE, "ITEM_FEAT table not uploaded with width cF=%d", c.cF);
-    if (h->comm.world > 1 && !h->comm.replicate) return set_err(h, CTR_ESTATE, "sharded tables: use the comm step path");
+    if (h->comm.world > 1 && (h->tab_sharded[CTR_TABLE_ITEM_EMB] || h->tab_sharded[CTR_TABLE_ITEM_FEAT]))
+        return set_err(h, CTR_ESTATE, "this entry point gathers locally: ITEM_EMB / ITEM_FEAT must both be replicated (or both sharded for the train / predict entry points)");
     return CTR_OK;
 }
 
@@ -671,6 +806,7 @@ int read_cost(ctr_handle* h, int B, float* cost) {
     CU(h, cudaMemcpyAsync(&s, h->d_cost, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     *cost = -(float)(s / (double)B);         // -mean, cost.go:15
+    if (h->comm.h_err && *h->comm.h_err) return set_err(h, CTR_ECOMM, "peer barrier timed out waiting for rank %d (a rank left the step loop?)", *h->comm.h_err - 1);
     return CTR_OK;
 }
 
@@ -680,7 +816,7 @@ int dense_src(ctr_handle* h, const int32_t ranges[8], int32_t xcols, RowSrc* out
     if (up1 - up0 != c.uP || ub1 - ub0 != c.S * c.D || it1 - it0 != c.D || cx1 - cx0 != c.cF)
         return set_err(h, CTR_EINVAL, "SampleInfo ranges do not match the model dims (uP=%d S*D=%d D=%d cF=%d)", c.uP, c.S * c.D, c.D, c.cF);
     for (int i = 0; i < 8; i++) if (ranges[i] < 0 || ranges[i] > xcols) return set_err(h, CTR_EINVAL, "SampleInfo range outside [0, xcols=%d]", xcols);
-    RowSrc r{}; r.dense = 1; r.ldx = xcols; r.up0 = up0; r.ub0 = ub0; r.it0 = it0; r.cx0 = cx0;
+    RowSrc r{}; r.dense = 1; r.world = 1; r.ldx = xcols; r.up0 = up0; r.ub0 = ub0; r.it0 = it0; r.cx0 = cx0;
     *out = r;
     return CTR_OK;
 }
@@ -782,6 +918,7 @@ int ctr_create(const ctr_config* cfg, ctr_handle** out) {
     *out = nullptr;
     const ctr_config& c = *cfg;
     if (c.model < 0 || c.model > 2) return set_err(nullptr, CTR_EINVAL, "unknown model %d", c.model);
+    if (c.table_opt < CTR_TABLE_FROZEN || c.table_opt > CTR_TABLE_ADAM) return set_err(nullptr, CTR_EINVAL, "unknown table optimiser %d", c.table_opt);
     if (c.uP < 0 || c.cF < 0 || c.S < 1 || c.D < 1 || c.H0 < 1 || c.H1 < 1 || c.batch < 1 || c.pred_batch < 1)
         return set_err(nullptr, CTR_EINVAL, "bad dims");
     if (c.D > 32 * kGenAcc) return set_err(nullptr, CTR_EINVAL, "D=%d > %d unsupported", c.D, 32 * kGenAcc);
@@ -807,7 +944,10 @@ int ctr_create(const ctr_config* cfg, ctr_handle** out) {
     h->lddx = round_up(2 * c.D, 4);
     h->Bmax = std::max(c.batch, c.pred_batch);
     h->wsize[0] = (size_t)h->Kp * h->H0p; h->wsize[1] = (size_t)h->H0p * h->H1p; h->wsize[2] = h->H1p; h->wsize[3] = h->Sp;
-    for (int i = 0; i < 4; i++) { RC(dalloc(h, &h->W[i], h->wsize[i])); RC(dalloc(h, &h->G[i], h->wsize[i])); RC(dalloc(h, &h->Mo[i], h->wsize[i])); RC(dalloc(h, &h->Vo[i], h->wsize[i])); }
+    h->Gflat_n = h->wsize[0] + h->wsize[1] + h->wsize[2] + h->wsize[3];
+    RC(dalloc(h, &h->Gflat, h->Gflat_n));
+    for (size_t i = 0, off = 0; i < 4; off += h->wsize[i], i++) h->G[i] = h->Gflat + off;
+    for (int i = 0; i < 4; i++) { RC(dalloc(h, &h->W[i], h->wsize[i])); RC(dalloc(h, &h->Mo[i], h->wsize[i])); RC(dalloc(h, &h->Vo[i], h->wsize[i])); }
     const size_t B = h->Bmax;
     RC(dalloc(h, &h->X0, B * h->Kp)); RC(dalloc(h, &h->H0d, B * h->H0p)); RC(dalloc(h, &h->H1d, B * h->H1p));
     RC(dalloc(h, &h->P, B)); RC(dalloc(h, &h->Z, B));
@@ -827,20 +967,24 @@ void ctr_destroy(ctr_handle* h) {
     cudaSetDevice(h->dev);
     if (h->stream) cudaStreamSynchronize(h->stream);
     comm_destroy(h);
-    for (int i = 0; i < 3; i++) if (h->tab[i]) cudaFree(h->tab[i]);
+    for (int i = 0; i < 3; i++) table_free(h, i);
     for (void* p : {(void*)h->ub_off, (void*)h->ub_ts, (void*)h->ub_items}) if (p) cudaFree(p);
     for (void* p : {(void*)h->idm_keys[0], (void*)h->idm_keys[1], (void*)h->idm_vals[0], (void*)h->idm_vals[1], (void*)h->k_keys, (void*)h->k_flags}) if (p) cudaFree(p);
     if (h->k_host) cudaFreeHost(h->k_host);
     for (int i = 0; i < 2; i++) for (float* p : {h->um.Wt0[i], h->um.Wt1[i], h->um.W1s[i], h->um.W0s[i]}) if (p) cudaFree(p);
-    for (int i = 0; i < 4; i++) for (float* p : {h->W[i], h->G[i], h->Mo[i], h->Vo[i]}) if (p) cudaFree(p);
+    for (int i = 0; i < 4; i++) for (float* p : {h->W[i], h->Mo[i], h->Vo[i]}) if (p) cudaFree(p);
+    if (h->Gflat) cudaFree(h->Gflat);
     for (void* p : {(void*)h->X0, (void*)h->H0d, (void*)h->H1d, (void*)h->P, (void*)h->Z, (void*)h->dZ1, (void*)h->dZ0, (void*)h->dX,
                     (void*)h->dUb, (void*)h->dIt, (void*)h->keys, (void*)h->keys2, (void*)h->pos, (void*)h->pos2, h->sort_tmp,
-                    (void*)h->d_cost, (void*)h->s_user, (void*)h->s_item, (void*)h->s_hist, (void*)h->s_label, (void*)h->dXd, (void*)h->dYd, (void*)h->hot_acc})
+                    (void*)h->d_cost, (void*)h->s_user, (void*)h->s_item, (void*)h->s_hist, (void*)h->s_label, (void*)h->dXd, (void*)h->dYd, (void*)h->hot_acc, (void*)h->emb_m, (void*)h->emb_v})
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]); }
-    for (void* p : {(void*)h->p_user, (void*)h->p_item, (void*)h->p_hist, (void*)h->p_label, (void*)h->d_costs}) if (p) cudaFree(p);
+    for (void* p : {(void*)h->feed_dev[0], (void*)h->feed_dev[1], (void*)h->d_costs, (void*)h->kt_user, (void*)h->kt_item, (void*)h->kt_ts, (void*)h->kt_label,
+                    (void*)h->kt_flag, (void*)h->kt_pos, h->kt_scan_tmp, (void*)h->kt_count}) if (p) cudaFree(p);
+    for (int i = 0; i < ctr_handle::kPin; i++) { if (h->feed_pin[i]) cudaFreeHost(h->feed_pin[i]); if (h->pin_free[i]) cudaEventDestroy(h->pin_free[i]); }
+    delete h->pool; h->pool = nullptr;
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -896,22 +1040,15 @@ int ctr_table_upload(ctr_handle* h, int which, const float* rows, int64_t nrows,
     const int want = which == CTR_TABLE_USER_FEAT ? c.uP : which == CTR_TABLE_ITEM_FEAT ? c.cF : c.D;
     if (width != want) return set_err(h, CTR_EINVAL, "table %d width %d != model dim %d", which, width, want);
     CU(h, cudaSetDevice(h->dev));
-    if (h->tab[which]) { cudaFree(h->tab[which]); h->tab[which] = nullptr; }
-    const long ld = round_up(width, 4);                       // 16-byte aligned rows for 128-bit loads
-    if (which == CTR_TABLE_ITEM_EMB) h->comm.replicate = emb_replicated(h, nrows, width);
-    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1 && !h->comm.replicate;
-    const int64_t local = shard ? (nrows - h->comm.rank + h->comm.world - 1) / h->comm.world : nrows;
-    CU(h, cudaMalloc(&h->tab[which], (size_t)std::max<int64_t>(local, 1) * ld * sizeof(float)));
-    CU(h, cudaMemsetAsync(h->tab[which], 0, (size_t)std::max<int64_t>(local, 1) * ld * sizeof(float), h->stream));
-    if (!shard) {
+    RET(table_alloc(h, which, nrows, width));
+    const long ld = h->tab_ld[which]; const int64_t local = h->tab_local_rows[which];
+    if (!h->tab_sharded[which]) {
         CU(h, cudaMemcpy2DAsync(h->tab[which], ld * sizeof(float), rows, (size_t)width * sizeof(float), (size_t)width * sizeof(float), (size_t)nrows, cudaMemcpyHostToDevice, h->stream));
     } else if (local > 0) {   // owner(row) = row % world; local row = row / world
         CU(h, cudaMemcpy2DAsync(h->tab[which], ld * sizeof(float), rows + (size_t)h->comm.rank * width, (size_t)width * h->comm.world * sizeof(float),
                                 (size_t)width * sizeof(float), (size_t)local, cudaMemcpyHostToDevice, h->stream));
     }
     CU(h, cudaStreamSynchronize(h->stream));
-    h->tab_ld[which] = ld; h->tab_rows[which] = nrows; h->tab_local_rows[which] = local; h->tab_width[which] = width;
-    if (which == CTR_TABLE_ITEM_EMB && h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; h->hot_rows = 0; }
     return CTR_OK;
 }
 
@@ -922,21 +1059,13 @@ int ctr_table_fill(ctr_handle* h, int which, int64_t nrows, int32_t width, uint3
     const int want = which == CTR_TABLE_USER_FEAT ? c.uP : which == CTR_TABLE_ITEM_FEAT ? c.cF : c.D;
     if (width != want) return set_err(h, CTR_EINVAL, "table %d width %d != model dim %d", which, width, want);
     CU(h, cudaSetDevice(h->dev));
-    if (h->tab[which]) { cudaFree(h->tab[which]); h->tab[which] = nullptr; }
-    const long ld = round_up(width, 4);
-    if (which == CTR_TABLE_ITEM_EMB) h->comm.replicate = emb_replicated(h, nrows, width);
-    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1 && !h->comm.replicate;
-    const int64_t local = shard ? (nrows - h->comm.rank + h->comm.world - 1) / h->comm.world : nrows;
-    const size_t bytes = (size_t)std::max<int64_t>(local, 1) * ld * sizeof(float);
-    CU(h, cudaMalloc(&h->tab[which], bytes));
-    CU(h, cudaMemsetAsync(h->tab[which], 0, bytes, h->stream));
+    RET(table_alloc(h, which, nrows, width));
+    const bool shard = h->tab_sharded[which];
     RET(launch(h, "table_fill", [&] {
-        k_table_fill<<<h->num_sms * 8, 256, 0, h->stream>>>(h->tab[which], ld, (long)local, width, shard ? h->comm.world : 1, shard ? h->comm.rank : 0,
-                                                           seed, (uint32_t)which, dist, scale);
+        k_table_fill<<<h->num_sms * 8, 256, 0, h->stream>>>(h->tab[which], h->tab_ld[which], (long)h->tab_local_rows[which], width, shard ? h->comm.world : 1,
+                                                           shard ? h->comm.rank : 0, seed, (uint32_t)which, dist, scale);
     }));
     CU(h, cudaStreamSynchronize(h->stream));
-    h->tab_ld[which] = ld; h->tab_rows[which] = nrows; h->tab_local_rows[which] = local; h->tab_width[which] = width;
-    if (which == CTR_TABLE_ITEM_EMB && h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; h->hot_rows = 0; }
     return CTR_OK;
 }
 
@@ -945,7 +1074,7 @@ int ctr_table_download(ctr_handle* h, int which, float* rows, int64_t nrows, int
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->tab[which] || nrows != h->tab_rows[which] || width != h->tab_width[which]) return set_err(h, CTR_EINVAL, "table %d shape mismatch", which);
     CU(h, cudaSetDevice(h->dev));
-    const bool shard = which == CTR_TABLE_ITEM_EMB && h->comm.world > 1 && !h->comm.replicate;
+    const bool shard = h->tab_sharded[which];
     if (!shard) {
         CU(h, cudaMemcpy2DAsync(rows, (size_t)width * sizeof(float), h->tab[which], h->tab_ld[which] * sizeof(float), (size_t)width * sizeof(float), (size_t)nrows, cudaMemcpyDeviceToHost, h->stream));
     } else if (h->tab_local_rows[which] > 0) {   // fills only this rank's rows (row % world == rank)
@@ -1052,17 +1181,25 @@ int train_opts(ctr_handle* h, const float* d_label, int B, StepOpts* out) {
     *out = o;
     return CTR_OK;
 }
+
+bool emb_sharded(const ctr_handle* h) { return h->comm.world > 1 && h->tab_sharded[CTR_TABLE_ITEM_EMB]; }
+
+// one train step on device-resident ids; rows >= nvalid are the zero-padded tail trained as label 0 (model.go:357-371)
+int train_step_dev(ctr_handle* h, const int32_t* d_user, const int32_t* d_item, const int32_t* d_hist, const float* d_label, int B, int nvalid) {
+    if (emb_sharded(h)) return comm_train_step(h, d_user, d_item, d_hist, d_label, B, nvalid);
+    RET(check_tables(h));
+    RowSrc r = idx_src(h, d_user, d_item, d_hist, B);
+    r.nvalid = nvalid;
+    StepOpts o;
+    RET(train_opts(h, d_label, B, &o));
+    return step_core(h, r, B, o);
+}
 }  // namespace
 
 int ctr_train_step_idx_dev(ctr_handle* h, const int32_t* d_user, const int32_t* d_item, const int32_t* d_hist, const float* d_label, int32_t B) {
     if (!h || !d_user || !d_item || !d_hist || !d_label) return set_err(h, CTR_EINVAL, "null argument");
     if (B != h->cfg.batch) return set_err(h, CTR_EINVAL, "B=%d != configured batch %d", B, h->cfg.batch);
-    if (h->comm.world > 1 && !h->comm.replicate) return comm_train_step(h, d_user, d_item, d_hist, d_label, B);
-    RET(check_tables(h));
-    RowSrc r = idx_src(h, d_user, d_item, d_hist, B);
-    StepOpts o;
-    RET(train_opts(h, d_label, B, &o));
-    return step_core(h, r, B, o);
+    return train_step_dev(h, d_user, d_item, d_hist, d_label, B, B);
 }
 
 int ctr_train_step_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row, const int32_t* hist, const float* label, int32_t B, ctr_step_stats* stats) {
@@ -1079,41 +1216,62 @@ int ctr_train_step_idx(ctr_handle* h, const int32_t* user_row, const int32_t* it
     return CTR_OK;
 }
 
+namespace {
+// lazily creates the pinned ring, the two device slots and the copy stream; slot size fits one idx batch
+int feed_init(ctr_handle* h) {
+    if (h->copy_stream) return CTR_OK;
+    const size_t B = (size_t)h->Bmax;
+    h->feed_bytes = (B * (size_t)(h->cfg.S + 3) * 4 + 255) & ~(size_t)255;      // [user | item | hist | label] — also fits [uid | iid | ts | label] chunks
+    h->feed_bytes = std::max(h->feed_bytes, (size_t)B * 28 + 256);
+    CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CU(h, cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)); CU(h, cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
+        CU(h, cudaMalloc(&h->feed_dev[i], h->feed_bytes));
+    }
+    for (int i = 0; i < ctr_handle::kPin; i++) {
+        CU(h, cudaHostAlloc(&h->feed_pin[i], h->feed_bytes, cudaHostAllocDefault));
+        CU(h, cudaEventCreateWithFlags(&h->pin_free[i], cudaEventDisableTiming));
+    }
+    h->pool = new CopyPool(3);
+    return CTR_OK;
+}
+int costs_reserve(ctr_handle* h, size_t nb) {
+    if (h->d_costs_cap >= nb) return CTR_OK;
+    if (h->d_costs) cudaFree(h->d_costs);
+    h->d_costs = nullptr; RET(dalloc(h, &h->d_costs, nb)); h->d_costs_cap = nb;
+    return CTR_OK;
+}
+}  // namespace
+
 int ctr_train_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row, const int32_t* hist, const float* label,
                   int64_t n, float* costs) {
     if (!h || !user_row || !item_row || !hist || !label || n < 1) return set_err(h, CTR_EINVAL, "bad train arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     CU(h, cudaSetDevice(h->dev));
-    if (h->comm.world > 1 && !h->comm.replicate) return set_err(h, CTR_ESTATE, "ctr_train_idx: sharded tables use ctr_train_step_idx per batch");
-    RET(check_tables(h));
+    if (!emb_sharded(h)) RET(check_tables(h));
     const int B = h->cfg.batch, S = h->cfg.S;
     const int64_t nb = (n + B - 1) / B;                      // model.go:96-99
-    if (!h->copy_stream) {
-        CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) { CU(h, cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)); CU(h, cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming)); }
-        RET(dalloc(h, &h->p_user, (size_t)h->Bmax)); RET(dalloc(h, &h->p_item, (size_t)h->Bmax));
-        RET(dalloc(h, &h->p_hist, (size_t)h->Bmax * S)); RET(dalloc(h, &h->p_label, (size_t)h->Bmax));
-    }
-    if (h->d_costs_cap < (size_t)nb) { if (h->d_costs) cudaFree(h->d_costs); h->d_costs = nullptr; RET(dalloc(h, &h->d_costs, (size_t)nb)); h->d_costs_cap = (size_t)nb; }
-    int* su[2] = {h->s_user, h->p_user}; int* si[2] = {h->s_item, h->p_item}; int* sh[2] = {h->s_hist, h->p_hist}; float* sl[2] = {h->s_label, h->p_label};
-    CU(h, cudaStreamSynchronize(h->stream));                 // staging set 0 may still be in use by an earlier call
+    RET(feed_init(h));
+    RET(costs_reserve(h, (size_t)nb));
+    const size_t o_item = (size_t)B * 4, o_hist = (size_t)B * 8, o_label = (size_t)B * (S + 2) * 4;
+    CU(h, cudaStreamSynchronize(h->stream));                 // a device slot may still be in use by an earlier call
     for (int64_t b = 0; b < nb; b++) {
-        const int slot = (int)(b & 1);
-        const int64_t start = b * B; const int nv = (int)std::min<int64_t>(B, n - start);
-        // H2D of batch b on the copy stream, after the compute that last used this slot (batch b-2)
+        const int slot = (int)(b & 1), ps = (int)(b % ctr_handle::kPin);
+        const int64_t start = b * B; const size_t nv = (size_t)std::min<int64_t>(B, n - start);
+        // caller memory → pinned slot (host threads; overlaps the GPU work already queued), then one DMA
+        if (b >= ctr_handle::kPin) CU(h, cudaEventSynchronize(h->pin_free[ps]));
+        unsigned char* pin = h->feed_pin[ps];
+        memcpy(pin, user_row + start, nv * 4); memcpy(pin + o_item, item_row + start, nv * 4); memcpy(pin + o_label, label + start, nv * 4);
+        h->pool->copy(pin + o_hist, hist + start * S, nv * S * 4);
+        // H2D of batch b on the copy stream, after the compute that last used this device slot (batch b-2)
         if (b >= 2) CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
-        CU(h, cudaMemcpyAsync(su[slot], user_row + start, sizeof(int) * (size_t)nv, cudaMemcpyHostToDevice, h->copy_stream));
-        CU(h, cudaMemcpyAsync(si[slot], item_row + start, sizeof(int) * (size_t)nv, cudaMemcpyHostToDevice, h->copy_stream));
-        CU(h, cudaMemcpyAsync(sh[slot], hist + start * S, sizeof(int) * (size_t)nv * S, cudaMemcpyHostToDevice, h->copy_stream));
-        CU(h, cudaMemcpyAsync(sl[slot], label + start, sizeof(float) * (size_t)nv, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(h, cudaMemcpyAsync(h->feed_dev[slot], pin, o_label + (size_t)B * 4, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(h, cudaEventRecord(h->pin_free[ps], h->copy_stream));
         CU(h, cudaEventRecord(h->ev_copied[slot], h->copy_stream));
-        // compute of batch b on the engine stream (overlaps the H2D of batch b+1)
+        // compute of batch b on the engine stream (overlaps the staging + H2D of batch b+1)
         CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
-        RowSrc r = idx_src(h, su[slot], si[slot], sh[slot], B);
-        r.nvalid = nv;                                       // ragged tail → zero rows with label 0 (model.go:357-371)
-        StepOpts o;
-        RET(train_opts(h, sl[slot], B, &o));
-        RET(step_core(h, r, B, o));
+        unsigned char* d = h->feed_dev[slot];
+        RET(train_step_dev(h, (const int*)d, (const int*)(d + o_item), (const int*)(d + o_hist), (const float*)(d + o_label), B, (int)nv));   // ragged tail → zero rows with label 0 (model.go:357-371)
         CU(h, cudaMemcpyAsync(h->d_costs + b, h->d_cost, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         CU(h, cudaEventRecord(h->ev_consumed[slot], h->stream));
     }
@@ -1121,13 +1279,106 @@ int ctr_train_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_ro
     CU(h, cudaMemcpyAsync(hc.data(), h->d_costs, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaStreamSynchronize(h->copy_stream));
+    if (h->comm.h_err && *h->comm.h_err) return set_err(h, CTR_ECOMM, "peer barrier timed out waiting for rank %d", *h->comm.h_err - 1);
     if (costs) for (int64_t b = 0; b < nb; b++) costs[b] = -(float)(hc[(size_t)b] / ((double)B * h->comm.world));   // d_cost is summed over the ranks
+    return CTR_OK;
+}
+
+// recommend.Train (rcmd.go:197-246) fed by sample keys: GetSample's assembly (rcmd.go:339-460) happens on the device —
+// id maps resolve {UserId, ItemId}, samples whose user or item has no features are DROPPED as the reference's
+// assembler skips them (rcmd.go:378-382), the survivors stay resident in HBM in input order, and every batch's
+// history rows come from the device ubcache at the sample's timestamp (GetUserBehavior(uid, S, -1, ts),
+// rcmd.go:509; prepare.go:13-38) right before its step — then model.Train's epoch loop (model.go:96-209).
+int ctr_train_keys(ctr_handle* h, const int64_t* user_ids, const int64_t* item_ids, const int64_t* ts, const float* label, int64_t n,
+                   int32_t epochs, int32_t early_stop, float* last_cost, int32_t* epochs_run, int64_t* rows_used) {
+    if (!h || !user_ids || !item_ids || !ts || !label || n < 1 || epochs < 0) return set_err(h, CTR_EINVAL, "bad train arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(h, cudaSetDevice(h->dev));
+    if (!h->idm_keys[0] || !h->idm_keys[1]) return set_err(h, CTR_ESTATE, "ctr_train_keys needs both id maps (ctr_idmap_build)");
+    if (!emb_sharded(h)) RET(check_tables(h));
+    const int B = h->cfg.batch, S = h->cfg.S;
+    RET(feed_init(h));
+    // ---- resident sample arrays (+B slack so a padded tail never indexes past the end)
+    const size_t cap = (size_t)n + (size_t)B;
+    if (h->kt_cap < cap) {
+        for (void* p : {(void*)h->kt_user, (void*)h->kt_item, (void*)h->kt_ts, (void*)h->kt_label}) if (p) cudaFree(p);
+        h->kt_user = h->kt_item = nullptr; h->kt_ts = nullptr; h->kt_label = nullptr; h->kt_cap = 0;
+        RET(dalloc(h, &h->kt_user, cap)); RET(dalloc(h, &h->kt_item, cap)); RET(dalloc(h, &h->kt_ts, cap)); RET(dalloc(h, &h->kt_label, cap));
+        h->kt_cap = cap;
+    }
+    const size_t chunk = std::min<size_t>((size_t)n, h->feed_bytes / 28);       // keys per staging slot
+    if (h->kt_chunk < chunk) {
+        for (void* p : {(void*)h->kt_flag, (void*)h->kt_pos, h->kt_scan_tmp}) if (p) cudaFree(p);
+        h->kt_flag = h->kt_pos = nullptr; h->kt_scan_tmp = nullptr;
+        RET(dalloc(h, &h->kt_flag, chunk + 1)); RET(dalloc(h, &h->kt_pos, chunk + 1));
+        cub::DeviceScan::ExclusiveSum(nullptr, h->kt_scan_bytes, h->kt_flag, h->kt_pos, (int)(chunk + 1), h->stream);
+        CU(h, cudaMalloc(&h->kt_scan_tmp, h->kt_scan_bytes));
+        h->kt_chunk = chunk;
+    }
+    if (!h->kt_count) RET(dalloc(h, &h->kt_count, 1));
+    CU(h, cudaMemsetAsync(h->kt_count, 0, sizeof(unsigned long long), h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    // ---- keys → (user row, item row, ts, label), unresolvable samples dropped, order kept
+    int64_t nchunks = ((int64_t)n + (int64_t)chunk - 1) / (int64_t)chunk;
+    for (int64_t c = 0; c < nchunks; c++) {
+        const int slot = (int)(c & 1), ps = (int)(c % ctr_handle::kPin);
+        const int64_t start = c * (int64_t)chunk; const size_t m = (size_t)std::min<int64_t>((int64_t)chunk, n - start);
+        if (c >= ctr_handle::kPin) CU(h, cudaEventSynchronize(h->pin_free[ps]));
+        unsigned char* pin = h->feed_pin[ps];
+        h->pool->copy(pin, user_ids + start, m * 8); h->pool->copy(pin + m * 8, item_ids + start, m * 8);
+        h->pool->copy(pin + m * 16, ts + start, m * 8); h->pool->copy(pin + m * 24, label + start, m * 4);
+        if (c >= 2) CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
+        CU(h, cudaMemcpyAsync(h->feed_dev[slot], pin, m * 28, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(h, cudaEventRecord(h->pin_free[ps], h->copy_stream));
+        CU(h, cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
+        const long long* dk = (const long long*)h->feed_dev[slot];
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((m + 255) / 256, (size_t)h->num_sms * 8));
+        RET(launch(h, "keys_rows", [&] {
+            k_keys_rows<<<grid, 256, 0, h->stream>>>(h->idm_keys[0], h->idm_vals[0], h->idm_cap[0] - 1, h->idm_keys[1], h->idm_vals[1], h->idm_cap[1] - 1,
+                                                    dk, dk + m, (long)m, h->kt_flag);
+        }));
+        RET(launch(h, "cub_exclusive_scan", [&] { cub::DeviceScan::ExclusiveSum(h->kt_scan_tmp, h->kt_scan_bytes, h->kt_flag, h->kt_pos, (int)(m + 1), h->stream); }));
+        RET(launch(h, "keys_compact", [&] {
+            k_keys_compact<<<grid, 256, 0, h->stream>>>(h->idm_keys[0], h->idm_vals[0], h->idm_cap[0] - 1, h->idm_keys[1], h->idm_vals[1], h->idm_cap[1] - 1,
+                                                       dk, dk + m, dk + 2 * m, (const float*)(dk + 3 * m), (long)m, h->kt_flag, h->kt_pos, h->kt_count,
+                                                       h->kt_user, h->kt_item, h->kt_ts, h->kt_label);
+        }));
+        RET(launch(h, "keys_advance", [&] { k_keys_advance<<<1, 1, 0, h->stream>>>(h->kt_pos + m, h->kt_count); }));
+        CU(h, cudaEventRecord(h->ev_consumed[slot], h->stream));
+    }
+    unsigned long long used = 0;
+    CU(h, cudaMemcpyAsync(&used, h->kt_count, sizeof used, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (rows_used) *rows_used = (int64_t)used;
+    // ---- model.Train's loop over the resident samples.  world > 1: every step is collective, so all ranks run the
+    // batch count of the rank with the most samples (ranks that ran out train on all-padding batches)
+    int64_t nmax = (int64_t)used;
+    if (h->comm.world > 1) RET(comm_max_i64(h, &nmax));
+    if (nmax == 0) return set_err(h, CTR_ENOTFOUND, "no sample resolved: every key has an unknown user or item");
+    const int64_t batches = nmax / B + (nmax % B != 0);     // model.go:96-99
+    float best = INFINITY, cost = 0.0f; int no_improve = 0, ep = 0;
+    for (ep = 0; ep < epochs; ep++) {
+        for (int64_t b = 0; b < batches; b++) {
+            const int64_t start = std::min<int64_t>(b * B, (int64_t)used);
+            const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(B, (int64_t)used - start));
+            if (h->ub_off && nv > 0) RET(ctr_ubcache_window_dev(h, h->kt_user + start, (const int64_t*)(h->kt_ts + start), nv, h->s_hist));
+            else if (nv > 0) CU(h, cudaMemsetAsync(h->s_hist, 0xff, sizeof(int) * (size_t)nv * S, h->stream));   // no UserBehavior provider → empty history (rcmd.go:498,509)
+            RET(train_step_dev(h, h->kt_user + start, h->kt_item + start, h->s_hist, h->kt_label + start, B, nv));
+        }
+        RET(read_cost(h, B * h->comm.world, &cost));       // cost of the epoch's last batch, model.go:198
+        if (cost < best) { best = cost; no_improve = 0; } else no_improve++;
+        if (early_stop != 0 && no_improve >= early_stop) { ep++; break; }   // model.go:206-209
+    }
+    if (last_cost) *last_cost = cost;
+    if (epochs_run) *epochs_run = ep;
     return CTR_OK;
 }
 
 int ctr_predict_idx_dev(ctr_handle* h, const int32_t* d_user, const int32_t* d_item, const int32_t* d_hist, int32_t B, float* d_out) {
     if (!h || !d_user || !d_item || !d_hist) return set_err(h, CTR_EINVAL, "null argument");
-    if (h->comm.world > 1 && !h->comm.replicate) return comm_predict(h, d_user, d_item, d_hist, B, d_out);
+    if (B < 1 || B > h->Bmax) return set_err(h, CTR_EINVAL, "batch %d outside (0, %d]", B, h->Bmax);
+    if (emb_sharded(h)) return comm_predict(h, d_user, d_item, d_hist, B, d_out);
     RET(check_tables(h));
     RowSrc r = idx_src(h, d_user, d_item, d_hist, B);
     StepOpts o;
@@ -1161,6 +1412,7 @@ int ctr_sync(ctr_handle* h) {
     if (!h) return CTR_EINVAL;
     CU(h, cudaSetDevice(h->dev));
     CU(h, cudaStreamSynchronize(h->stream));
+    if (h->comm.h_err && *h->comm.h_err) return set_err(h, CTR_ECOMM, "peer barrier timed out waiting for rank %d (a rank left the step loop?)", *h->comm.h_err - 1);
     return CTR_OK;
 }
 
@@ -1201,6 +1453,7 @@ int ctr_debug_grads_idx(ctr_handle* h, const int32_t* user_row, const int32_t* i
     CU(h, cudaSetDevice(h->dev));
     RET(check_tables(h));
     const ctr_config& c = h->cfg;
+    if (B < 1 || B > h->Bmax) return set_err(h, CTR_EINVAL, "batch %d outside (0, %d]", B, h->Bmax);
     RET(stage_idx(h, user_row, item_row, hist, label, B));
     RET(zero_grads(h));
     RowSrc r = idx_src(h, h->s_user, h->s_item, h->s_hist, B);
@@ -1375,6 +1628,7 @@ struct CkptHeader {
     int64_t tab_rows[3], tab_local_rows[3];
     int32_t tab_width[3];
     int32_t replicated;            // ITEM_EMB placement under world > 1 (1 = every rank holds the whole table)
+    int32_t has_moments;           // ITEM_EMB Adam moments follow the tables (CTR_TABLE_ADAM)
 };
 constexpr size_t kCkptChunk = 32u << 20;
 
@@ -1421,8 +1675,9 @@ int ctr_checkpoint_save(ctr_handle* h, const char* path) {
     const ctr_config& c = h->cfg;
     CkptHeader hd{};
     memcpy(hd.magic, "CTRB200", 8);
-    hd.version = 1; hd.model = c.model; hd.uP = c.uP; hd.S = c.S; hd.D = c.D; hd.cF = c.cF; hd.H0 = c.H0; hd.H1 = c.H1;
+    hd.version = 2; hd.model = c.model; hd.uP = c.uP; hd.S = c.S; hd.D = c.D; hd.cF = c.cF; hd.H0 = c.H0; hd.H1 = c.H1;
     hd.rank = h->comm.rank; hd.world = h->comm.world; hd.step = h->step; hd.replicated = h->comm.replicate ? 1 : 0;
+    hd.has_moments = (h->emb_m && h->tab[CTR_TABLE_ITEM_EMB]) ? 1 : 0;
     for (int t = 0; t < 3; t++) { hd.has_table[t] = h->tab[t] != nullptr; hd.tab_rows[t] = h->tab_rows[t]; hd.tab_local_rows[t] = h->tab_local_rows[t]; hd.tab_width[t] = h->tab_width[t]; }
     int rc = fwrite(&hd, sizeof hd, 1, f) == 1 ? CTR_OK : set_err(h, CTR_EIO, "checkpoint: short write");
     for (int i = 0; i < 4 && rc == CTR_OK; i++) {
@@ -1431,6 +1686,9 @@ int ctr_checkpoint_save(ctr_handle* h, const char* path) {
     }
     for (int t = 0; t < 3 && rc == CTR_OK; t++)
         if (h->tab[t]) rc = ckpt_write_2d(h, f, h->tab[t], h->tab_ld[t], h->tab_local_rows[t], h->tab_width[t], bounce);
+    if (hd.has_moments)
+        for (float* src : {h->emb_m, h->emb_v})
+            if (rc == CTR_OK) rc = ckpt_write_2d(h, f, src, h->tab_ld[CTR_TABLE_ITEM_EMB], h->tab_local_rows[CTR_TABLE_ITEM_EMB], h->tab_width[CTR_TABLE_ITEM_EMB], bounce);
     cudaFreeHost(bounce);
     if (fclose(f) != 0 && rc == CTR_OK) rc = set_err(h, CTR_EIO, "checkpoint: close failed");
     return rc;
@@ -1445,7 +1703,7 @@ int ctr_checkpoint_load(ctr_handle* h, const char* path) {
     CkptHeader hd{};
     const ctr_config& c = h->cfg;
     int rc = CTR_OK;
-    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "CTRB200", 8) != 0 || hd.version != 1) rc = set_err(h, CTR_EIO, "checkpoint: %s is not a version-1 ctr-b200 snapshot", path);
+    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "CTRB200", 8) != 0 || hd.version != 2) rc = set_err(h, CTR_EIO, "checkpoint: %s is not a version-2 ctr-b200 snapshot", path);
     else if (hd.model != c.model || hd.uP != c.uP || hd.S != c.S || hd.D != c.D || hd.cF != c.cF || hd.H0 != c.H0 || hd.H1 != c.H1)
         rc = set_err(h, CTR_EINVAL, "checkpoint: model dims differ from this handle");
     else if (hd.rank != h->comm.rank || hd.world != h->comm.world) rc = set_err(h, CTR_EINVAL, "checkpoint: written by rank %d/%d, this handle is %d/%d", hd.rank, hd.world, h->comm.rank, h->comm.world);
@@ -1459,16 +1717,23 @@ int ctr_checkpoint_load(ctr_handle* h, const char* path) {
         if (!hd.has_table[t]) continue;
         const int want = t == CTR_TABLE_USER_FEAT ? c.uP : t == CTR_TABLE_ITEM_FEAT ? c.cF : c.D;
         if (hd.tab_width[t] != want || hd.tab_rows[t] < 1 || hd.tab_local_rows[t] < 0) { rc = set_err(h, CTR_EIO, "checkpoint: bad table %d header", t); break; }
-        if (h->tab[t]) { cudaFree(h->tab[t]); h->tab[t] = nullptr; }
         const long ld = round_up(hd.tab_width[t], 4);
         const size_t bytes = (size_t)std::max<int64_t>(hd.tab_local_rows[t], 1) * ld * sizeof(float);
-        if (cudaMalloc(&h->tab[t], bytes) != cudaSuccess) { cudaGetLastError(); rc = set_err(h, CTR_ENOMEM, "checkpoint: table %d (%zu bytes)", t, bytes); break; }
-        cudaMemsetAsync(h->tab[t], 0, bytes, h->stream);
+        // placement travels with the snapshot: a shard holds fewer rows than the logical table
+        h->tab_sharded[t] = h->comm.world > 1 && t != CTR_TABLE_USER_FEAT && (t == CTR_TABLE_ITEM_EMB ? hd.replicated != 1 : hd.tab_local_rows[t] != hd.tab_rows[t]);
+        rc = table_mem(h, t, h->tab_sharded[t], bytes);
+        if (rc != CTR_OK) break;
         h->tab_ld[t] = ld; h->tab_rows[t] = hd.tab_rows[t]; h->tab_local_rows[t] = hd.tab_local_rows[t]; h->tab_width[t] = hd.tab_width[t];
-        // placement travels with the snapshot
         if (t == CTR_TABLE_ITEM_EMB) h->comm.replicate = h->comm.world > 1 && hd.replicated == 1;
+        if (t != CTR_TABLE_USER_FEAT) h->tab_gen++;
         rc = ckpt_read_2d(h, f, h->tab[t], ld, hd.tab_local_rows[t], hd.tab_width[t], bounce);
         if (t == CTR_TABLE_ITEM_EMB && h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; h->hot_rows = 0; }
+    }
+    for (float** p : {&h->emb_m, &h->emb_v}) if (*p) { cudaFree(*p); *p = nullptr; }
+    if (rc == CTR_OK && hd.has_moments) {
+        rc = ensure_moments(h);
+        for (float* dst : {h->emb_m, h->emb_v})
+            if (rc == CTR_OK) rc = ckpt_read_2d(h, f, dst, h->tab_ld[CTR_TABLE_ITEM_EMB], h->tab_local_rows[CTR_TABLE_ITEM_EMB], h->tab_width[CTR_TABLE_ITEM_EMB], bounce);
     }
     if (bounce) cudaFreeHost(bounce);
     fclose(f);
@@ -1477,7 +1742,7 @@ int ctr_checkpoint_load(ctr_handle* h, const char* path) {
 }
 
 int ctr_roc_auc(ctr_handle* h, const float* pred, const float* y, int64_t n, double* auc) {
-    if (!h || !pred || !y || !auc || n < 1) return set_err(h, CTR_EINVAL, "bad auc arguments");
+    if (!h || !pred || !y || !auc || n < 1 || n > 0x7fffffff) return set_err(h, CTR_EINVAL, "bad auc arguments (n must be in [1, 2^31))");
     std::lock_guard<std::mutex> lk(h->mu);
     CU(h, cudaSetDevice(h->dev));
     { cudaError_t e = auc_run(h->stream, pred, y, (long)n, auc); if (e != cudaSuccess) return set_err(h, CTR_ECUDA, "auc: %s", cudaGetErrorString(e)); return CTR_OK; }

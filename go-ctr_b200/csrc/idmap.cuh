@@ -108,4 +108,34 @@ k_keys_resolve(const unsigned long long* __restrict__ ukeys, const int* __restri
     }
 }
 
+// ---- recommend.GetSample's assembly for training (rcmd.go:339-460), on the device -----------------------------
+// A sample whose user or item has no features is skipped by the reference's assembler goroutines
+// (rcmd.go:378-382: `continue` on GetSampleVector's error); here: flag → exclusive scan → ordered compaction.
+__global__ void __launch_bounds__(256)
+k_keys_rows(const unsigned long long* __restrict__ ukeys, const int* __restrict__ uvals, unsigned long long umask,
+            const unsigned long long* __restrict__ ikeys, const int* __restrict__ ivals, unsigned long long imask,
+            const long long* __restrict__ uid, const long long* __restrict__ iid, long n, int* __restrict__ flag) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        flag[i] = (idmap_find(ukeys, uvals, umask, (unsigned long long)uid[i]) >= 0 &&
+                   idmap_find(ikeys, ivals, imask, (unsigned long long)iid[i]) >= 0) ? 1 : 0;
+}
+// survivors are appended after the *count samples of the earlier chunks, input order kept
+__global__ void __launch_bounds__(256)
+k_keys_compact(const unsigned long long* __restrict__ ukeys, const int* __restrict__ uvals, unsigned long long umask,
+               const unsigned long long* __restrict__ ikeys, const int* __restrict__ ivals, unsigned long long imask,
+               const long long* __restrict__ uid, const long long* __restrict__ iid, const long long* __restrict__ ts,
+               const float* __restrict__ label, long n, const int* __restrict__ flag, const int* __restrict__ pos,
+               const unsigned long long* __restrict__ count, int* __restrict__ out_user, int* __restrict__ out_item,
+               long long* __restrict__ out_ts, float* __restrict__ out_label) {
+    const unsigned long long base = *count;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        if (!flag[i]) continue;
+        const unsigned long long o = base + (unsigned long long)pos[i];
+        out_user[o] = idmap_find(ukeys, uvals, umask, (unsigned long long)uid[i]);
+        out_item[o] = idmap_find(ikeys, ivals, imask, (unsigned long long)iid[i]);
+        out_ts[o] = ts[i]; out_label[o] = label[i];
+    }
+}
+__global__ void k_keys_advance(const int* __restrict__ chunk_total, unsigned long long* __restrict__ count) { *count += (unsigned long long)*chunk_total; }
+
 }  // namespace ctr

@@ -11,11 +11,11 @@ from . import build as _build
 
 __all__ = ["Engine", "Config", "StepStats", "CtrError", "load_library", "MODEL_YOUTUBE", "MODEL_DIN_COS",
            "MODEL_DIN_EUC", "TABLE_USER_FEAT", "TABLE_ITEM_FEAT", "TABLE_ITEM_EMB", "TABLE_FROZEN", "TABLE_SGD",
-           "TABLE_SGD_DETERMINISTIC", "GEMM_AUTO", "GEMM_FP32", "GEMM_TCGEN05_3XTF32", "EXPORTS", "IDMAP_USER", "IDMAP_ITEM", "ENOTFOUND"]
+           "TABLE_SGD_DETERMINISTIC", "TABLE_ADAM", "GEMM_AUTO", "GEMM_FP32", "GEMM_TCGEN05_3XTF32", "EXPORTS", "IDMAP_USER", "IDMAP_ITEM", "ENOTFOUND"]
 
 MODEL_YOUTUBE, MODEL_DIN_COS, MODEL_DIN_EUC = 0, 1, 2
 TABLE_USER_FEAT, TABLE_ITEM_FEAT, TABLE_ITEM_EMB = 0, 1, 2
-TABLE_FROZEN, TABLE_SGD, TABLE_SGD_DETERMINISTIC = 0, 1, 2
+TABLE_FROZEN, TABLE_SGD, TABLE_SGD_DETERMINISTIC, TABLE_ADAM = 0, 1, 2, 3
 GEMM_AUTO, GEMM_FP32, GEMM_TCGEN05_3XTF32 = 0, 1, 2
 IDMAP_USER, IDMAP_ITEM = 0, 1
 ENOTFOUND = 7
@@ -23,7 +23,7 @@ ENOTFOUND = 7
 # every symbol include/ctr_b200.h declares (tests check the .so exports all of them)
 EXPORTS = ["ctr_abi_version", "ctr_config_default", "ctr_create", "ctr_destroy", "ctr_last_error",
            "ctr_init_weights", "ctr_set_weights", "ctr_get_weights", "ctr_table_upload", "ctr_table_download", "ctr_table_fill",
-           "ctr_gather_rows", "ctr_train_dense", "ctr_predict_dense", "ctr_train_step_idx", "ctr_train_idx", "ctr_predict_idx",
+           "ctr_gather_rows", "ctr_train_dense", "ctr_predict_dense", "ctr_train_step_idx", "ctr_train_idx", "ctr_train_keys", "ctr_predict_idx",
            "ctr_train_step_idx_dev", "ctr_predict_idx_dev", "ctr_last_cost", "ctr_sync", "ctr_get_stream",
            "ctr_set_stream", "ctr_launch_count", "ctr_profile_enable", "ctr_profile_get", "ctr_profile_reset",
            "ctr_profile_dump", "ctr_debug_grads_idx", "ctr_ubcache_upload", "ctr_ubcache_window", "ctr_ubcache_window_dev", "ctr_idmap_build", "ctr_idmap_lookup", "ctr_idmap_lookup_dev",
@@ -213,6 +213,16 @@ class Engine:
         """Raw host pointers (pinned buffers owned by the caller)."""
         self._ck(self.L.ctr_train_idx(self.h, C.c_void_p(up), C.c_void_p(ip), C.c_void_p(hp), C.c_void_p(yp), C.c_int64(n),
                                       C.c_void_p(costs_ptr) if costs_ptr else None))
+
+    def train_keys(self, user_ids, item_ids, ts, label, epochs=1, early_stop=0):
+        """recommend.Train over sample keys (rcmd.go:197-246); returns (epochs_run, last_cost, rows_used)."""
+        u = np.ascontiguousarray(user_ids, np.int64); i = np.ascontiguousarray(item_ids, np.int64); t = np.ascontiguousarray(ts, np.int64)
+        y, yp = _f(label)
+        assert u.size == i.size == t.size == y.size
+        cost = C.c_float(0); ep = C.c_int32(0); used = C.c_int64(0)
+        self._ck(self.L.ctr_train_keys(self.h, u.ctypes.data_as(_lp), i.ctypes.data_as(_lp), t.ctypes.data_as(_lp), yp, C.c_int64(u.size),
+                                       C.c_int32(epochs), C.c_int32(early_stop), C.byref(cost), C.byref(ep), C.byref(used)))
+        return ep.value, cost.value, used.value
 
     def predict_idx(self, user_row, item_row, hist):
         u, up = _i(user_row); it, ip = _i(item_row); hs, hp = _i(hist)

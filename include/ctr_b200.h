@@ -35,8 +35,11 @@ enum { CTR_TABLE_USER_FEAT = 0, CTR_TABLE_ITEM_FEAT = 1, CTR_TABLE_ITEM_EMB = 2 
  * learnables: din.go:161-169).  SGD fuses gradient scatter-add + update into the backward kernel
  * with red.global.add.v4.f32 (order-nondeterministic, Hogwild within a batch like the reference's
  * own item2vec trainer).  SGD_DETERMINISTIC sorts (row, sample, slot) keys and reduces each row's
- * segment in a fixed order — the parity-test mode. */
-enum { CTR_TABLE_FROZEN = 0, CTR_TABLE_SGD = 1, CTR_TABLE_SGD_DETERMINISTIC = 2 };
+ * segment in a fixed order — the parity-test mode.  ADAM applies the dense solver's update (model.go:88: Adam, step
+ * table_lr, cfg betas / eps, gradient divided by the batch size first, no L2) once per DISTINCT row of the batch with
+ * that row's summed gradient (sorted keys → segment reduction, deterministic); rows the batch did not touch keep their
+ * moments ("lazy" Adam).  Single GPU or replicated table; the moments are part of the checkpoint. */
+enum { CTR_TABLE_FROZEN = 0, CTR_TABLE_SGD = 1, CTR_TABLE_SGD_DETERMINISTIC = 2, CTR_TABLE_ADAM = 3 };
 
 /* dense-layer GEMM engine: exact fp32 FFMA, or tcgen05 3xTF32 (error-compensated, fp32 accumulate
  * in TMEM).  AUTO = tcgen05 when the shape qualifies. */
@@ -131,12 +134,24 @@ int ctr_train_step_idx(ctr_handle* h, const int32_t* user_row, const int32_t* it
                        const int32_t* hist_rows, const float* label, int32_t B, ctr_step_stats* stats);
 /* model.Train's batch loop for one pass over n samples (model.go:107-196) fed by row ids: batches of
  * cfg.batch are consumed in order, the ragged tail is zero-padded with label 0 (model.go:357-371), and
- * the host→device copy of batch i+1 overlaps the compute of batch i (second stream).  One coarse call
+ * the host→device copy of batch i+1 overlaps the compute of batch i: the caller's (pageable) buffers are copied into
+ * an internal pinned ring by a few host threads and DMA'd from there on a second stream.  One coarse call
  * per epoch is the shape a cgo caller wants.  costs (may be NULL) receives ceil(n/batch) batch costs.
- * With world > 1 (replicated ITEM_EMB) every step contains collectives: all ranks must call with the same n;
- * row-sharded tables use ctr_train_step_idx per batch. */
+ * With world > 1 every step is collective (both placements): all ranks must call with the same n. */
 int ctr_train_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row,
                   const int32_t* hist_rows, const float* label, int64_t n, float* costs);
+/* recommend.Train (rcmd.go:197-246) fed by sample keys {UserId, ItemId, Timestamp, Label} (rcmd.go:189-194) — the
+ * whole of GetSample (rcmd.go:339-460) runs on the device: the id maps (ctr_idmap_build) resolve the keys, samples
+ * whose user or item has no features are dropped as the reference's assembler skips them (rcmd.go:378-382), the
+ * survivors stay in HBM in input order, and each batch's history rows are windowed from the device ubcache at the
+ * sample's timestamp (GetUserBehavior(uid, S, -1, ts): rcmd.go:509, prepare.go:13-38; no ubcache uploaded → empty
+ * history) right before its step.  Then model.Train's loop: batches of cfg.batch, zero-padded tail with label 0,
+ * *last_cost = cost of the epoch's last batch, early_stop = no-improvement epochs (0 = off) (model.go:96-209).
+ * Host traffic: 28 bytes per sample, staged through an internal pinned ring (the caller's buffers may be pageable).
+ * *rows_used = samples that survived.  world > 1: collective — every rank passes its own keys; all ranks run the
+ * batch count of the rank with the most surviving samples. */
+int ctr_train_keys(ctr_handle* h, const int64_t* user_ids, const int64_t* item_ids, const int64_t* ts, const float* label,
+                   int64_t n, int32_t epochs, int32_t early_stop, float* last_cost, int32_t* epochs_run, int64_t* rows_used);
 /* recommend.BatchPredict → model.Predict (rcmd.go:277-337) fed by indices. out is [n]. */
 int ctr_predict_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_row,
                     const int32_t* hist_rows, int64_t n, float* out);

@@ -572,7 +572,8 @@ float orc_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_state* 
                          const float* user_feat, long ldu, const float* item_feat, long ldi,
                          float* item_emb, long lde, long n_items,
                          const int32_t* user_row, const int32_t* item_row, const int32_t* hist,
-                         const float* y, int B, float table_lr, float* p_out, int nthreads) {
+                         const float* y, int B, float table_lr, float* p_out, int nthreads,
+                         float* emb_m, float* emb_v) {
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #else
@@ -633,6 +634,18 @@ float orc_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_state* 
                     j++;
                 }
                 float* e = item_emb + (long)rp[i].row * lde;
+                if (emb_m) {
+                    /* engine extension CTR_TABLE_ADAM: the dense solver's update (model.go:88; orc_adam_step) on the
+                     * touched row with its summed gradient — g *= 1/B first, no L2, shared step counter t */
+                    float* mm = emb_m + (long)rp[i].row * lde; float* vv = emb_v + (long)rp[i].row * lde;
+                    const float c1 = (float)(1.0 - pow((double)s->b1, (double)st->t)), c2 = (float)(1.0 - pow((double)s->b2, (double)st->t));
+                    for (int k = 0; k < D; k++) {
+                        float g = (float)acc[k] * (B > 1 ? 1.0f / (float)B : 1.0f);
+                        mm[k] = s->b1 * mm[k] + (1.0f - s->b1) * g;
+                        vv[k] = s->b2 * vv[k] + (1.0f - s->b2) * g * g;
+                        e[k] -= table_lr * (mm[k] / c1) / (sqrtf(vv[k] / c2) + s->eps);
+                    }
+                } else
                 for (int k = 0; k < D; k++) e[k] = (float)((double)e[k] - (double)table_lr * acc[k]);
                 i = j;
             }

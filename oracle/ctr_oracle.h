@@ -112,12 +112,20 @@ typedef struct {
 } orc_adam_state;
 /* table_lr == 0 → frozen table (reference behaviour, din.go:161-169). Duplicated rows accumulate
  * in (b, slot) order in double, then row -= table_lr * grad. Returns cost. */
+/* the TIMED CPU arm (cpu_fast.c): same step, float32, blocked thread-parallel SGEMMs, Hogwild row update */
+float orc_fast_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_state* st,
+                              float* W0, float* W1, float* W2, float* att,
+                              const float* user_feat, long ldu, const float* item_feat, long ldi,
+                              float* item_emb, long lde, long n_items,
+                              const int32_t* user_row, const int32_t* item_row, const int32_t* hist,
+                              const float* y, int B, float table_lr, int nthreads);
 float orc_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_state* st,
                          float* W0, float* W1, float* W2, float* att,
                          const float* user_feat, long ldu, const float* item_feat, long ldi,
                          float* item_emb, long lde, long n_items,
                          const int32_t* user_row, const int32_t* item_row, const int32_t* hist,
-                         const float* y, int B, float table_lr, float* p_out, int nthreads);
+                         const float* y, int B, float table_lr, float* p_out, int nthreads,
+                         float* emb_m, float* emb_v /* non-NULL: lazy Adam on the touched rows instead of SGD */);
 
 #ifdef __cplusplus
 }

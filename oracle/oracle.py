@@ -16,7 +16,7 @@ YOUTUBE, DIN_COS, DIN_EUC = 0, 1, 2
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("ctr_oracle.c", "i2v_oracle.c", "ctr_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ctr_oracle.c", "i2v_oracle.c", "mlp64_oracle.c", "cpu_fast.c", "ctr_oracle.h", "Makefile")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in src)):
         return _SO
@@ -67,6 +67,7 @@ def lib():
         L.orc_ws_free.argtypes = [C.c_void_p]
         L.orc_backward.restype = C.c_float
         L.orc_train_step_idx.restype = C.c_float
+        L.orc_fast_train_step_idx.restype = C.c_float
         L.orc_hash_onehot32.argtypes = [C.c_char_p, C.c_int]
         L.orc_i2v_train.restype = C.c_long
         L.orc_i2v_sigmoid_lut.restype = C.c_double
@@ -285,17 +286,34 @@ class IdxTrainer:
         self._mv = [np.zeros_like(a) for a in self.W for _ in (0, 1)]
         self.st = AdamState(*[a.ctypes.data_as(_fp) for a in self._mv], 0)
 
-    def step(self, user_row, item_row, hist, y, table_lr=0.0, nthreads=0):
+    def step(self, user_row, item_row, hist, y, table_lr=0.0, nthreads=0, table_adam=False):
         ur, urp = _i(user_row); ir, irp = _i(item_row); hs, hsp = _i(hist); ya, yp = _f(y)
         B = hs.shape[0]; p = np.empty(B, np.float32)
+        if table_adam and not hasattr(self, "emb_m"):
+            self.emb_m = np.zeros_like(self.emb); self.emb_v = np.zeros_like(self.emb)
+        mp = self.emb_m.ctypes.data_as(_fp) if table_adam else None
+        vp = self.emb_v.ctypes.data_as(_fp) if table_adam else None
         cost = lib().orc_train_step_idx(
             C.byref(self.cfg), C.byref(self.solver), C.byref(self.st),
             *[a.ctypes.data_as(_fp) for a in self.W],
             self.uf.ctypes.data_as(_fp), C.c_long(self.uf.shape[1]),
             self.itf.ctypes.data_as(_fp), C.c_long(self.itf.shape[1]),
             self.emb.ctypes.data_as(_fp), C.c_long(self.emb.shape[1]), C.c_long(self.emb.shape[0]),
-            urp, irp, hsp, yp, C.c_int(B), C.c_float(table_lr), p.ctypes.data_as(_fp), C.c_int(nthreads))
+            urp, irp, hsp, yp, C.c_int(B), C.c_float(table_lr), p.ctypes.data_as(_fp), C.c_int(nthreads), mp, vp)
         return float(cost), p
+
+
+    def step_fast(self, user_row, item_row, hist, y, table_lr=0.0, nthreads=0):
+        """The timed CPU arm (oracle/cpu_fast.c): same step in float32 with blocked, thread-parallel SGEMMs."""
+        ur, urp = _i(user_row); ir, irp = _i(item_row); hs, hsp = _i(hist); ya, yp = _f(y)
+        cost = lib().orc_fast_train_step_idx(
+            C.byref(self.cfg), C.byref(self.solver), C.byref(self.st),
+            *[a.ctypes.data_as(_fp) for a in self.W],
+            self.uf.ctypes.data_as(_fp), C.c_long(self.uf.shape[1]),
+            self.itf.ctypes.data_as(_fp), C.c_long(self.itf.shape[1]),
+            self.emb.ctypes.data_as(_fp), C.c_long(self.emb.shape[1]), C.c_long(self.emb.shape[0]),
+            urp, irp, hsp, yp, C.c_int(hs.shape[0]), C.c_float(table_lr), C.c_int(nthreads))
+        return float(cost)
 
 
 # ---- item2vec (BASELINE config 5) -----------------------------------------------------------------
