@@ -25,19 +25,25 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
+    # BASELINE.json configs[3] — the north-star placement: DIN over a 100M-row item table (25.6 GB + 22.4 GB of item
+    # features), row-sharded row % N over the N GPUs of the box and gathered / updated over NVLink peer memory;
+    # N = 1 keeps the whole table on one GPU (HBM regime).  65536 samples per GPU and step (weak scaling).
+    "din_100m": dict(model="din", U=138493, I=100_000_000, D=64, S=50, uP=52, cF=53, B=65536, zipf=False,
+                     note="BASELINE.json configs[3]: DIN, 100M-row table (row-sharded row%N for N>1, NVLink peer gather / red.add), batch 65536 per GPU, S=50, uniform ids"),
     # BASELINE.json configs[1]: DIN on synthetic MovieLens-20M-shaped batches (138k users, 27k items, dim 64)
     "din_ml20m": dict(model="din", U=138493, I=27278, D=64, S=50, uP=52, cF=53, B=65536, zipf=True,
-                      note="BASELINE.json configs[1]; item table 7 MB is L2-resident (reported, not an HBM reading)"),
+                      note="BASELINE.json configs[1]; item table 7 MB is L2-resident (reported, not an HBM reading); replicated for N>1"),
     # BASELINE.json configs[2]: YouTube DNN, 10M-item table dim 64, batch 16384
     "youtube_10m": dict(model="youtube", U=138493, I=10_000_000, D=64, S=50, uP=52, cF=53, B=16384, zipf=False,
                         note="BASELINE.json configs[2]"),
-    # BASELINE.json configs[3] per-GPU shard: DIN, 100M rows / 8 GPUs = 12.5M rows (3.2 GB), batch 65536, S=50
-    # BASELINE.json configs[3] itself: 100M rows (25.6 GB) row-sharded over the GPUs, global batch 65536 at 8 GPUs
-    "din_100m": dict(model="din", U=138493, I=100_000_000, D=64, S=50, uP=52, cF=53, B=8192, zipf=False,
-                     note="BASELINE.json configs[3]: 100M-row table sharded row%world, 8192 samples per GPU (65536 global at 8 GPUs), uniform ids"),
     "din_100m_shard": dict(model="din", U=138493, I=12_500_000, D=64, S=50, uP=52, cF=53, B=65536, zipf=False,
-                           note="BASELINE.json configs[3], one GPU's 1/8 row shard; uniform indices (worst case for caches)"),
+                           note="one GPU's 1/8 row shard of configs[3] held locally; uniform indices"),
 }
+
+# NVLink 5 per GPU and direction: nominal, and what a random 256-byte-row gather / red.add.v4 reaches between two
+# processes' VMM mappings on this pool (tests/cuda/peer_probe.cu, profiles/r02/peer_probe.md)
+NVLINK_NOMINAL_GBS = 900.0
+NVLINK_PROBE_GBS = {"gather": 487.0, "red_add": 677.0}
 
 
 def load_peaks():
@@ -114,66 +120,88 @@ def algorithmic_bytes(w, hist, ir):
     return gather, scatter, rows
 
 
-def run_reference(args, w, wname):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference is Go
-    (gorgonia) and cannot be built here (no Go toolchain, deps not vendored), so this times the
-    C port of its semantics (oracle/) with all host threads on a bounded sample per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import oracle as orc
-    rng = np.random.default_rng(42)
-    Bc = args.cpu_batch
-    wc = dict(w); wc["I"] = min(w["I"], 2_000_000)            # the port allocates a dense f64 accumulator per step
-    model = orc.DIN_COS if w["model"] == "din" else orc.YOUTUBE
-    ocfg = orc.make_cfg(model, w["uP"], w["S"], w["D"], w["cF"], 200, 80, 0.005, 0.005)
-    uf = rng.random((wc["U"], w["uP"]), dtype=np.float32); itf = rng.random((wc["I"], w["cF"]), dtype=np.float32)
-    emb = (rng.standard_normal((wc["I"], w["D"]), dtype=np.float32) / np.sqrt(w["D"])).astype(np.float32)
-    tr = orc.IdxTrainer(ocfg, orc.default_solver(0), orc.init_weights(ocfg, 0), uf, itf, emb)
-    from tests.util import make_batch
-    batches = [make_batch(rng, wc["U"], wc["I"], Bc, w["S"], zipf=w["zipf"]) for _ in range(2)]
-    cores = os.cpu_count() or 1
-    for i in range(args.warmup):
-        tr.step(*batches[i % 2], table_lr=0.05, nthreads=cores)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        tr.step(*batches[i % 2], table_lr=0.05, nthreads=cores)
-    dt = time.perf_counter() - t0
-    v = Bc * args.steps / dt
-    line = {"impl": "reference", "metric": "ctr_train_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wname, "note": w["note"], "graph": w["model"], "users": w["U"], "items": w["I"], "D": w["D"], "S": w["S"],
-                       "uP": w["uP"], "cF": w["cF"], "per_gpu_batch": w["B"], "global_batch": w["B"] * args.gpus,
-                       "ids": "zipf(1.05)" if w["zipf"] else "uniform", "history_padding": "20% of samples have a -1 padded tail",
-                       "sample": "each step = %d samples of this workload on the host cores (bounded CPU sample; item table capped at %d rows)" % (Bc, wc["I"])},
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": "%d steps x %d samples, OpenMP %d threads, C port of go-ctr semantics (Go reference unbuildable here)" % (args.steps, Bc, cores)},
-            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+def config_of(args, w, wname, world):
+    """identical keys for both arms (the driver compares them)"""
+    return {"workload": wname, "note": w["note"], "graph": w["model"], "users": w["U"], "items": w["I"], "D": w["D"], "S": w["S"],
+            "uP": w["uP"], "cF": w["cF"], "per_gpu_batch": w["B"], "global_batch": w["B"] * world,
+            "ids": "zipf(1.05)" if w["zipf"] else "uniform", "history_padding": "20% of samples have a -1 padded tail",
+            "l2": "GPU arm: a 256 MiB buffer is written before every timed step (outside the event pair), per-step event pairs are summed; "
+                  "CPU arm: host caches as they are"}
 
 
-def cpu_baseline(w, seconds=12.0, Bc=16384):
+def cpu_arm(w, seconds, Bc, threads, seed=43):
+    """The reference's CPU path for this workload on the host cores: oracle/cpu_fast.c (float32, blocked thread-parallel
+    SGEMMs like gonum's under gorgonia, Hogwild row update) stepping Bc-sample batches for ~`seconds`.  The item table is
+    capped at 2M rows (512 MB) so the arm fits any host; ids are drawn in that range."""
     from oracle import oracle as orc
     from tests.util import make_batch
-    rng = np.random.default_rng(43)
-    I = min(w["I"], 1_000_000)
+    rng = np.random.default_rng(seed)
+    I = min(w["I"], 2_000_000)
     model = orc.DIN_COS if w["model"] == "din" else orc.YOUTUBE
     ocfg = orc.make_cfg(model, w["uP"], w["S"], w["D"], w["cF"], 200, 80, 0.005, 0.005)
     uf = rng.random((w["U"], w["uP"]), dtype=np.float32); itf = rng.random((I, w["cF"]), dtype=np.float32)
     emb = (rng.standard_normal((I, w["D"]), dtype=np.float32) / np.sqrt(w["D"])).astype(np.float32)
     tr = orc.IdxTrainer(ocfg, orc.default_solver(0), orc.init_weights(ocfg, 0), uf, itf, emb)
-    batch = make_batch(rng, w["U"], I, Bc, w["S"], zipf=w["zipf"])
-    cores = os.cpu_count() or 1
-    tr.step(*batch, table_lr=0.05, nthreads=cores)           # warm
+    batches = [make_batch(rng, w["U"], I, Bc, w["S"], zipf=w["zipf"]) for _ in range(2)]
+    tr.step_fast(*batches[0], table_lr=0.05, nthreads=threads)           # warm
     n = 0; t0 = time.perf_counter()
     while True:
-        tr.step(*batch, table_lr=0.05, nthreads=cores); n += 1
+        tr.step_fast(*batches[n % 2], table_lr=0.05, nthreads=threads); n += 1
         dt = time.perf_counter() - t0
         if dt >= seconds and n >= 2:
             break
-    return {"value": Bc * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": "%d steps x %d samples of the same workload shape in %.1f s, OpenMP %d threads" % (n, Bc, dt, cores)}
+    return Bc * n / dt, n, dt, I
+
+
+def run_reference(args, w, wname):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Go (gorgonia + gonum) and
+    cannot be built here (no Go toolchain, modules not vendored), so this times the C restatement of its CPU path
+    (oracle/cpu_fast.c: blocked f32 SGEMMs, all host threads) on the SAME step shape as the engine arm: every step is one
+    65536-sample batch of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from tests.util import make_batch
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(42)
+    Bc = w["B"]
+    I = min(w["I"], 2_000_000)
+    model = orc.DIN_COS if w["model"] == "din" else orc.YOUTUBE
+    ocfg = orc.make_cfg(model, w["uP"], w["S"], w["D"], w["cF"], 200, 80, 0.005, 0.005)
+    uf = rng.random((w["U"], w["uP"]), dtype=np.float32); itf = rng.random((I, w["cF"]), dtype=np.float32)
+    emb = (rng.standard_normal((I, w["D"]), dtype=np.float32) / np.sqrt(w["D"])).astype(np.float32)
+    tr = orc.IdxTrainer(ocfg, orc.default_solver(0), orc.init_weights(ocfg, 0), uf, itf, emb)
+    batches = [make_batch(rng, w["U"], I, Bc, w["S"], zipf=w["zipf"]) for _ in range(2)]
+    steps = max(1, min(args.steps, 20)); warm = max(1, min(args.warmup, 2))
+    for i in range(warm):
+        tr.step_fast(*batches[i % 2], table_lr=0.05, nthreads=cores)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        tr.step_fast(*batches[i % 2], table_lr=0.05, nthreads=cores)
+    dt = time.perf_counter() - t0
+    v = Bc * steps / dt
+    v1, n1, dt1, _ = cpu_arm(w, 3.0, 4096, 1)
+    line = {"impl": "reference", "metric": "ctr_train_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(args, w, wname, args.gpus),
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": "%d steps x %d samples (the engine arm's step), OpenMP %d threads, blocked-SGEMM C restatement of go-ctr's CPU path "
+                                       "(Go reference unbuildable here); item table capped at %d rows; 1 thread: %.0f samples/s" % (steps, Bc, cores, I, v1),
+                             "one_thread_value": v1},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline(w, seconds=10.0):
+    cores = os.cpu_count() or 1
+    v, n, dt, I = cpu_arm(w, seconds, w["B"], cores)
+    v1, n1, dt1, _ = cpu_arm(w, 3.0, 4096, 1)
+    return {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "one_thread_value": v1,
+            "sample": "%d steps x %d samples of the same workload shape in %.1f s (item table capped at %d rows), OpenMP %d threads; "
+                      "blocked-SGEMM f32 C restatement of the reference's CPU path (oracle/cpu_fast.c), cross-checked against the "
+                      "double-accumulating checker by tests/test_oracle_fast.py; 1 thread: %.0f samples/s on 4096-sample steps" % (n, w["B"], dt, I, cores, v1)}
 
 
 def run_item2vec(args):
@@ -237,20 +265,19 @@ def run_item2vec(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="din_ml20m", choices=list(WORKLOADS) + ["item2vec"])
+    ap.add_argument("--workload", default="din_100m", choices=list(WORKLOADS) + ["item2vec"])
     ap.add_argument("--i2v-vocab", type=int, default=10_000_000)
     ap.add_argument("--i2v-tokens", type=int, default=50_000_000)
     ap.add_argument("--i2v-dim", type=int, default=64)
     ap.add_argument("--i2v-cpu-tokens", type=int, default=2_000_000)
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
-    ap.add_argument("--cpu-batch", type=int, default=16384)
-    ap.add_argument("--table-opt", default="sgd", choices=["sgd", "det", "frozen"])
+    ap.add_argument("--table-opt", default="sgd", choices=["sgd", "det", "frozen", "adam"])
     ap.add_argument("--gemm", default="auto", choices=["auto", "fp32", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-hbm-leg", action="store_true")
+    ap.add_argument("--no-side-legs", action="store_true", help="only the timed workload (+ roofline, e2e)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wname = args.workload
@@ -275,16 +302,19 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hbm_peak, peak_src = load_peaks()
+    dev = torch.device("cuda", local)
 
-    def build_engine(w, B, placement=0):
+    def build_engine(w, B, placement=0, world_=None, rank_=None, table_opt=None, dropout=None):
+        wd = world if world_ is None else world_; rk = rank if rank_ is None else rank_
         model = g.MODEL_DIN_COS if w["model"] == "din" else g.MODEL_YOUTUBE
-        topt = {"sgd": g.TABLE_SGD, "det": g.TABLE_SGD_DETERMINISTIC, "frozen": g.TABLE_FROZEN}[args.table_opt]
+        topt = {"sgd": g.TABLE_SGD, "det": g.TABLE_SGD_DETERMINISTIC, "frozen": g.TABLE_FROZEN, "adam": g.TABLE_ADAM}[table_opt or args.table_opt]
         gm = {"auto": g.GEMM_AUTO, "fp32": g.GEMM_FP32, "tcgen05": g.GEMM_TCGEN05_3XTF32}[args.gemm]
+        kw = {} if dropout is None else dict(dropout0=dropout, dropout1=dropout)
         cfg = g.engine.default_config(model, uP=w["uP"], S=w["S"], D=w["D"], cF=w["cF"], batch=B, pred_batch=B,
-                                      table_opt=topt, table_lr=0.05, gemm=gm, device=local, rank=rank, world=world, seed=1)
-        cfg.reserved[1] = placement          # ITEM_EMB under world > 1: 0 = by size, 1 = row-sharded, 2 = replicated
+                                      table_opt=topt, table_lr=0.05, gemm=gm, device=local, rank=rk, world=wd, seed=1, **kw)
+        cfg.reserved[1] = placement          # ITEM_* under world > 1: 0 = by size (> 32 MB shards), 1 = row-sharded, 2 = replicated
         eng = g.Engine(cfg)
-        if world > 1:
+        if wd > 1:
             ids = [None]
             if rank == 0:
                 ids[0] = eng.comm_unique_id()
@@ -296,23 +326,19 @@ def main():
         eng.table_fill(g.TABLE_ITEM_EMB, w["I"], w["D"], seed=5, dist=1, scale=float(1.0 / np.sqrt(w["D"])))
         return eng
 
-    def make_batches(w, B, nb, seed):
+    def make_batches(w, B, nb, seed, zipf=None):
         rng = np.random.default_rng(seed + rank)
-        out = []
-        for _ in range(nb):
-            out.append(synth_batch(w, rng, B))
-        return out
+        from tests.util import make_batch
+        return [make_batch(rng, w["U"], w["I"], B, w["S"], pad_frac=0.2, zipf=w["zipf"] if zipf is None else zipf) for _ in range(nb)]
 
-    dev = torch.device("cuda", local)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    def timed_leg(eng, w, B, steps, warmup, profile=False, clocks=True):
+    def timed_leg(eng, w, B, steps, warmup, profile=False, clocks=True, zipf=None, seed=100):
         """K timed steps, inputs resident in HBM, L2 flushed before every step (outside the events)."""
-        host = make_batches(w, B, 4, 100)
+        host = make_batches(w, B, 4, seed, zipf)
         devb = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in host]
         st = torch.cuda.ExternalStream(eng.stream, device=dev)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        l0 = eng.launch_count()
 
         def one(i, e=None):
             ur, ir, hist, y = devb[i % len(devb)]
@@ -340,16 +366,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         l2 = eng.launch_count()
-        clocks = None
+        clk = None
         if sampler:      # untimed tail: the same steps keep the load up until nvidia-smi has had >= 0.3 s to sample it
             k = 0
-            # multi-rank steps contain collectives: every rank must run the same number of tail steps
-            while (k < 300) if world > 1 else (time.time() - c0 < 0.3 and k < 400):
+            # multi-rank steps are collective: every rank must run the same number of tail steps
+            ntail = max(8, int(0.35 / max(wall / steps, 1e-4)))
+            while (k < ntail) if world > 1 else (time.time() - c0 < 0.3 and k < 400):
                 one(k); k += 1
                 if k % 8 == 0:
                     eng.sync()
             eng.sync(); torch.cuda.synchronize()
-            clocks = sampler.stop(c0, time.time())
+            clk = sampler.stop(c0, time.time())
         if profile:
             eng.profile(False)
         ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -357,75 +384,46 @@ def main():
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        launches = (l2 - l1)        # kernels launched inside the timed region only
         cost = eng.last_cost()
-        return dict(ms=ms, wall=wall, clocks=clocks, launches=launches, host=host, cost=cost, prof=eng.profile_dump() if profile else None)
+        return dict(ms=ms, wall=wall, clocks=clk, launches=(l2 - l1), host=host, cost=cost, prof=eng.profile_dump() if profile else None)
 
-    def e2e_leg(eng, w, B, steps, warmup):
-        """Same metric through the public host-buffer entry point ctr_train_idx (one model.Train pass over
-        `steps` batches held in pinned HOST memory): every batch's ids/labels are copied H2D inside the call
-        (overlapped with the previous batch's compute on a second stream) and every batch's cost is read
-        back D2H before the call returns.  Single-GPU; with sharded tables (world > 1) the per-batch entry
-        point ctr_train_step_idx is timed instead."""
-        host = make_batches(w, B, 4, 200)
-        if world > 1 and w["I"] * w["D"] * 4 > 32 * 2**20:     # row-sharded tables: per-batch entry point
-            pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
-            st = g.StepStats()
-            for i in range(warmup):
-                ur, ir, hist, y = pinned[i % 4]
-                eng.train_step_idx_ptr(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B, st)
-            dist.barrier(); torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for i in range(steps):
-                ur, ir, hist, y = pinned[(warmup + i) % 4]
-                eng.train_step_idx_ptr(ur.data_ptr(), ir.data_ptr(), hist.data_ptr(), y.data_ptr(), B, st)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item()); last = st.cost
-            h2d = sum(a.numel() * a.element_size() for a in pinned[0])
-        else:
-            cat = [torch.from_numpy(np.concatenate([host[i % 4][j] for i in range(steps)])).pin_memory() for j in range(4)]
-            costs = torch.empty(steps, dtype=torch.float32).pin_memory()
-            eng.train_idx_ptr(cat[0].data_ptr(), cat[1].data_ptr(), cat[2].data_ptr(), cat[3].data_ptr(), B * min(steps, max(warmup, 2)), costs.data_ptr())
-            torch.cuda.synchronize()
+    def rowstats(w, leg):
+        """rows a step touches on this rank, and how many of them live on a peer (row % world != rank)"""
+        rows = remote = 0
+        for ur, ir, hist, y in leg["host"]:
+            v = hist >= 0
+            rows += int(v.sum()) + int((ir >= 0).sum())
             if world > 1:
-                dist.barrier(); torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            eng.train_idx_ptr(cat[0].data_ptr(), cat[1].data_ptr(), cat[2].data_ptr(), cat[3].data_ptr(), B * steps, costs.data_ptr())
-            dt = time.perf_counter() - t0
-            if world > 1:       # slowest rank
-                t = torch.tensor([dt], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
-            last = float(costs[-1])
-            h2d = sum(a.numel() * a.element_size() for a in cat) // steps
-        return dict(value=B * world * steps / dt, unit="samples/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=8,
-                    ms_per_step=1e3 * dt / steps, last_cost=last)
+                remote += int((v & (hist % world != rank)).sum()) + int(((ir >= 0) & (ir % world != rank)).sum())
+        n = len(leg["host"])
+        return rows / n, remote / n
 
-    def roofline_of(w, leg, prof, B, workload_name=None):
-        ur, ir, hist, y = leg["host"][0]
-        gbytes, sbytes, rows = algorithmic_bytes(w, hist, ir)
+    def roofline_of(w, leg, steps, B, traffic_key=None):
+        prof = leg["prof"]
+        rows, remote = rowstats(w, leg)
+        row_bytes = w["D"] * 4
+        gbytes = rows * row_bytes + B * (w["S"] + 2) * 4 + B * (w["uP"] + w["cF"]) * 4      # SURVEY §8(d): gather
+        sbytes = 2 * rows * row_bytes                                                       # scatter-add = row read-modify-write
         kern = {}
         for name, (ms, n) in prof.items():
-            kern[name] = {"ms_per_launch": ms / max(n, 1), "launches_per_step": n / max(args.steps, 1)}
+            kern[name] = {"ms_per_launch": ms / max(n, 1), "launches_per_step": n / max(steps, 1)}
         fwd = next((k for k in kern if k.startswith("attn_fwd")), None)
         bwd = next((k for k in kern if k.startswith("attn_bwd")), None)
         if fwd:
-            kern[fwd]["algorithmic_bytes"] = gbytes
-            kern[fwd]["gbs"] = gbytes / (kern[fwd]["ms_per_launch"] * 1e-3) / 1e9
+            kern[fwd].update(algorithmic_bytes=gbytes, gbs=gbytes / (kern[fwd]["ms_per_launch"] * 1e-3) / 1e9)
         if bwd:
-            kern[bwd]["algorithmic_bytes"] = sbytes
-            kern[bwd]["gbs"] = sbytes / (kern[bwd]["ms_per_launch"] * 1e-3) / 1e9
+            kern[bwd].update(algorithmic_bytes=sbytes, gbs=sbytes / (kern[bwd]["ms_per_launch"] * 1e-3) / 1e9)
+        step_ms = sum(v["ms_per_launch"] * v["launches_per_step"] for v in kern.values())
+        for v in kern.values():
+            v["share_of_step"] = v["ms_per_launch"] * v["launches_per_step"] / step_ms if step_ms else None
         cand = [k for k in (fwd, bwd) if k]
         if not cand:
-            return None, kern
+            return None, kern, None
         dom = max(cand, key=lambda k: kern[k]["ms_per_launch"])
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(workload_name or wname, {}).get(dom)
+        if os.path.exists(tp) and traffic_key:
+            traffic = json.load(open(tp)).get(traffic_key, {}).get(dom)
         pair_ms = sum(kern[k]["ms_per_launch"] for k in cand)
         rl = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
               "frac": kern[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
@@ -434,73 +432,175 @@ def main():
                              "achieved": (gbytes + sbytes) / (pair_ms * 1e-3) / 1e9,
                              "frac": (gbytes + sbytes) / (pair_ms * 1e-3) / 1e9 / hbm_peak},
               "rows_per_launch": rows,
-              "how": "second pass of the same %d steps with every launch bracketed by CUDA events on the engine stream" % args.steps}
-        return rl, kern
+              "how": "second pass of the same %d steps with every launch bracketed by CUDA events on the engine stream" % steps}
+        nv = None
+        if world > 1 and fwd and bwd:
+            # the sharded step is NVLink bound: every remote row crosses once inbound (forward gather) and once outbound
+            # (backward red.add); the HBM fraction above is reported for continuity, the NVLink block is the binding roofline
+            rb = remote * row_bytes
+            nv = {"remote_rows_per_step": remote, "remote_fraction": remote / max(rows, 1), "bytes_each_way_per_step": rb,
+                  "gather_in_GBs": rb / (kern[fwd]["ms_per_launch"] * 1e-3) / 1e9, "red_add_out_GBs": rb / (kern[bwd]["ms_per_launch"] * 1e-3) / 1e9,
+                  "nominal_GBs_per_direction": NVLINK_NOMINAL_GBS, "probe_GBs": NVLINK_PROBE_GBS,
+                  "frac_of_nominal": {"gather": rb / (kern[fwd]["ms_per_launch"] * 1e-3) / 1e9 / NVLINK_NOMINAL_GBS,
+                                      "red_add": rb / (kern[bwd]["ms_per_launch"] * 1e-3) / 1e9 / NVLINK_NOMINAL_GBS},
+                  "step_floor_ms_at_probe_rate": rb / 1e6 / NVLINK_PROBE_GBS["gather"] + rb / 1e6 / NVLINK_PROBE_GBS["red_add"],
+                  "note": "the two directions are used one after the other (gather, then red.add, separated by the MLP and a barrier): "
+                          "per-GPU ceiling = remote bytes / probe rate, each way"}
+            rl["note"] = "row-sharded step: the attention kernels wait on NVLink, not HBM — see `nvlink`"
+        return rl, kern, nv
 
+    def e2e_legs(eng, w, B, steps):
+        """The same metric through the reference-facing host entry points, caller buffers in PAGEABLE host memory
+        (plain numpy, as a cgo caller's Go slices would be): (a) ctr_train_keys — recommend.Train over sample keys
+        {UserId, ItemId, Timestamp, Label}: 28 B/sample H2D, id maps + ubcache window + training on the device;
+        (b) ctr_train_idx — precomputed row ids + history rows: (S+3)*4 B/sample H2D.  Both stage through the internal
+        pinned ring; the batch costs are read back D2H before the call returns."""
+        out = {}
+        rng = np.random.default_rng(200 + rank)
+        U, I, S = w["U"], w["I"], w["S"]
+        n = B * steps
+        # (b) ids
+        from tests.util import make_batch
+        ur, ir, hist, y = make_batch(rng, U, I, n, S, pad_frac=0.2, zipf=w["zipf"])
+        eng.train_idx(ur[:2 * B], ir[:2 * B], hist[:2 * B], y[:2 * B])            # warm (allocates the ring)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        costs = eng.train_idx(ur, ir, hist, y)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        out["idx"] = dict(value=B * world * steps / dt, unit="samples/s", h2d_bytes_per_step=int(B * (S + 3) * 4), d2h_bytes_per_step=8,
+                          ms_per_step=1e3 * dt / steps, last_cost=float(costs[-1]), entry="ctr_train_idx", host_memory="pageable (numpy)")
+        del hist
+        # (a) keys: sparse external ids, per-user behaviour sequences in the device ubcache
+        uid = (np.arange(U, dtype=np.int64) * 7 + 3); iid = (np.arange(I, dtype=np.int64) * 5 + 11)
+        eng.idmap_build(g.IDMAP_USER, uid); eng.idmap_build(g.IDMAP_ITEM, iid)
+        L = 2 * S                                                                   # events per user
+        off = (np.arange(U + 1, dtype=np.int64) * L)
+        ts = np.tile(np.arange(L, 0, -1, dtype=np.int64) * 1000, U)
+        items = (rng.zipf(1.05, U * L) - 1) % I if w["zipf"] else rng.integers(0, I, U * L)
+        eng.ubcache_upload(off, ts, items.astype(np.int32))
+        su = rng.integers(0, U, n); si = ((rng.zipf(1.05, n) - 1) % I) if w["zipf"] else rng.integers(0, I, n)
+        k_user = uid[su]; k_item = iid[si]; k_ts = rng.integers(1000, (L + 1) * 1000, n).astype(np.int64)
+        eng.train_keys(k_user[:2 * B], k_item[:2 * B], k_ts[:2 * B], y[:2 * B])
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ep, cost, used = eng.train_keys(k_user, k_item, k_ts, y, epochs=1)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        out["keys"] = dict(value=used * world / dt, unit="samples/s", h2d_bytes_per_step=int(B * 28), d2h_bytes_per_step=8,
+                           ms_per_step=1e3 * dt / steps, last_cost=float(cost), entry="ctr_train_keys", host_memory="pageable (numpy)",
+                           rows_used=int(used))
+        return out
+
+    def parity_block():
+        """N ranks x batch Bp on a row-sharded table == one GPU x batch N*Bp on the whole table (same samples, same
+        init, dropout off): batch costs, dense weights after k steps, and the updated table rows.  Rank 0 holds the
+        single-GPU reference engine.  Tolerances: both sides scatter with fp32 red.add in arbitrary order."""
+        wp = dict(w); wp["I"] = 1_000_003; wp["U"] = 5000
+        Bp, k = 2048, 3
+        eng_s = build_engine(wp, Bp, placement=1, dropout=0.0)
+        rngp = np.random.default_rng(4242)
+        from tests.util import make_batch
+        glob = [make_batch(rngp, wp["U"], wp["I"], Bp * world, wp["S"], pad_frac=0.2, zipf=True) for _ in range(k)]
+        sl = slice(rank * Bp, (rank + 1) * Bp)
+        costs = [eng_s.train_step_idx(*(a[sl] for a in b)).cost for b in glob]
+        ws = eng_s.get_weights()
+        probe_rows = np.unique(np.concatenate([glob[0][2][glob[0][2] >= 0][:4000], glob[0][1][:1000]]))
+        # every rank scores the same probe batch through the sharded tables: reads every owner's updated rows
+        pr = make_batch(np.random.default_rng(7), wp["U"], wp["I"], Bp, wp["S"], zipf=True)
+        eng_s.sync(); dist.barrier()
+        p_shard = eng_s.predict_idx(pr[0], pr[1], pr[2])
+        dist.barrier()
+        res = None
+        if rank == 0:
+            eng_1 = build_engine(wp, Bp * world, world_=1, rank_=0, dropout=0.0)
+            want = [eng_1.train_step_idx(*b).cost for b in glob]
+            w1 = eng_1.get_weights()
+            cfgp = g.engine.default_config(g.MODEL_DIN_COS, uP=wp["uP"], S=wp["S"], D=wp["D"], cF=wp["cF"], batch=Bp, pred_batch=Bp, device=local, seed=1)
+            # score the probe batch on the single-GPU engine's tables (pred_batch = N*Bp >= Bp)
+            p_one = eng_1.predict_idx(pr[0], pr[1], pr[2])
+            dcost = float(np.max(np.abs(np.array(costs) - np.array(want)) / np.maximum(1.0, np.abs(want))))
+            dw = max(float(np.mean(np.abs(a - b) > 2e-4 + 2e-3 * np.abs(b))) for a, b in zip(ws, w1))
+            dp = float(np.max(np.abs(p_shard - p_one) / np.maximum(1e-6, np.abs(p_one))))
+            ok = bool(dcost <= 2e-4 and dw <= 0.005 and dp <= 2e-3)
+            res = {"ok": ok, "what": "%d ranks x batch %d on a row-sharded 1M-row table vs 1 GPU x batch %d, %d SGD steps (Zipf ids, dropout off)" % (world, Bp, Bp * world, k),
+                   "max_rel_cost_diff": dcost, "frac_dense_weights_outside_tol": dw, "max_rel_score_diff_after_training": dp,
+                   "costs": [float(c) for c in costs], "tolerances": {"cost": 2e-4, "weights": "rtol 2e-3 + atol 2e-4 on >= 99.5 %", "scores": 2e-3}}
+            del eng_1
+        del eng_s
+        torch.cuda.empty_cache()
+        return res
+
+    # ------------------------------------------------------------------------------------------------ main line
     B = w["B"]
     eng = build_engine(w, B)
+    sharded = world > 1 and w["I"] * w["D"] * 4 > 32 * 2**20
     leg = timed_leg(eng, w, B, args.steps, args.warmup)
-    prof_leg = timed_leg(eng, w, B, args.steps, 1, profile=True)
-    rl, kern = roofline_of(w, prof_leg, prof_leg["prof"], B)
-    e2e = e2e_leg(eng, w, B, max(3, min(args.steps, 64)), 2)
+    psteps = max(5, min(args.steps, 20))
+    prof_leg = timed_leg(eng, w, B, psteps, 1, profile=True)
+    rl, kern, nv = roofline_of(w, prof_leg, psteps, B, traffic_key=wname if world == 1 else None)
     value = B * world * args.steps / (leg["ms"] * 1e-3)
-    step_ms = sum(v["ms_per_launch"] * v["launches_per_step"] for v in kern.values())
-    for v in kern.values():
-        v["share_of_step"] = v["ms_per_launch"] * v["launches_per_step"] / step_ms if step_ms else None
+    cfg = config_of(args, w, wname, world)
+    engine_cfg = dict(table_opt=args.table_opt, gemm=args.gemm,
+               placement=("single GPU: the whole table in one HBM (%.1f GB ITEM_EMB + %.1f GB ITEM_FEAT)" % (w["I"] * w["D"] * 4 / 1e9, w["I"] * 56 * 4 / 1e9) if world == 1 else
+                          "1 process per GPU; ITEM_EMB / ITEM_FEAT rows sharded row%world; gather and red.add go to the owner's HBM over NVLink peer mappings "
+                          "(VMM allocations shared as fds), 2 device-side barriers + 1 NCCL all-reduce (dense gradients) per step" if sharded else
+                          "1 process per GPU; ITEM_EMB (%.0f MB) replicated, row + dense gradients all-reduced (NCCL)" % (w["I"] * w["D"] * 4 / 1e6)))
     line = {"metric": "ctr_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": leg["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wname, "note": w["note"], "graph": w["model"], "users": w["U"], "items": w["I"], "D": w["D"], "S": w["S"],
-                       "uP": w["uP"], "cF": w["cF"], "per_gpu_batch": B, "global_batch": B * world, "table_opt": args.table_opt,
-                       "gemm": args.gemm, "ids": "zipf(1.05)" if w["zipf"] else "uniform", "history_padding": "20% of samples have a -1 padded tail",
-                       "l2": "256 MiB buffer written before every timed step (outside the event pair); per-step event pairs are summed",
-                       "placement": ("single GPU" if world == 1 else
-                                       "1 process per GPU; ITEM_EMB (%.0f MB) replicated, row + dense gradients all-reduced (NCCL)" % (w["I"] * w["D"] * 4 / 1e6)
-                                       if w["I"] * w["D"] * 4 <= 32 * 2**20 else "1 process per GPU; ITEM_EMB rows sharded row%world, de-duplicated all-to-all exchange (NCCL)")},
-            "clocks": leg["clocks"], "e2e": {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
-            "e2e_ms_per_step": e2e["ms_per_step"], "gpu_launches": int(leg["launches"]), "last_cost": leg["cost"],
+            "vs_baseline": None, "dtype": "f32 (3xTF32 fwd/dgrad GEMMs, 1xTF32-RN wgrad GEMMs, fp32 everything else)", "data": "synthetic",
+            "config": cfg, "engine": engine_cfg, "clocks": leg["clocks"], "gpu_launches": int(leg["launches"]), "last_cost": leg["cost"],
             "wall_s_timed_region": leg["wall"], "roofline": rl, "kernels": kern}
-    if rl is not None and w["I"] * w["D"] * 4 / (1 if w["I"] * w["D"] * 4 <= 32 * 2**20 else world) < 126e6:
+    if nv:
+        line["nvlink"] = nv
+    if rl is not None and w["I"] * w["D"] * 4 / (world if sharded else 1) < 126e6:
         rl["note"] = "table is L2-resident in the timed workload (DRAM traffic << algorithmic bytes): not an HBM reading"
-    if world > 1 and w["I"] * w["D"] * 4 <= 32 * 2**20 and not args.no_hbm_leg:
-        # the timed workload's table is small enough to be replicated; the same steps with the table forced onto
-        # the row-sharded NCCL all-to-all path (BASELINE north_star's placement for large tables) — all ranks, collective
+    e2e = e2e_legs(eng, w, B, max(4, min(args.steps, 32)))
+    line["e2e"] = {k: e2e["keys"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+    line["e2e_detail"] = e2e
+    if not args.no_side_legs:
+        side = {}
+        # Zipf(1.05) item popularity on the same table: hot rows are gathered / updated by every sample
+        zl = timed_leg(eng, w, B, max(5, args.steps // 4), 3, clocks=False, zipf=True, seed=300)
+        side["zipf_ids"] = {"what": "same engine and table, item / history ids drawn Zipf(1.05)", "value": B * world * max(5, args.steps // 4) / (zl["ms"] * 1e-3),
+                            "unit": "samples/s", "ms_per_step": zl["ms"] / max(5, args.steps // 4)}
         del eng
         torch.cuda.empty_cache()
-        eng_s = build_engine(w, B, placement=1)
-        ks = max(5, args.steps // 4)
-        leg_s = timed_leg(eng_s, w, B, ks, 3, clocks=False)
-        if rank == 0:
-            line["sharded_exchange"] = {"what": "same workload, ITEM_EMB forced row-sharded (row % world) with the de-duplicated all-to-all exchange",
-                                        "value": B * world * ks / (leg_s["ms"] * 1e-3), "unit": "samples/s", "ms_per_step": leg_s["ms"] / ks}
-        del eng_s
-    if rank == 0 and world == 1 and not args.no_hbm_leg and wname != "din_100m_shard":
-        # HBM-fair reading of the same kernels: a table far larger than L2
-        del eng
-        torch.cuda.empty_cache()
-        w2 = dict(WORKLOADS["din_100m_shard"])
-        eng2 = build_engine(w2, w2["B"])
-        leg2 = timed_leg(eng2, w2, w2["B"], max(5, args.steps // 2), 3)
-        p2 = timed_leg(eng2, w2, w2["B"], max(5, args.steps // 2), 1, profile=True)
-        steps_saved = args.steps; args.steps = max(5, args.steps // 2)
-        rl2, kern2 = roofline_of(w2, p2, p2["prof"], w2["B"], "din_100m_shard")
-        args.steps = steps_saved
-        line["hbm_roofline"] = {"workload": "din_100m_shard", "note": w2["note"], "items": w2["I"], "per_gpu_batch": w2["B"],
-                                "samples_per_sec": w2["B"] * max(5, steps_saved // 2) / (leg2["ms"] * 1e-3),
-                                "ms_per_step": leg2["ms"] / max(5, steps_saved // 2), "roofline": rl2,
-                                "kernels": {k: v for k, v in kern2.items() if k.startswith("attn")}}
-        del eng2
-        if w["I"] * w["D"] * 4 < 126e6:
-            # the timed workload's table fits the 126 MB L2, so its own GB/s is an L2 reading; the graded HBM roofline is
-            # the same kernels, same batch shape, on the table that does not fit (measured just above, in this run)
-            line["roofline_timed_workload"] = rl
-            line["roofline"] = dict(rl2, workload="din_100m_shard",
-                                    note="dominant kernel on a 12.5 M-row (3.2 GB) table, uniform ids; measured in this run after the timed region")
+        if world > 1 and sharded:
+            # BASELINE configs[3] read literally: GLOBAL batch 65536 over the N GPUs (strong-scaling point of the same table)
+            Bg = max(256, w["B"] // world)
+            eng_g = build_engine(w, Bg)
+            ks = max(10, args.steps // 2)
+            lg = timed_leg(eng_g, w, Bg, ks, 3, clocks=False, seed=400)
+            side["global_batch_%d" % (Bg * world)] = {"what": "configs[3] with the batch read as global: %d samples per GPU and step" % Bg,
+                                                     "value": Bg * world * ks / (lg["ms"] * 1e-3), "unit": "samples/s", "ms_per_step": lg["ms"] / ks}
+            del eng_g
+            torch.cuda.empty_cache()
+            side_par = parity_block()
+            if rank == 0:
+                line["parity"] = side_par
+        if world == 1 and wname != "din_ml20m":
+            # BASELINE configs[1] (the 7 MB, L2-resident table) on one GPU — kept as a side reading
+            w2 = dict(WORKLOADS["din_ml20m"])
+            eng2 = build_engine(w2, w2["B"])
+            k2 = max(5, args.steps // 2)
+            l2_ = timed_leg(eng2, w2, w2["B"], k2, 3, clocks=False, seed=500)
+            side["configs1_din_ml20m"] = {"what": w2["note"], "value": w2["B"] * k2 / (l2_["ms"] * 1e-3), "unit": "samples/s", "ms_per_step": l2_["ms"] / k2}
+            del eng2
+        line["side_legs"] = side
     if rank == 0:
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w)
+        if world > 1 and "parity" in line and line["parity"] and not line["parity"]["ok"]:
+            print(json.dumps(line))
+            raise SystemExit("parity check failed: %s" % json.dumps(line["parity"]))
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

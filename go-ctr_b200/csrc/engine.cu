@@ -9,6 +9,7 @@
 #include "ubcache.cuh"
 #include "idmap.cuh"
 #include "item2vec.cuh"
+#include "mlp64.cuh"
 #include "comm.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -1869,6 +1870,242 @@ done:
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+// ---- model/mlp: the float64 MLP classifier (row a11) ---------------------------------------------------------
+struct ctr_mlp {
+    ctr_mlp_config cfg{};
+    Mlp64Dims d{};
+    long np = 0;
+    int dev = 0, num_sms = 148;
+    cudaStream_t stream = nullptr;
+    mutable std::string err;
+    std::mutex mu;
+    double *params = nullptr, *grads = nullptr, *ms = nullptr, *vs = nullptr;
+    double *act[kMlpMaxLayers] = {}, *del[kMlpMaxLayers] = {};       // [rows_cap, units[l]]
+    long rows_cap = 0;
+    double *X64 = nullptr; float* Y32 = nullptr; long* idx = nullptr; size_t x_cap = 0, y_cap = 0, idx_cap = 0;
+    double* scal = nullptr;                                           // [0] batch loss, [1] epoch accumulator
+    double adam_calls = 0;                                            // AdamOptimizer64.t
+    bool fitted = false;
+};
+namespace {
+int mlp_err(const ctr_mlp* m, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (m) m->err = buf; else g_create_error = buf;
+    return code;
+}
+#define MCU(m, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return mlp_err(m, e_ == cudaErrorMemoryAllocation ? CTR_ENOMEM : CTR_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+int mlp_grid(const ctr_mlp* m, long work) { return (int)std::max<long>(1, std::min<long>((work + 255) / 256, (long)m->num_sms * 8)); }
+int mlp_rows(ctr_mlp* m, long rows) {
+    if (m->rows_cap >= rows) return CTR_OK;
+    for (int l = 1; l < m->d.n_layers; l++) {
+        if (m->act[l]) cudaFree(m->act[l]);
+        if (m->del[l]) cudaFree(m->del[l]);
+        m->act[l] = m->del[l] = nullptr;
+        MCU(m, cudaMalloc(&m->act[l], sizeof(double) * (size_t)rows * m->d.units[l]));
+        MCU(m, cudaMalloc(&m->del[l], sizeof(double) * (size_t)rows * m->d.units[l]));
+    }
+    m->rows_cap = rows;
+    return CTR_OK;
+}
+// f32 host matrix → f64 device matrix (mlp.go:47-52 / :17-29), through a bounded f32 staging buffer
+int mlp_upload_x(ctr_mlp* m, const float* X, int64_t n, int nin) {
+    const size_t need = (size_t)n * nin;
+    if (m->x_cap < need) { if (m->X64) cudaFree(m->X64); m->X64 = nullptr; MCU(m, cudaMalloc(&m->X64, need * sizeof(double))); m->x_cap = need; }
+    const size_t chunk = std::min<size_t>(need, (size_t)16 << 20);
+    float* st = nullptr;
+    MCU(m, cudaMalloc(&st, chunk * sizeof(float)));
+    int rc = CTR_OK;
+    for (size_t o = 0; o < need && rc == CTR_OK; o += chunk) {
+        const size_t c = std::min(chunk, need - o);
+        if (cudaMemcpyAsync(st, X + o, c * sizeof(float), cudaMemcpyHostToDevice, m->stream) != cudaSuccess) { rc = mlp_err(m, CTR_ECUDA, "upload X: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        k_f32_to_f64<<<mlp_grid(m, (long)c), 256, 0, m->stream>>>(st, m->X64 + o, (long)c);
+        if (cudaStreamSynchronize(m->stream) != cudaSuccess) rc = mlp_err(m, CTR_ECUDA, "upload X: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(st);
+    return rc;
+}
+// forwardPass (basemlp64.go:259-275) over m rows; layer 0 reads X64 through idx (may be null = identity) from row0
+void mlp_forward(ctr_mlp* m, const long* idx, long row0, int rows) {
+    const int L = m->d.n_layers, nin = m->d.units[0];
+    for (int l = 0; l + 1 < L; l++)
+        k_mlp64_layer<<<mlp_grid(m, (long)rows * m->d.units[l + 1]), 256, 0, m->stream>>>(m->params, m->d, l, m->X64 + (idx ? 0 : row0 * nin), nin, idx,
+                                                                                      l == 0 ? nullptr : m->act[l], m->act[l + 1], rows);
+}
+}  // namespace
+
+void ctr_mlp_config_default(ctr_mlp_config* c, int32_t n_features) {
+    memset(c, 0, sizeof *c);
+    c->n_layers = 3; c->units[0] = n_features; c->units[1] = 100; c->units[2] = 1;      // HiddenLayerSizes {100}, basemlp64.go:239
+    c->hidden_act = CTR_MLP_RELU; c->batch = 200; c->max_iter = 200; c->n_iter_no_change = 10; c->shuffle = 1;   // :229-254
+    c->adaptive = 0; c->warm_start = 0; c->seed = 0; c->device = 0;
+    c->alpha = 1e-4; c->lr_init = 1e-3; c->beta1 = 0.9; c->beta2 = 0.999; c->eps = 1e-8; c->tol = 1e-4;
+}
+const char* ctr_mlp_last_error(const ctr_mlp* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+int ctr_mlp_create(const ctr_mlp_config* cfg, ctr_mlp** out) {
+    if (!cfg || !out) return mlp_err(nullptr, CTR_EINVAL, "null argument");
+    *out = nullptr;
+    const ctr_mlp_config& c = *cfg;
+    if (c.n_layers < 2 || c.n_layers > kMlpMaxLayers) return mlp_err(nullptr, CTR_EINVAL, "n_layers must be in [2, %d]", kMlpMaxLayers);
+    for (int i = 0; i < c.n_layers; i++) if (c.units[i] < 1) return mlp_err(nullptr, CTR_EINVAL, "layer %d has %d units", i, c.units[i]);
+    if (c.units[c.n_layers - 1] != 1) return mlp_err(nullptr, CTR_EINVAL, "binary classifier: one output unit (basemlp64.go:423-425)");
+    if (c.hidden_act < CTR_MLP_RELU || c.hidden_act > CTR_MLP_IDENTITY || c.max_iter < 1) return mlp_err(nullptr, CTR_EINVAL, "bad activation / max_iter");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return mlp_err(nullptr, CTR_ENODEV, "no CUDA device: this engine has no CPU fallback"); }
+    if (c.device < 0 || c.device >= ndev) return mlp_err(nullptr, CTR_ENODEV, "device %d of %d", c.device, ndev);
+    cudaDeviceProp prop{}; cudaGetDeviceProperties(&prop, c.device);
+    if (prop.major != 10) return mlp_err(nullptr, CTR_ENODEV, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+    ctr_mlp* m = new ctr_mlp();
+    m->cfg = c; m->dev = c.device; m->num_sms = prop.multiProcessorCount;
+    m->d.n_layers = c.n_layers; m->d.hidden_act = c.hidden_act;
+    long off = 0;
+    for (int l = 0; l < c.n_layers; l++) { m->d.units[l] = c.units[l]; if (l + 1 < c.n_layers) { m->d.off[l] = off; off += (long)(1 + c.units[l]) * c.units[l + 1]; } }
+    m->np = off;
+    bool ok = cudaSetDevice(m->dev) == cudaSuccess && cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (double** p : {&m->params, &m->grads, &m->ms, &m->vs}) ok = ok && cudaMalloc(p, sizeof(double) * (size_t)m->np) == cudaSuccess && cudaMemset(*p, 0, sizeof(double) * (size_t)m->np) == cudaSuccess;
+    ok = ok && cudaMalloc(&m->scal, 2 * sizeof(double)) == cudaSuccess;
+    if (!ok) { mlp_err(nullptr, CTR_ECUDA, "ctr_mlp_create: %s", cudaGetErrorString(cudaGetLastError())); ctr_mlp_destroy(m); return CTR_ECUDA; }
+    *out = m;
+    return CTR_OK;
+}
+
+void ctr_mlp_destroy(ctr_mlp* m) {
+    if (!m) return;
+    cudaSetDevice(m->dev);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (void* p : {(void*)m->params, (void*)m->grads, (void*)m->ms, (void*)m->vs, (void*)m->X64, (void*)m->Y32, (void*)m->idx, (void*)m->scal}) if (p) cudaFree(p);
+    for (int l = 0; l < kMlpMaxLayers; l++) { if (m->act[l]) cudaFree(m->act[l]); if (m->del[l]) cudaFree(m->del[l]); }
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int ctr_mlp_get_params(ctr_mlp* m, double* params, int64_t cap, int64_t* np) {
+    if (!m) return CTR_EINVAL;
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (np) *np = m->np;
+    if (!params) return CTR_OK;
+    if (cap < m->np) return mlp_err(m, CTR_EINVAL, "parameter buffer too small: need %ld", m->np);
+    MCU(m, cudaSetDevice(m->dev));
+    MCU(m, cudaMemcpyAsync(params, m->params, sizeof(double) * (size_t)m->np, cudaMemcpyDeviceToHost, m->stream));
+    MCU(m, cudaStreamSynchronize(m->stream));
+    return CTR_OK;
+}
+int ctr_mlp_set_params(ctr_mlp* m, const double* params, int64_t np) {
+    if (!m || !params) return CTR_EINVAL;
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (np != m->np) return mlp_err(m, CTR_EINVAL, "expected %ld packed parameters, got %lld", m->np, (long long)np);
+    MCU(m, cudaSetDevice(m->dev));
+    MCU(m, cudaMemcpyAsync(m->params, params, sizeof(double) * (size_t)m->np, cudaMemcpyHostToDevice, m->stream));
+    MCU(m, cudaStreamSynchronize(m->stream));
+    m->fitted = true;
+    return CTR_OK;
+}
+
+int ctr_mlp_fit(ctr_mlp* m, const float* X, const float* Y, int64_t n, int32_t xcols, int32_t* n_iter, double* loss_curve) {
+    if (!m || !X || !Y || n < 1) return mlp_err(m, CTR_EINVAL, "bad fit arguments");
+    std::lock_guard<std::mutex> lk(m->mu);
+    const ctr_mlp_config& c = m->cfg;
+    const int nin = m->d.units[0];
+    if (xcols != nin) return mlp_err(m, CTR_EINVAL, "X has %d columns, the network %d inputs", xcols, nin);
+    MCU(m, cudaSetDevice(m->dev));
+    long bs = c.batch;
+    if (bs <= 0) bs = n < 200 ? n : 200; else if (bs > n) bs = n;                       // basemlp64.go:517-527
+    RET(mlp_upload_x(m, X, n, nin));
+    if (m->y_cap < (size_t)n) { if (m->Y32) cudaFree(m->Y32); m->Y32 = nullptr; MCU(m, cudaMalloc(&m->Y32, sizeof(float) * (size_t)n)); m->y_cap = (size_t)n; }
+    if (m->idx_cap < (size_t)n) { if (m->idx) cudaFree(m->idx); m->idx = nullptr; MCU(m, cudaMalloc(&m->idx, sizeof(long) * (size_t)n)); m->idx_cap = (size_t)n; }
+    MCU(m, cudaMemcpyAsync(m->Y32, Y, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    RET(mlp_rows(m, bs));
+    if (!c.warm_start || !m->fitted) {
+        // initialize, basemlp64.go:459-476: every packed element (intercepts too) = U[0,1)·sqrt(f/(fi+fo)), f = 6, or 2 for a
+        // logistic hidden activation — non-negative; counter RNG instead of the reference's time-seeded source
+        std::vector<double> p((size_t)m->np);
+        long pos = 0;
+        for (int l = 0; l + 1 < m->d.n_layers; l++) {
+            const int fi = m->d.units[l], fo = m->d.units[l + 1];
+            const double bound = std::sqrt((c.hidden_act == CTR_MLP_LOGISTIC ? 2.0 : 6.0) / (double)(fi + fo));
+            const long end = pos + (long)(1 + fi) * fo;
+            for (; pos < end; pos++) p[(size_t)pos] = (double)(mix64(c.seed, 7, (uint64_t)pos) >> 11) * (1.0 / 9007199254740992.0) * bound;
+        }
+        MCU(m, cudaMemcpyAsync(m->params, p.data(), sizeof(double) * (size_t)m->np, cudaMemcpyHostToDevice, m->stream));
+        MCU(m, cudaStreamSynchronize(m->stream));
+    }
+    MCU(m, cudaMemsetAsync(m->ms, 0, sizeof(double) * (size_t)m->np, m->stream));        // a fresh optimizer per fit (:541-556)
+    MCU(m, cudaMemsetAsync(m->vs, 0, sizeof(double) * (size_t)m->np, m->stream));
+    m->adam_calls = 0;
+    std::vector<long> idx((size_t)n);
+    for (int64_t i = 0; i < n; i++) idx[(size_t)i] = i;
+    double lr_init = c.lr_init, lr_last = c.lr_init, best = INFINITY;
+    int no_improve = 0, it = 0;
+    const int L = m->d.n_layers;
+    for (it = 0; it < c.max_iter;) {
+        if (c.shuffle) {                                                 // rand.Shuffle (:788): Fisher–Yates from the top
+            for (long i = n - 1; i > 0; i--) { const long j = (long)(mix64(c.seed, 100u + (uint32_t)it, (uint64_t)i) % (uint64_t)(i + 1)); std::swap(idx[(size_t)i], idx[(size_t)j]); }
+        }
+        MCU(m, cudaMemcpyAsync(m->idx, idx.data(), sizeof(long) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+        MCU(m, cudaMemsetAsync(m->scal, 0, 2 * sizeof(double), m->stream));
+        for (long b0 = 0; b0 < n; b0 += bs) {                            // :791-808
+            const int rows = (int)std::min<long>(bs, n - b0);
+            const long* bi = m->idx + b0;
+            mlp_forward(m, bi, 0, rows);
+            k_mlp64_loss<<<1, 256, 0, m->stream>>>(m->params, m->d, m->act[L - 1], m->Y32, bi, rows, c.alpha, m->del[L - 1], m->scal, m->scal + 1);
+            for (int l = L - 2; l >= 0; l--) {                           // backprop :382-402
+                k_mlp64_grads<<<mlp_grid(m, (long)(m->d.units[l] + 1) * m->d.units[l + 1]), 256, 0, m->stream>>>(
+                    m->params, m->grads, m->d, l, m->X64, nin, bi, l == 0 ? nullptr : m->act[l], m->del[l + 1], rows, c.alpha);
+                if (l >= 1) k_mlp64_delta<<<mlp_grid(m, (long)rows * m->d.units[l]), 256, 0, m->stream>>>(m->params, m->d, l, m->act[l], m->del[l + 1], m->del[l], rows);
+            }
+            k_mlp64_adam<<<mlp_grid(m, m->np), 256, 0, m->stream>>>(m->params, m->grads, m->ms, m->vs, m->np, m->adam_calls, lr_init, c.beta1, c.beta2, c.eps);
+            m->adam_calls += 1;
+        }
+        it++;
+        double sc[2] = {0, 0};
+        MCU(m, cudaMemcpyAsync(sc, m->scal, sizeof sc, cudaMemcpyDeviceToHost, m->stream));
+        MCU(m, cudaStreamSynchronize(m->stream));
+        MCU(m, cudaGetLastError());
+        const double loss = sc[1] / (double)n;                           // :810-811
+        if (loss_curve) loss_curve[it - 1] = loss;
+        {   // the learning rate the optimizer last used (:1088): decides "adaptive" stopping (:1059-1064)
+            const double e = m->adam_calls * (double)m->np;
+            lr_last = lr_init * std::sqrt(1.0 - std::pow(c.beta2, e)) / (1.0 - std::pow(c.beta1, e));
+        }
+        if (loss > best - c.tol) no_improve++; else no_improve = 0;      // :886-892
+        if (loss < best) best = loss;
+        if (no_improve > c.n_iter_no_change) {                           // :826-840
+            if (!c.adaptive) break;                                      // triggerStopping :1053-1058
+            if (lr_last <= 1e-6) break;
+            lr_init *= .8;
+            no_improve = 0;
+        }
+    }
+    if (n_iter) *n_iter = it;
+    m->fitted = true;
+    return CTR_OK;
+}
+
+int ctr_mlp_predict(ctr_mlp* m, const float* X, int64_t n, int32_t xcols, float* out) {
+    if (!m || !X || !out || n < 1) return mlp_err(m, CTR_EINVAL, "bad predict arguments");
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (!m->fitted) return mlp_err(m, CTR_ESTATE, "predict before fit");
+    const int nin = m->d.units[0], L = m->d.n_layers;
+    if (xcols != nin) return mlp_err(m, CTR_EINVAL, "X has %d columns, the network %d inputs", xcols, nin);
+    MCU(m, cudaSetDevice(m->dev));
+    RET(mlp_upload_x(m, X, n, nin));
+    const long chunk = 8192;
+    RET(mlp_rows(m, std::min<long>(chunk, n)));
+    float* d_out = nullptr;
+    MCU(m, cudaMalloc(&d_out, sizeof(float) * (size_t)std::min<long>(chunk, n)));
+    int rc = CTR_OK;
+    for (long r0 = 0; r0 < n && rc == CTR_OK; r0 += chunk) {            // predictProbas :897-931: raw probabilities for the f64 class
+        const int rows = (int)std::min<long>(chunk, n - r0);
+        mlp_forward(m, nullptr, r0, rows);
+        k_f64_to_f32<<<mlp_grid(m, rows), 256, 0, m->stream>>>(m->act[L - 1], d_out, rows);
+        if (cudaMemcpyAsync(out + r0, d_out, sizeof(float) * (size_t)rows, cudaMemcpyDeviceToHost, m->stream) != cudaSuccess ||
+            cudaStreamSynchronize(m->stream) != cudaSuccess) rc = mlp_err(m, CTR_ECUDA, "predict: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(d_out);
     return rc;
 }
 

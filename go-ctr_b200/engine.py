@@ -9,7 +9,7 @@ import numpy as np
 
 from . import build as _build
 
-__all__ = ["Engine", "Config", "StepStats", "CtrError", "load_library", "MODEL_YOUTUBE", "MODEL_DIN_COS",
+__all__ = ["Engine", "Config", "MLPClassifier", "MlpConfig", "StepStats", "CtrError", "load_library", "MODEL_YOUTUBE", "MODEL_DIN_COS",
            "MODEL_DIN_EUC", "TABLE_USER_FEAT", "TABLE_ITEM_FEAT", "TABLE_ITEM_EMB", "TABLE_FROZEN", "TABLE_SGD",
            "TABLE_SGD_DETERMINISTIC", "TABLE_ADAM", "GEMM_AUTO", "GEMM_FP32", "GEMM_TCGEN05_3XTF32", "EXPORTS", "IDMAP_USER", "IDMAP_ITEM", "ENOTFOUND"]
 
@@ -27,7 +27,9 @@ EXPORTS = ["ctr_abi_version", "ctr_config_default", "ctr_create", "ctr_destroy",
            "ctr_train_step_idx_dev", "ctr_predict_idx_dev", "ctr_last_cost", "ctr_sync", "ctr_get_stream",
            "ctr_set_stream", "ctr_launch_count", "ctr_profile_enable", "ctr_profile_get", "ctr_profile_reset",
            "ctr_profile_dump", "ctr_debug_grads_idx", "ctr_ubcache_upload", "ctr_ubcache_window", "ctr_ubcache_window_dev", "ctr_idmap_build", "ctr_idmap_lookup", "ctr_idmap_lookup_dev",
-           "ctr_batch_predict_keys", "ctr_checkpoint_save", "ctr_checkpoint_load", "ctr_roc_auc", "ctr_i2v_config_default", "ctr_i2v_paths", "ctr_i2v_train", "ctr_comm_unique_id", "ctr_comm_init"]
+           "ctr_batch_predict_keys", "ctr_checkpoint_save", "ctr_checkpoint_load", "ctr_roc_auc", "ctr_i2v_config_default", "ctr_i2v_paths", "ctr_i2v_train", "ctr_comm_unique_id", "ctr_comm_init",
+           "ctr_mlp_config_default", "ctr_mlp_create", "ctr_mlp_destroy", "ctr_mlp_last_error", "ctr_mlp_fit", "ctr_mlp_predict",
+           "ctr_mlp_get_params", "ctr_mlp_set_params"]
 
 
 class CtrError(RuntimeError):
@@ -43,6 +45,13 @@ class Config(C.Structure):
                 ("dropout0", C.c_float), ("dropout1", C.c_float), ("seed", C.c_uint32),
                 ("table_opt", C.c_int32), ("table_lr", C.c_float), ("gemm", C.c_int32), ("device", C.c_int32),
                 ("rank", C.c_int32), ("world", C.c_int32), ("reserved", C.c_int32 * 8)]
+
+
+class MlpConfig(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("units", C.c_int32 * 8), ("hidden_act", C.c_int32), ("batch", C.c_int32), ("max_iter", C.c_int32),
+                ("n_iter_no_change", C.c_int32), ("shuffle", C.c_int32), ("adaptive", C.c_int32), ("warm_start", C.c_int32), ("seed", C.c_uint32),
+                ("device", C.c_int32), ("alpha", C.c_double), ("lr_init", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("tol", C.c_double)]
 
 
 class StepStats(C.Structure):
@@ -73,6 +82,11 @@ def load_library():
     L.ctr_destroy.argtypes = [C.c_void_p]
     L.ctr_destroy.restype = None
     L.ctr_config_default.restype = None
+    L.ctr_mlp_last_error.restype = C.c_char_p
+    L.ctr_mlp_last_error.argtypes = [C.c_void_p]
+    L.ctr_mlp_destroy.argtypes = [C.c_void_p]
+    L.ctr_mlp_destroy.restype = None
+    L.ctr_mlp_config_default.restype = None
     _lib = L
     return L
 
@@ -332,3 +346,68 @@ class Engine:
         auc = C.c_double(0)
         self._ck(self.L.ctr_roc_auc(self.h, pp, tp, C.c_int64(p.size), C.byref(auc)))
         return auc.value
+
+
+MLP_ACT = {"relu": 0, "logistic": 1, "identity": 2}
+
+
+class MLPClassifier:
+    """nn.MLPClassifier on the device (float64): NewMLPClassifier(hidden, activation, "adam", alpha) with
+    NewBaseMultilayerPerceptron64's defaults (multilayer_perceptron.go:81-90, basemlp64.go:227-256)."""
+
+    def __init__(self, n_features, hidden=(100,), activation="relu", alpha=1e-4, batch=200, max_iter=200, lr_init=1e-3,
+                 adaptive=False, shuffle=True, seed=0, tol=1e-4, n_iter_no_change=10, warm_start=False, device=0):
+        self.L = load_library()
+        cfg = MlpConfig()
+        self.L.ctr_mlp_config_default(C.byref(cfg), C.c_int32(n_features))
+        units = [n_features, *hidden, 1]
+        cfg.n_layers = len(units)
+        for i, u in enumerate(units):
+            cfg.units[i] = u
+        cfg.hidden_act = MLP_ACT[activation]; cfg.alpha = alpha; cfg.batch = batch; cfg.max_iter = max_iter; cfg.lr_init = lr_init
+        cfg.adaptive = int(adaptive); cfg.shuffle = int(shuffle); cfg.seed = seed; cfg.tol = tol; cfg.n_iter_no_change = n_iter_no_change
+        cfg.warm_start = int(warm_start); cfg.device = device
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.L.ctr_mlp_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise CtrError(rc, self.L.ctr_mlp_last_error(None).decode())
+        self.n_iter = 0; self.loss_curve = np.zeros(0)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise CtrError(rc, self.L.ctr_mlp_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.ctr_mlp_destroy(self.h); self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def fit(self, X, Y):
+        Xa, Xp = _f(X); Ya, Yp = _f(Y)
+        it = C.c_int32(0); curve = np.zeros(self.cfg.max_iter, np.float64)
+        self._ck(self.L.ctr_mlp_fit(self.h, Xp, Yp, C.c_int64(Xa.shape[0]), C.c_int32(Xa.shape[1]), C.byref(it), curve.ctypes.data_as(C.POINTER(C.c_double))))
+        self.n_iter = it.value; self.loss_curve = curve[:it.value]
+        return self
+
+    def predict(self, X):
+        Xa, Xp = _f(X)
+        out = np.empty(Xa.shape[0], np.float32)
+        self._ck(self.L.ctr_mlp_predict(self.h, Xp, C.c_int64(Xa.shape[0]), C.c_int32(Xa.shape[1]), out.ctypes.data_as(_fp)))
+        return out
+
+    def get_params(self):
+        n = C.c_int64(0)
+        self._ck(self.L.ctr_mlp_get_params(self.h, None, C.c_int64(0), C.byref(n)))
+        p = np.empty(n.value, np.float64)
+        self._ck(self.L.ctr_mlp_get_params(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(n.value), C.byref(n)))
+        return p
+
+    def set_params(self, p):
+        p = np.ascontiguousarray(p, np.float64)
+        self._ck(self.L.ctr_mlp_set_params(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(p.size)))

@@ -8,6 +8,7 @@ the reference's own tests (model/model_test.go, example/movielens/dinimpl_test.g
     youtube.NewYoutubeDnn / ...FromJson / Marshal dnn.go:49-160
     model.Train / InitForwardOnlyVm / Predict     model.go:27, 215, 242
     movielens dinImpl / YoutubeDnnImpl (Fitter + PredictAbstract)   dinimpl.go:13-92, youtube.go:13-91
+    mlp.SimpleMlpFitWrap / SimpleMlpPredWrap (Fitter + PredictAbstract) model/mlp/mlp.go:11-65
 
 The gorgonia-typed half of model.Model (Fwd/Graph/Vm, model.go:16-25) has no meaning on a GPU
 engine; the seam is Fitter / PredictAbstract + Train / Predict + the Marshal JSON schema
@@ -22,7 +23,7 @@ from . import engine as _e
 
 __all__ = ["SampleInfo", "TrainSample", "DinNet", "YoutubeDnn", "NewDinNet", "NewDinNetFromJson",
            "NewYoutubeDnn", "NewYoutubeDnnFromJson", "Train", "InitForwardOnlyVm", "Predict",
-           "DinImpl", "YoutubeDnnImpl", "RocAuc32"]
+           "DinImpl", "YoutubeDnnImpl", "RocAuc32", "SimpleMlpFitWrap", "SimpleMlpPredWrap"]
 
 mlp0_1, mlp1_2 = 200, 80          # din.go:17-18
 
@@ -214,6 +215,33 @@ class DinImpl(_Impl):
 class YoutubeDnnImpl(_Impl):
     _new = staticmethod(NewYoutubeDnn)
     _from_json = staticmethod(NewYoutubeDnnFromJson)
+
+
+class SimpleMlpPredWrap:
+    """model/mlp/mlp.go:11-39: PredictAbstract over the fitted classifier — float32 X in, float32 [n, 1] out."""
+
+    def __init__(self, pred):
+        self.pred = pred
+
+    def Predict(self, X):
+        X = np.asarray(X, np.float32)
+        return self.pred.predict(X).reshape(-1, 1)
+
+
+class SimpleMlpFitWrap:
+    """model/mlp/mlp.go:41-65: Fitter over nn.MLPClassifier (main.go:42-52 builds it with NewMLPClassifier([]int{100},
+    "relu", "adam", 1e-4) — pass the same through **mlp_kw).  Model is created at Fit time from the sample width."""
+
+    def __init__(self, **mlp_kw):
+        self.mlp_kw = mlp_kw
+        self.Model = None
+
+    def Fit(self, trainSample):
+        X = np.asarray(trainSample.X, np.float32).reshape(trainSample.Rows, trainSample.XCols)
+        Y = np.asarray(trainSample.Y, np.float32)
+        self.Model = _e.MLPClassifier(trainSample.XCols, **self.mlp_kw)
+        self.Model.fit(X, Y)
+        return SimpleMlpPredWrap(self.Model)
 
 
 def RocAuc32(pred, y, engine=None):

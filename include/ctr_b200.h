@@ -261,6 +261,38 @@ int  ctr_i2v_paths(const int64_t* count, int32_t vocab, int32_t max_depth, int64
 int  ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, int32_t vocab,
                    float* emb_out, ctr_i2v_stats* stats);
 
+/* ---- model/mlp: the float64 MLP classifier of the reference's default path (BASELINE configs[0]; SURVEY.md §8a row
+ * a11) — main.go:42-52 → model/mlp/mlp.go:45-65 (SimpleMlpFitWrap.Fit / SimpleMlpPredWrap.Predict: float32 samples →
+ * float64 → nn.MLPClassifier) → nn/neural_network/basemlp64.go.  Float64 arithmetic on the device; packed parameter
+ * vector in the reference's layout (basemlp64.go:459-463: per layer [intercepts | coefs row-major]). -------------- */
+enum { CTR_MLP_RELU = 0, CTR_MLP_LOGISTIC = 1, CTR_MLP_IDENTITY = 2 };
+typedef struct ctr_mlp ctr_mlp;
+typedef struct {
+    int32_t n_layers;                 /* len(layerUnits): hidden layers + 2 (basemlp64.go:495-497) */
+    int32_t units[8];                 /* [nFeatures, HiddenLayerSizes..., 1] */
+    int32_t hidden_act;               /* Activation "relu" (:229) | "logistic" | "identity"; the output is logistic (:423-425) */
+    int32_t batch, max_iter, n_iter_no_change;   /* BatchSize 200, MaxIter 200, NIterNoChange 10 (:233,238,254) */
+    int32_t shuffle, adaptive;        /* Shuffle true (:241); LearningRate == "adaptive" */
+    int32_t warm_start;               /* WarmStart (:245): keep the current parameters instead of re-initialising */
+    uint32_t seed;                    /* init + shuffle counter RNG (the reference's source is time-seeded, :448,500) */
+    int32_t device;
+    double alpha, lr_init, beta1, beta2, eps, tol;   /* 1e-4, 1e-3, .9, .999, 1e-8, 1e-4 (:232-252) */
+} ctr_mlp_config;
+void ctr_mlp_config_default(ctr_mlp_config* cfg, int32_t n_features);      /* NewBaseMultilayerPerceptron64, :227-256 */
+int  ctr_mlp_create(const ctr_mlp_config* cfg, ctr_mlp** out);             /* nn.NewMLPClassifier */
+void ctr_mlp_destroy(ctr_mlp* m);
+const char* ctr_mlp_last_error(const ctr_mlp* m);
+/* SimpleMlpFitWrap.Fit (mlp.go:45-65): X [n, xcols] float32, Y [n] float32 in {0,1} → fit (basemlp64.go:484-567 →
+ * fitStochastic :729-857, solver adam).  *n_iter = epochs run (NIter); loss_curve (may be NULL) receives max_iter
+ * per-epoch losses at most. */
+int  ctr_mlp_fit(ctr_mlp* m, const float* X, const float* Y, int64_t n, int32_t xcols, int32_t* n_iter, double* loss_curve);
+/* SimpleMlpPredWrap.Predict (mlp.go:15-39): probabilities as float32 [n] (the 64-bit class returns them raw,
+ * basemlp64.go:897-931). */
+int  ctr_mlp_predict(ctr_mlp* m, const float* X, int64_t n, int32_t xcols, float* out);
+/* packed parameter vector; ctr_mlp_get_params(m, NULL, 0, &np) returns the length */
+int  ctr_mlp_get_params(ctr_mlp* m, double* params, int64_t cap, int64_t* np);
+int  ctr_mlp_set_params(ctr_mlp* m, const double* params, int64_t np);
+
 /* Multi-GPU (world > 1): one handle per rank/process.  The id is ncclUniqueId bytes produced on
  * rank 0 by ctr_comm_unique_id and distributed by the host (torch.distributed / Go). */
 int ctr_comm_unique_id(void* id_out, int32_t* id_bytes /* in: capacity, out: used */);

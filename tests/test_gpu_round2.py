@@ -35,12 +35,13 @@ def test_auc_parity_at_the_baseline_config_shape(model):
     ur, ir, hist, _ = make_batch(rng, U, I, NTR + NTE, NS["S"], pad_frac=0.2, zipf=True)
     S, D, uP, cF = NS["S"], NS["D"], NS["uP"], NS["cF"]
     ranges = orc.make_ranges(uP, S, D, cF)
-    # teacher: a DIN with moderate weights scores every sample; the label is a Bernoulli draw of that score
+    # teacher: a DIN with moderate weights scores every sample; the label is a Bernoulli draw of its standardised logit
+    # (Bayes AUC ~0.86, so a trained model lands far from chance and the +-0.002 bar is informative)
     tcfg = orc.make_cfg(orc.DIN_COS, uP, S, D, cF, 200, 80)
     Wt = scaled_init(orc, tcfg, 99, s0=0.25, s1=0.25, s2=1.0)
-    pt = np.concatenate([orc.forward(tcfg, Wt, orc.gather_rows(uf, itf, emb, ur[i:i + 5000], ir[i:i + 5000], hist[i:i + 5000]), ranges)[0]
-                         for i in range(0, NTR + NTE, 5000)])
-    pt = 1.0 / (1.0 + np.exp(-8.0 * (pt - np.median(pt))))          # spread the teacher's scores over (0, 1)
+    zt = np.concatenate([orc.forward(tcfg, Wt, orc.gather_rows(uf, itf, emb, ur[i:i + 5000], ir[i:i + 5000], hist[i:i + 5000]), ranges)[1]
+                         for i in range(0, NTR + NTE, 5000)]).astype(np.float64)
+    pt = 1.0 / (1.0 + np.exp(-2.0 * (zt - np.median(zt)) / zt.std()))
     y = (rng.random(NTR + NTE) < pt).astype(np.float32)
     ocfg = orc.make_cfg(OMODEL[model], uP, S, D, cF, 200, 80, cfg.dropout0, cfg.dropout1)
     W = [w.copy() for w in orc.init_weights(ocfg, 7)]
@@ -59,7 +60,7 @@ def test_auc_parity_at_the_baseline_config_shape(model):
                             for i in range(NTR, NTR + NTE, 5000)])
     auc_gpu = eng.roc_auc(p_gpu, y[sl]); auc_cpu = orc.roc_auc(p_cpu, y[sl])
     assert abs(auc_gpu - orc.roc_auc(p_gpu, y[sl])) < 1e-9            # device AUC == reference-semantics AUC
-    assert auc_cpu > 0.55 and abs(auc_gpu - auc_cpu) <= 0.002, (auc_gpu, auc_cpu)
+    assert auc_cpu > 0.75 and abs(auc_gpu - auc_cpu) <= 0.002, (auc_gpu, auc_cpu)
 
 
 def _keys_world(rng, U, I, S, n):
