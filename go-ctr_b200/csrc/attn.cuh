@@ -211,6 +211,12 @@ template <bool PEER>
 __device__ __forceinline__ float* emb_ptr(const RowSrc& r, int idx) {
     return PEER ? r.peer_emb[idx & r.wmask] + (long)(idx >> r.wshift) * r.lde : const_cast<float*>(r.emb) + (long)idx * r.lde;
 }
+// read side of a sharded table: the replicated hot rows are local
+template <bool PEER>
+__device__ __forceinline__ const float* emb_src(const RowSrc& r, int idx) {
+    if (PEER && idx < r.hot_k) return r.hot_tab + (long)idx * r.lde;
+    return emb_ptr<PEER>(r, idx);
+}
 
 // PEER: ITEM_EMB (and ITEM_FEAT when large) are row-sharded over the GPUs of the box and every shard is mapped into
 // this process (CUDA IPC): the gather reads the owner's HBM directly over NVLink — the transfer is the load itself, so
@@ -264,7 +270,7 @@ k_attn_fwd_idx(RowSrc r, Dims d, const float* __restrict__ att, float* __restric
         cp_async_commit();
         float4 v[VPL], acc[VPL];
         float ny2 = 0.0f;
-        const float* ip = emb_ptr<PEER>(r, id.z >= 0 ? id.z : 0);
+        const float* ip = emb_src<PEER>(r, id.z >= 0 ? id.z : 0);
         float* cache_b = (PEER && r.rows_cache) ? r.rows_cache + (long)b * (d.S + 1) * DD : nullptr;    // predict keeps no rows
 #pragma unroll
         for (int q = 0; q < VPL; q++) {
@@ -278,7 +284,7 @@ k_attn_fwd_idx(RowSrc r, Dims d, const float* __restrict__ att, float* __restric
             const int s = s0 + sub;
             const int a0 = __shfl_sync(0xffffffffu, id.x, s & 31), a1 = __shfl_sync(0xffffffffu, id.y, s & 31);
             row = s < d.S ? (s < 32 ? a0 : a1) : -1;
-            const float* p = emb_ptr<PEER>(r, row >= 0 ? row : 0) + lir * 4;
+            const float* p = emb_src<PEER>(r, row >= 0 ? row : 0) + lir * 4;
 #pragma unroll
             for (int q = 0; q < VPL; q++) u[q] = row >= 0 ? (PEER ? ld4_peer(p + q * LPR * 4) : ldg4_stream(p + q * LPR * 4)) : zero4();
         };
@@ -695,7 +701,7 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
             if (s < d.S) {
                 const float e1 = c1 * sc, e2 = c2 * sc, e3 = c3 * sc;
                 float* dst = nullptr;
-                if (FUSED) { if (row >= 0) dst = (PEER ? emb_ptr<true>(r, row) : scatter_dst(r, d, o, row, rep)) + lir * 4; }
+                if (FUSED) { if (row >= 0) dst = ((PEER && row >= o.hot_rows) ? emb_ptr<true>(r, row) : scatter_dst(r, d, o, row, rep)) + lir * 4; }
                 else if (o.dUb) dst = o.dUb + ((long)b * d.S + s) * d.D + lir * 4;
 #pragma unroll
                 for (int q = 0; q < VPL; q++) {
@@ -726,7 +732,7 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
         }
         if (sub == 0) {
             float* dst = nullptr;
-            if (FUSED) { if (id.z >= 0) dst = (PEER ? emb_ptr<true>(r, id.z) : scatter_dst(r, d, o, id.z, rep)) + lir * 4; }
+            if (FUSED) { if (id.z >= 0) dst = ((PEER && id.z >= o.hot_rows) ? emb_ptr<true>(r, id.z) : scatter_dst(r, d, o, id.z, rep)) + lir * 4; }
             else if (o.dIt) dst = o.dIt + (long)b * d.D + lir * 4;
 #pragma unroll
             for (int q = 0; q < VPL; q++) {
@@ -768,6 +774,25 @@ k_hot_apply(float* __restrict__ emb, long lde, float* __restrict__ hot_acc, int 
             t.x = fmaf(neg_lr, s.x, t.x); t.y = fmaf(neg_lr, s.y, t.y); t.z = fmaf(neg_lr, s.z, t.z); t.w = fmaf(neg_lr, s.w, t.w);
             *e = t;
         }
+    }
+}
+
+// sharded tables, replicated hot rows: every rank copies rows [0, hot_k) from their owners' shards (once per table
+// generation), and writes its own rows back before the shard is read by the host (download / checkpoint)
+__global__ void __launch_bounds__(256)
+k_hot_pull(RowSrc r, float* __restrict__ hot_tab, int hot_k, int D) {
+    const int q4 = D / 4;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)hot_k * q4; i += (long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / q4), c = (int)(i % q4) * 4;
+        *reinterpret_cast<float4*>(hot_tab + (long)row * r.lde + c) = *reinterpret_cast<const float4*>(emb_ptr<true>(r, row) + c);
+    }
+}
+__global__ void __launch_bounds__(256)
+k_hot_writeback(float* __restrict__ shard, long lde, const float* __restrict__ hot_tab, int hot_k, int D, int world, int rank) {
+    const int q4 = D / 4;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)hot_k * q4; i += (long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / q4), c = (int)(i % q4) * 4;
+        if (row % world == rank) *reinterpret_cast<float4*>(shard + (long)(row / world) * lde + c) = *reinterpret_cast<const float4*>(hot_tab + (long)row * lde + c);
     }
 }
 

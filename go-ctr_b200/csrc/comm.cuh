@@ -9,7 +9,9 @@
 //    red.global.add.v4.f32 into the owner's row pre-scaled by -lr/world.  Two device-side barriers per step
 //    (flag exchange over peer memory) order the phases: nobody reads a row before every rank's update of the
 //    previous step has landed, nobody updates a row before every rank has finished reading.  Semantics =
-//    single-GPU training on the global batch with gradients taken at the step-start table.
+//    single-GPU training on the global batch with gradients taken at the step-start table.  The most popular rows
+//    (ids [0, 32768) by default, cfg.reserved[0]) are additionally replicated on every rank: local reads, gradient
+//    sums all-reduced — what a Zipf-distributed id stream needs.
 //  * replicated (tables <= 32 MB): every rank keeps the whole table, row gradients are summed into a
 //    table-shaped buffer and all-reduced with the dense gradients (NCCL), applied identically everywhere.
 //
@@ -49,6 +51,10 @@ struct Comm {
     int* h_err = nullptr; int* d_err = nullptr;       // pinned + mapped: set by a barrier that timed out
     float* rows_cache = nullptr; size_t rows_cache_cap = 0;   // [Bmax, S+1, D] rows fetched by the forward
     void* d_xchg = nullptr;                           // device staging of the handle all-gather
+    // replicated hot rows of a sharded ITEM_EMB: rows [0, hot_k) live on every rank (hot_tab), their -lr/world scaled
+    // gradient sums (hot_sum) are all-reduced with the dense gradients — a Zipf-popular row is neither pulled over
+    // NVLink by every sample nor hammered by every rank's red.add
+    int hot_k = 0; float* hot_tab = nullptr; float* hot_sum = nullptr; float* hot_acc = nullptr; int hot_reps = 0;
 };
 
 }  // namespace ctr

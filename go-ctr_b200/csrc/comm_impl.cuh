@@ -76,6 +76,8 @@ struct FdHdr { int rank, nfds; int which[3]; };
 
 void comm_sock_name(const Comm& cm, int rank, char* out, size_t n) { snprintf(out, n, "ctrb200.%016llx.%d", (unsigned long long)cm.job_hash, rank); }
 
+int comm_hot_setup(ctr_handle* h);
+
 int comm_close_peers(ctr_handle* h) {
     Comm& cm = h->comm;
     for (int j = 0; j < kMaxPeers; j++)
@@ -142,7 +144,37 @@ int comm_publish(ctr_handle* h) {
         if (!cm.peer_emb[j] || !cm.peer_arena[j] || (rec.has[1] && !cm.peer_ifeat[j])) return set_err(h, CTR_ESTATE, "rank %d published no shard", j);
     }
     cm.published_gen = h->tab_gen;
+    return comm_hot_setup(h);
+}
+
+// (re)builds this rank's replica of the hot rows from the owners' shards; collective through its caller
+int comm_hot_setup(ctr_handle* h) {
+    Comm& cm = h->comm;
+    const int D = h->cfg.D;
+    int want = h->cfg.reserved[0];
+    if (want == 0) want = 32768;
+    if (want < 0) want = 0;
+    want = (int)std::min<int64_t>(want, h->tab_rows[CTR_TABLE_ITEM_EMB]);
+    for (float** p : {&cm.hot_tab, &cm.hot_sum, &cm.hot_acc}) if (*p) { cudaFree(*p); *p = nullptr; }
+    cm.hot_k = want; cm.hot_reps = 0;
+    if (want == 0) return CTR_OK;
+    if (h->tab_ld[CTR_TABLE_ITEM_EMB] != D) return set_err(h, CTR_EINVAL, "replicated hot rows need D %% 4 == 0");
+    RET(dalloc(h, &cm.hot_tab, (size_t)want * D, false)); RET(dalloc(h, &cm.hot_sum, (size_t)want * D));
+    cm.hot_reps = (int)std::min<size_t>(16, std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)want * D * sizeof(float))));
+    RET(dalloc(h, &cm.hot_acc, (size_t)cm.hot_reps * want * D));
+    RowSrc r{}; r.lde = D; r.wmask = cm.world - 1; r.wshift = cm.wshift; r.world = cm.world;
+    for (int j = 0; j < cm.world; j++) r.peer_emb[j] = cm.peer_emb[j];
+    RET(launch(h, "hot_rows_pull", [&] { k_hot_pull<<<h->num_sms * 4, 256, 0, h->stream>>>(r, cm.hot_tab, want, D); }));
+    CU(h, cudaStreamSynchronize(h->stream));
     return CTR_OK;
+}
+// the owner's shard rows of the hot range are stale while training runs on the replicas: refresh this rank's own
+int comm_hot_writeback(ctr_handle* h) {
+    Comm& cm = h->comm;
+    if (cm.hot_k <= 0 || !cm.hot_tab || cm.published_gen != h->tab_gen) return CTR_OK;
+    return launch(h, "hot_rows_writeback", [&] {
+        k_hot_writeback<<<h->num_sms * 4, 256, 0, h->stream>>>(h->tab[CTR_TABLE_ITEM_EMB], h->tab_ld[CTR_TABLE_ITEM_EMB], cm.hot_tab, cm.hot_k, h->cfg.D, cm.world, cm.rank);
+    });
 }
 
 int comm_check(ctr_handle* h) {
@@ -181,6 +213,7 @@ RowSrc comm_src(ctr_handle* h, const int* d_user, const int* d_item, const int* 
     r.ifeat_sharded = h->tab_sharded[CTR_TABLE_ITEM_FEAT] ? 1 : 0;
     for (int j = 0; j < cm.world; j++) { r.peer_emb[j] = cm.peer_emb[j]; r.peer_ifeat[j] = cm.peer_ifeat[j]; }
     r.rows_cache = cache ? cm.rows_cache : nullptr;
+    r.hot_k = cm.hot_k; r.hot_tab = cm.hot_tab;
     return r;
 }
 
@@ -290,7 +323,8 @@ static int comm_init(ctr_handle* h, const void* id, int32_t id_bytes) {
 static void comm_destroy(ctr_handle* h) {
     Comm& cm = h->comm;
     comm_close_peers(h);
-    for (void* p : {(void*)cm.table_grad, (void*)cm.rows_cache, cm.d_xchg}) if (p) cudaFree(p);
+    for (void* p : {(void*)cm.table_grad, (void*)cm.rows_cache, cm.d_xchg, (void*)cm.hot_tab, (void*)cm.hot_sum, (void*)cm.hot_acc}) if (p) cudaFree(p);
+    cm.hot_tab = cm.hot_sum = cm.hot_acc = nullptr; cm.hot_k = 0;
     vmm_free(&cm.arena_vmm);
     if (cm.lsock >= 0) { close(cm.lsock); cm.lsock = -1; }
     if (cm.h_err) cudaFreeHost(cm.h_err);

@@ -116,6 +116,9 @@ struct RowSrc {
     float* peer_emb[kMaxPeers];
     const float* peer_ifeat[kMaxPeers];
     float* rows_cache;   // [B, S+1, D]: the forward keeps every fetched row for the backward (one NVLink pull per row)
+    // the hot_k most popular rows (ids [0, hot_k): keep rows ordered by popularity) are replicated on every rank:
+    // reads are local, their gradients are summed locally and all-reduced (comm.cuh)
+    int hot_k; const float* hot_tab;
 };
 
 struct Dims { int uP, S, D, cF, in; };

@@ -284,6 +284,11 @@ void launch_bwd_idx(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
 }
 template <bool PEER>
 void dispatch_fwd_idx(ctr_handle* h, const RowSrc& r, int B) {
+    if (PEER && h->cfg.D == 64) {     // NVLink: wider contiguous segments per load instruction (A/B switch CTR_PEER_FWD_MAP)
+        static const int map = getenv("CTR_PEER_FWD_MAP") ? atoi(getenv("CTR_PEER_FWD_MAP")) : 0;
+        if (map == 1) { launch_fwd_idx<8, 2, 8, PEER>(h, r, B); return; }
+        if (map == 2) { launch_fwd_idx<16, 1, 8, PEER>(h, r, B); return; }
+    }
     switch (h->cfg.D / 4) {
         case 4: launch_fwd_idx<4, 1, 8, PEER>(h, r, B); break;    case 8: launch_fwd_idx<4, 2, 8, PEER>(h, r, B); break;
         case 16: launch_fwd_idx<4, 4, 8, PEER>(h, r, B); break;
@@ -292,6 +297,10 @@ void dispatch_fwd_idx(ctr_handle* h, const RowSrc& r, int B) {
 }
 template <bool PEER>
 void dispatch_bwd_idx(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
+    if (PEER && h->cfg.D == 64) {
+        static const int map = getenv("CTR_PEER_BWD_MAP") ? atoi(getenv("CTR_PEER_BWD_MAP")) : 0;
+        if (map == 2) { launch_bwd_idx<16, 1, 8, PEER>(h, r, o, B); return; }
+    }
     switch (h->cfg.D / 4) {
         case 4: launch_bwd_idx<4, 1, 8, PEER>(h, r, o, B); break;    case 8: launch_bwd_idx<4, 2, 8, PEER>(h, r, o, B); break;
         // D = 64: 8 lanes x 2 float4 (128-byte contiguous red.add / load segments per row) measured faster than
@@ -670,9 +679,15 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         bo.scatter_base = o.table_grad ? o.table_grad : h->tab[CTR_TABLE_ITEM_EMB];
         const bool hot = bo.sgd && vec_ok(h, r) && !o.comm;
         if (hot) { RET(ensure_hot(h)); bo.hot_acc = h->hot_acc; bo.hot_rows = h->hot_rows; bo.hot_reps = h->hot_reps; }
+        const bool peer_hot = o.peer && bo.sgd && h->comm.hot_k > 0;
+        if (peer_hot) { bo.hot_acc = h->comm.hot_acc; bo.hot_rows = h->comm.hot_k; bo.hot_reps = h->comm.hot_reps; }
         // sharded tables: nobody's red.add may land in a row before every rank's forward has read it
         if (o.peer && bo.sgd) RET(comm_barrier(h));
         RET(attn_backward(h, r, bo, B));
+        if (peer_hot)      // replica accumulators of the replicated hot rows → this rank's gradient sum (all-reduced below)
+            RET(launch(h, "hot_rows_fold", [&] {
+                k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(h->comm.hot_sum, c.D, h->comm.hot_acc, h->comm.hot_k, h->comm.hot_reps, c.D, 1.0f);
+            }));
         if (hot && h->hot_rows > 0)
             RET(launch(h, "hot_rows_apply", [&] {
                 k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(bo.scatter_base, h->tab_ld[CTR_TABLE_ITEM_EMB], h->hot_acc,
@@ -682,7 +697,12 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
     }
     if (o.update) {
         const bool tg = o.table_grad && c.table_opt != CTR_TABLE_FROZEN;
-        if (o.comm || o.table_grad) RET(comm_allreduce_grads(h, tg ? o.table_grad : nullptr, tg ? o.table_grad_n : 0));
+        const bool ph = o.peer && c.table_opt != CTR_TABLE_FROZEN && h->comm.hot_k > 0;
+        if (o.comm || o.table_grad) RET(comm_allreduce_grads(h, tg ? o.table_grad : ph ? h->comm.hot_sum : nullptr, tg ? o.table_grad_n : ph ? (size_t)h->comm.hot_k * c.D : 0));
+        if (ph)
+            RET(launch(h, "hot_rows_apply", [&] {
+                k_apply_table_grad<<<h->num_sms * 8, 256, 0, h->stream>>>(h->comm.hot_tab, h->comm.hot_sum, (long)h->comm.hot_k * c.D / 4);
+            }));
         if (tg && c.table_opt == CTR_TABLE_ADAM) {
             RET(ensure_moments(h));
             const int t = (int)h->step + 1; const int ab = o.adam_batch > 0 ? o.adam_batch : B;
@@ -1076,6 +1096,7 @@ int ctr_table_download(ctr_handle* h, int which, float* rows, int64_t nrows, int
     if (!h->tab[which] || nrows != h->tab_rows[which] || width != h->tab_width[which]) return set_err(h, CTR_EINVAL, "table %d shape mismatch", which);
     CU(h, cudaSetDevice(h->dev));
     const bool shard = h->tab_sharded[which];
+    if (shard && which == CTR_TABLE_ITEM_EMB) RET(comm_hot_writeback(h));
     if (!shard) {
         CU(h, cudaMemcpy2DAsync(rows, (size_t)width * sizeof(float), h->tab[which], h->tab_ld[which] * sizeof(float), (size_t)width * sizeof(float), (size_t)nrows, cudaMemcpyDeviceToHost, h->stream));
     } else if (h->tab_local_rows[which] > 0) {   // fills only this rank's rows (row % world == rank)
@@ -1668,6 +1689,7 @@ int ctr_checkpoint_save(ctr_handle* h, const char* path) {
     if (!h || !path) return set_err(h, CTR_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CU(h, cudaSetDevice(h->dev));
+    if (h->tab_sharded[CTR_TABLE_ITEM_EMB]) RET(comm_hot_writeback(h));
     CU(h, cudaStreamSynchronize(h->stream));
     FILE* f = fopen(path, "wb");
     if (!f) return set_err(h, CTR_EIO, "checkpoint: cannot open %s for writing", path);
@@ -1810,6 +1832,40 @@ int ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, i
         CI(cudaMemcpyAsync(d_z, z.data(), sizeof(double) * (size_t)V, cudaMemcpyHostToDevice, st));
         CI(cudaMemcpyAsync(d_poff, poff.data(), sizeof(long long) * ((size_t)V + 1), cudaMemcpyHostToDevice, st));
         if (!pnode.empty()) { CI(cudaMemcpyAsync(d_pnode, pnode.data(), sizeof(int) * pnode.size(), cudaMemcpyHostToDevice, st)); CI(cudaMemcpyAsync(d_pcode, pcode.data(), pcode.size(), cudaMemcpyHostToDevice, st)); }
+        if (c.reserved[0] == 1) {
+            // sequential float64 parity mode (item2vec.cuh): one warp, the reference's single-goroutine order
+            double *d64_0 = nullptr, *d64_1 = nullptr, *d_lut64 = nullptr; float* d_out32 = nullptr;
+            std::vector<double> lut64(1000);
+            for (int i = 0; i < 1000; i++) { double e = std::exp(((double)i / 1000.0 * 2.0 - 1.0) * 6.0); lut64[(size_t)i] = e / (e + 1.0); }   // sigmoid_table.go:28-45
+            cudaError_t e1_ = cudaMalloc(&d64_0, sizeof(double) * (size_t)V * D), e2_ = cudaMalloc(&d64_1, sizeof(double) * (size_t)std::max(V - 1, 1) * D),
+                        e3_ = cudaMalloc(&d_lut64, sizeof(double) * 1000), e4_ = cudaMalloc(&d_out32, sizeof(float) * (size_t)V * D);
+            if (e1_ != cudaSuccess || e2_ != cudaSuccess || e3_ != cudaSuccess || e4_ != cudaSuccess) rc = set_err(nullptr, CTR_ENOMEM, "item2vec float64 tables");
+            if (rc == CTR_OK) {
+                cudaMemcpyAsync(d_lut64, lut64.data(), sizeof(double) * 1000, cudaMemcpyHostToDevice, st);
+                cudaMemsetAsync(d64_1, 0, sizeof(double) * (size_t)std::max(V - 1, 1) * D, st);
+                cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), st);
+                k_i2v_init64<<<prop.multiProcessorCount * 8, 256, 0, st>>>(d64_0, (long)V * D, D, c.seed); launches++;
+                I2vSeqArgs sa{}; sa.doc = d_doc; sa.nd = nd; sa.n_stream = (long)n; sa.z = d_z; sa.poff = d_poff; sa.pnode = d_pnode; sa.pcode = d_pcode;
+                sa.syn0 = d64_0; sa.syn1 = d64_1; sa.lut = d_lut64; sa.D = D; sa.W = W; sa.upd = c.update_lr_batch; sa.iters = c.iter;
+                sa.init_lr = (double)c.init_lr; sa.min_lr = (double)c.min_lr; sa.seed = c.seed; sa.counters = d_cnt;
+                cudaEventRecord(e0, st);
+                k_i2v_seq_f64<<<1, 32, 0, st>>>(sa); launches++;
+                cudaEventRecord(e1, st);
+                k_f64_to_f32_i2v<<<prop.multiProcessorCount * 8, 256, 0, st>>>(d64_0, d_out32, (long)V * D); launches++;
+                cudaMemcpyAsync(emb_out, d_out32, sizeof(float) * (size_t)V * D, cudaMemcpyDeviceToHost, st);
+                cudaMemcpyAsync(hc, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st);
+                if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = set_err(nullptr, CTR_ECUDA, "item2vec sequential mode: %s", cudaGetErrorString(cudaGetLastError()));
+                else {
+                    cudaEventElapsedTime(&ms_total, e0, e1);
+                    if (stats) {
+                        stats->doc_len = nd; stats->trained_positions = (int64_t)hc[0]; stats->pairs = (int64_t)hc[1]; stats->node_visits = (int64_t)hc[2];
+                        stats->algorithmic_bytes = 2.0 * D * 8.0 * ((double)hc[1] + (double)hc[2]); stats->ms_device = ms_total; stats->launches = launches;
+                    }
+                }
+            }
+            for (void* p : {(void*)d64_0, (void*)d64_1, (void*)d_lut64, (void*)d_out32}) if (p) cudaFree(p);
+            goto done;
+        }
         CI(cudaMemcpyToSymbolAsync(c_i2v_lut, lut.data(), sizeof(float) * 1000, 0, cudaMemcpyHostToDevice, st));
         CI(cudaMemsetAsync(d_syn1, 0, sizeof(float) * (size_t)(V - 1) * D, st));       // huffman.go:40
         CI(cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), st));

@@ -131,6 +131,93 @@ k_i2v_skipgram_hs(I2vArgs a) {
     }
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// Sequential float64 mode (ctr_i2v_config.reserved[0] = 1): ONE warp walks the document in order, float64 tables and
+// arithmetic, no staleness compensation, no hot-node aggregation — the reference's algorithm as a single goroutine
+// would run it (word2vec.go:198-221, model.go:48-78, optimizer.go:107-129), operation for operation: the dot product
+// is accumulated in element order, multiplications and additions are rounded separately (the CPU restatement is
+// built without FMA contraction), the sigmoid comes from the same 1000-entry table.  It exists for PARITY: on the same
+// tokens it reproduces oracle/i2v_oracle.c bit for bit (tests/test_gpu_i2v.py), which pins the device-side dictionary
+// filter, subsampling draws, window draws, Huffman paths, learning-rate schedule and update rule that the parallel
+// kernel above shares.  Throughput is irrelevant here (~10^5 tokens/s).
+// -------------------------------------------------------------------------------------------------------------------
+struct I2vSeqArgs {
+    const int* doc; long nd; long n_stream;
+    const double* z;
+    const long long* poff; const int* pnode; const unsigned char* pcode;
+    double* syn0; double* syn1; const double* lut;      // lut: 1000-entry sigmoid table in float64
+    int D, W, upd, iters;
+    double init_lr, min_lr;
+    uint32_t seed;
+    unsigned long long* counters;
+};
+__global__ void __launch_bounds__(32)
+k_i2v_seq_f64(I2vSeqArgs a) {
+    constexpr int MAXJ = 4;                              // D <= 128
+    const int lane = threadIdx.x;
+    const int D = a.D, nj = (D + 31) / 32;
+    unsigned long long n_tr = 0, n_pair = 0, n_node = 0;
+    double lr = a.init_lr;                               // w.currentlr persists across iterations
+    for (int iter = 0; iter < a.iters; iter++) {
+        long seen = 0;
+        for (long pos = 0; pos < a.nd; pos++) {
+            const int id = a.doc[pos];
+            const double u = (double)(mix64(a.seed, 200u + (uint32_t)iter, (uint64_t)pos) >> 11) * (1.0 / 9007199254740992.0);
+            if (a.z[id] > u) {                           // Subsampler.Trial, subsample.go:45-52
+                const int del = (int)(mix64(a.seed, 300u + (uint32_t)iter, (uint64_t)pos) % (uint64_t)a.W);
+                const long long p0 = a.poff[id]; const int np = (int)(a.poff[id + 1] - p0);
+                for (int aa = del; aa < a.W * 2 + 1 - del; aa++) {          // model.go:59-77
+                    if (aa == a.W) continue;
+                    const long cpos = pos - a.W + aa;
+                    if (cpos < 0 || cpos >= a.nd) continue;
+                    double* ctx = a.syn0 + (long)a.doc[cpos] * D;
+                    double c[MAXJ], tmp[MAXJ];
+#pragma unroll
+                    for (int j = 0; j < MAXJ; j++) { const int k = lane + 32 * j; c[j] = (j < nj && k < D) ? ctx[k] : 0.0; tmp[j] = 0.0; }
+                    n_pair++;
+                    for (int i = 0; i < np; i++) {                           // optimizer.go:113-128
+                        double* nvp = a.syn1 + (long)a.pnode[p0 + i] * D;
+                        double nv[MAXJ], prod[MAXJ];
+#pragma unroll
+                        for (int j = 0; j < MAXJ; j++) { const int k = lane + 32 * j; nv[j] = (j < nj && k < D) ? nvp[k] : 0.0; prod[j] = __dmul_rn(c[j], nv[j]); }
+                        double inner = 0.0;                                  // element order k = 0 .. D-1, like the scalar loop
+                        for (int k = 0; k < D; k++) {
+                            const int j = k >> 5;
+                            const double pj = j == 0 ? prod[0] : j == 1 ? prod[1] : j == 2 ? prod[2] : prod[3];
+                            inner = __dadd_rn(inner, __shfl_sync(0xffffffffu, pj, k & 31));
+                        }
+                        if (inner <= -6.0 || inner >= 6.0) break;            // `return`: abandons the rest of the path
+                        const double g = __dmul_rn(__dadd_rn(__dadd_rn(1.0, -(double)a.pcode[p0 + i]), -a.lut[(int)((inner + 6.0) * (1000.0 / 6.0 / 2.0))]), lr);
+#pragma unroll
+                        for (int j = 0; j < MAXJ; j++) {
+                            const int k = lane + 32 * j;
+                            if (j < nj && k < D) { tmp[j] = __dadd_rn(tmp[j], __dmul_rn(g, nv[j])); nvp[k] = __dadd_rn(nv[j], __dmul_rn(g, c[j])); }
+                        }
+                        n_node++;
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int j = 0; j < MAXJ; j++) { const int k = lane + 32 * j; if (j < nj && k < D) ctx[k] = __dadd_rn(c[j], tmp[j]); }
+                    __syncwarp();
+                }
+                n_tr++;
+            }
+            seen++;                                      // observe(), word2vec.go:223-233
+            if (seen % a.upd == 0) lr = lr < a.min_lr ? a.min_lr : a.init_lr * (1.0 - (double)seen / (double)a.n_stream);
+        }
+    }
+    if (lane == 0) { a.counters[0] = n_tr; a.counters[1] = n_pair; a.counters[2] = n_node; }
+}
+__global__ void k_i2v_init64(double* __restrict__ syn0, long n, int D, uint32_t seed) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const double u = (double)(mix64(seed, 100u, (uint64_t)i) >> 11) * (1.0 / 9007199254740992.0);
+        syn0[i] = (u - 0.5) / (double)D;
+    }
+}
+__global__ void k_f64_to_f32_i2v(const double* __restrict__ a, float* __restrict__ b, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) b[i] = (float)a[i];
+}
+
 // syn0 = (U[0,1) - 0.5) / dim (word2vec.go:103-111) with the counter RNG
 __global__ void k_i2v_init(float* __restrict__ syn0, long n, int D, uint32_t seed) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {

@@ -3,6 +3,9 @@
     embedding.TrainEmbedding(inputCh, window, dim, iter)        wordemb.go:9-32
     model.GenEmbeddingMap32() map[string][]float32              word2vec.go:298-324
 
+    vector.Save(f, dic, mat, ...)  word2vec text format           model/modelutil/vector/vector.go:40-67
+    emb.Load(r) / parse / parseLine → []Embedding{Word,Dim,Vector,Norm}   emb/embedding.go:73-131
+
 The channel carries one WORD per message (cpsutil.ReadWord, cpsutil.go:46-53); ids are assigned by first
 appearance (dictionary.Add, dictionary.go:70-81)."""
 import ctypes as C
@@ -11,7 +14,8 @@ import numpy as np
 
 from . import engine as _e
 
-__all__ = ["i2v_paths", "I2vConfig", "I2vStats", "i2v_default_config", "i2v_train_ids", "TrainEmbedding", "EmbeddingModel"]
+__all__ = ["i2v_paths", "I2vConfig", "I2vStats", "i2v_default_config", "i2v_train_ids", "TrainEmbedding", "EmbeddingModel",
+           "Embedding", "SaveVectors", "LoadVectors", "ParseLine"]
 
 
 class I2vConfig(C.Structure):
@@ -82,3 +86,60 @@ def TrainEmbedding(inputCh, window, dim, iter, **kw):
         toks.append(i)
     emb, st = i2v_train_ids(np.asarray(toks, np.int32), len(id2word), window=window, dim=dim, iter=iter, **kw)
     return EmbeddingModel(id2word, emb, st)
+
+
+# ---- the word2vec text format the reference saves / loads its vectors in -------------------------------------
+class Embedding:
+    """emb.Embedding (emb/embedding.go:27-32): Word, Dim, Vector (float64), Norm = sqrt(sum v^2) (embutil.Norm)."""
+
+    def __init__(self, Word, Vector):
+        self.Word = Word
+        self.Vector = np.asarray(Vector, np.float64)
+        self.Dim = int(self.Vector.size)
+        n = 0.0
+        for v in self.Vector:                      # embutil/embutil.go: sequential float64 sum
+            n += float(v) * float(v)
+        self.Norm = float(np.sqrt(n))
+
+    def Validate(self):                            # embedding.go:34-43
+        if self.Word == "":
+            raise ValueError("word must not be empty")
+        if self.Dim == 0:
+            raise ValueError("Dim of %s is zero" % self.Word)
+
+    def __eq__(self, o):
+        return (self.Word, self.Dim, self.Norm) == (o.Word, o.Dim, o.Norm) and np.array_equal(self.Vector, o.Vector)
+
+
+def ParseLine(line):
+    """emb.parseLine (embedding.go:107-131): whitespace-separated fields, the first is the word."""
+    fields = line.split()
+    if len(fields) < 2:
+        raise ValueError("Must be over 2 lenghth for word and vector elems")
+    return Embedding(fields[0], [float(x) for x in fields[1:]])
+
+
+def LoadVectors(r):
+    """emb.Load (embedding.go:73-105): one embedding per line; lines that START WITH A SPACE are skipped; every vector
+    must be non-empty.  r: iterable of lines, a file object, or one string."""
+    lines = r.splitlines() if isinstance(r, str) else r
+    out = []
+    for line in lines:
+        line = line.rstrip("\r\n")
+        if line.startswith(" "):
+            continue
+        e = ParseLine(line)
+        e.Validate()
+        out.append(e)
+    if out and any(e.Dim != out[0].Dim for e in out):      # Embeddings.Validate, :61-71
+        raise ValueError("dimension for all vectors must be the same")
+    return out
+
+
+def SaveVectors(f, words, mat):
+    """vector.Save (vector.go:40-67): per word `word ` then every element as `%f ` (six decimals, trailing space), newline."""
+    mat = np.asarray(mat)
+    if len(words) != mat.shape[0]:
+        raise ValueError("different for length of dic and row of matrix: %d, %d" % (len(words), mat.shape[0]))
+    for w, row in zip(words, mat):
+        f.write("%s " % w + "".join("%f " % float(v) for v in row) + "\n")

@@ -54,3 +54,26 @@ def test_train_embedding_mirror_and_dims():
         assert emb.shape == (50, d) and np.isfinite(emb).all() and st.trained_positions > 0
     with pytest.raises(g.CtrError):
         g.i2v_train_ids(np.zeros(10, np.int32), 5, dim=12)                   # not a power of two
+
+
+@pytest.mark.parametrize("dim", [16, 64])
+def test_sequential_float64_mode_reproduces_the_oracle_bit_for_bit(dim):
+    """cfg.reserved[0] = 1: one warp walks the document in order with float64 tables — the reference's algorithm as a
+    single goroutine runs it (word2vec.go:198-221, model.go:48-78, optimizer.go:107-129).  Same tokens, same counter-RNG
+    draws: the embeddings equal oracle/i2v_oracle.c's exactly, which pins the MinCount filter, subsampling, window
+    draws, Huffman paths, lr schedule and update rule the parallel kernel shares."""
+    rng = np.random.default_rng(12)
+    toks, remap, nc, per = planted_corpus(rng, n_clusters=5, per=8, n_users=60, seq=40)
+    V = nc * per + 3
+    toks = np.concatenate([toks, [V - 1, V - 2, V - 1]]).astype(np.int32)      # rare words: filtered from the document
+    cfg = g.i2v_default_config(dim=dim, window=5, iter=2, seed=21, update_lr_batch=500)
+    cfg.reserved[0] = 1
+    emb, st = g.i2v_train_ids(toks, V, cfg=cfg)
+    ocfg = orc.i2v_cfg(dim=dim, window=5, iters=2, seed=21, rng_mode=1)
+    ocfg.update_lr_batch = 500
+    # the C ABI carries init_lr / min_lr / subsample as float32: give the float64 oracle the same values
+    ocfg.init_lr = float(np.float32(cfg.init_lr)); ocfg.min_lr = float(np.float32(cfg.min_lr)); ocfg.subsample = float(np.float32(cfg.subsample))
+    oemb, otrained = orc.i2v_train(ocfg, toks, V)
+    assert st.trained_positions == otrained and st.doc_len == toks.size - 3
+    assert np.abs(emb - orc.i2v_train(orc.i2v_cfg(dim=dim, window=5, iters=1, seed=21, rng_mode=1), toks, V)[0]).max() > 1e-4   # training moved them
+    assert emb.tobytes() == oemb.tobytes()

@@ -1,7 +1,8 @@
-"""Two-rank NCCL test of both ITEM_EMB placements (row-sharded with the all-to-all exchange; replicated with
-gradient all-reduce)  (needs >= 2 GPUs: `gpurun --gpus 2`): a step on 2 GPUs with
-per-GPU batch B == a step on 1 GPU with batch 2B (same samples), for scores, cost, dense weights and the
-updated embedding table."""
+"""Two-rank test of the ITEM_EMB placements (needs >= 2 GPUs: `gpurun --gpus 2`): row-sharded with every lookup
+served from the owner's HBM over NVLink peer mappings; the same with the most popular rows replicated on every rank;
+replicated with gradient all-reduce.  A step on 2 GPUs with per-GPU batch B == a step on 1 GPU with batch 2B (same
+samples), for scores, cost, dense weights and the updated embedding table; plus the pipelined epoch entry with a ragged
+tail on the sharded path."""
 import os
 import socket
 
@@ -29,7 +30,7 @@ def _data():
     return uf, itf, emb, batches
 
 
-def _worker(rank, world, port, out_dir, policy):
+def _worker(rank, world, port, out_dir, policy, hot):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -38,6 +39,7 @@ def _worker(rank, world, port, out_dir, policy):
     cfg = g.engine.default_config(g.MODEL_DIN_COS, batch=B, pred_batch=B, table_opt=g.TABLE_SGD, table_lr=0.7, dropout0=0.0, dropout1=0.0,
                                   seed=3, device=rank, rank=rank, world=world, **DIMS)
     cfg.reserved[1] = policy                  # 1 = shard rows, 2 = replicate the table (auto would replicate: 13 KB)
+    cfg.reserved[0] = hot                     # sharded: rows [0, hot) replicated on every rank (-1: none)
     eng = g.Engine(cfg)
     ids = [eng.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
@@ -45,8 +47,11 @@ def _worker(rank, world, port, out_dir, policy):
     eng.table_upload(g.TABLE_USER_FEAT, uf); eng.table_upload(g.TABLE_ITEM_FEAT, itf); eng.table_upload(g.TABLE_ITEM_EMB, emb)
     costs = []
     sl = slice(rank * B, (rank + 1) * B)
-    for ur, ir, hist, y in batches:
-        costs.append(eng.train_step_idx(ur[sl], ir[sl], hist[sl], y[sl]).cost)
+    for k, (ur, ir, hist, y) in enumerate(batches):
+        if k < STEPS - 1:
+            costs.append(eng.train_step_idx(ur[sl], ir[sl], hist[sl], y[sl]).cost)
+        else:           # the last batch goes through the epoch entry point (pageable buffers, pinned ring) — collective too
+            costs.append(float(eng.train_idx(ur[sl], ir[sl], hist[sl], y[sl])[0]))
     ur, ir, hist, y = batches[0]
     p = eng.predict_idx(ur[sl], ir[sl], hist[sl])
     np.save(os.path.join(out_dir, "p%d.npy" % rank), p)
@@ -58,13 +63,13 @@ def _worker(rank, world, port, out_dir, policy):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("policy", [1, 2], ids=["sharded", "replicated"])
-def test_two_gpu_step_equals_single_gpu_global_batch(tmp_path, policy):
+@pytest.mark.parametrize("policy,hot", [(1, -1), (1, 64), (2, 0)], ids=["sharded_peer", "sharded_hot_rows", "replicated"])
+def test_two_gpu_step_equals_single_gpu_global_batch(tmp_path, policy, hot):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), policy), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), policy, hot), nprocs=world, join=True)
     uf, itf, emb, batches = _data()
     cfg = g.engine.default_config(g.MODEL_DIN_COS, batch=2 * B, pred_batch=2 * B, table_opt=g.TABLE_SGD_DETERMINISTIC, table_lr=0.7,
                                   dropout0=0.0, dropout1=0.0, seed=3, **DIMS)
