@@ -462,7 +462,7 @@ def main():
         # (b) ids
         from tests.util import make_batch
         ur, ir, hist, y = make_batch(rng, U, I, n, S, pad_frac=0.2, zipf=w["zipf"])
-        eng.train_idx(ur[:2 * B], ir[:2 * B], hist[:2 * B], y[:2 * B])            # warm (allocates the ring)
+        eng.train_idx(ur, ir, hist, y)                                              # warm pass: the ring, the per-call buffers
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -483,7 +483,12 @@ def main():
         eng.ubcache_upload(off, ts, items.astype(np.int32))
         su = rng.integers(0, U, n); si = ((rng.zipf(1.05, n) - 1) % I) if w["zipf"] else rng.integers(0, I, n)
         k_user = uid[su]; k_item = iid[si]; k_ts = rng.integers(1000, (L + 1) * 1000, n).astype(np.int64)
-        eng.train_keys(k_user[:2 * B], k_item[:2 * B], k_ts[:2 * B], y[:2 * B])
+        eng.train_keys(k_user, k_item, k_ts, y, epochs=1)                           # warm pass: resident sample arrays of this size
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        eng.train_keys(k_user, k_item, k_ts, y, epochs=0)                           # GetSample only (resolve + compact on the device)
+        dt_resolve = time.perf_counter() - t0
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -493,7 +498,7 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         out["keys"] = dict(value=used * world / dt, unit="samples/s", h2d_bytes_per_step=int(B * 28), d2h_bytes_per_step=8,
                            ms_per_step=1e3 * dt / steps, last_cost=float(cost), entry="ctr_train_keys", host_memory="pageable (numpy)",
-                           rows_used=int(used))
+                           rows_used=int(used), resolve_ms=1e3 * dt_resolve)
         return out
 
     def parity_block():

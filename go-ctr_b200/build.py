@@ -23,10 +23,16 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO, os.path.join(SRC, "engine.cu")]
+    tmp = SO + ".tmp.%d" % os.getpid()          # built aside and renamed: a snapshot of the tree never sees a half-written library
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(SRC, "engine.cu")]
     if verbose:
         print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    try:
+        subprocess.check_call(cmd)
+        os.replace(tmp, SO)
+    finally:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
     return SO
 
 

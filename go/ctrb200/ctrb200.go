@@ -272,3 +272,100 @@ func (d *Impl) Predict(X tensor.Tensor) tensor.Tensor {
 	}
 	return tensor.NewDense(tensor.Float32, tensor.Shape{numPred, 1}, tensor.WithBacking(y))
 }
+
+// TrainKeys is recommend.Train's sample path (rcmd.go:197-246) on the device: the samples go down as keys (28 bytes
+// each), GetSample's assembly (id maps, drop-unknown, history window at the sample's timestamp; rcmd.go:339-460) and
+// model.Train's epoch loop run in HBM.  Needs LoadIDMaps (and UploadUserBehavior for DIN's history).
+func (e *Engine) TrainKeys(samples []rcmd.Sample, epochs, earlyStop int) (lastCost float32, rowsUsed int64, err error) {
+	n := len(samples)
+	u, it, ts, y := make([]int64, n), make([]int64, n), make([]int64, n), make([]float32, n)
+	for i, s := range samples {
+		u[i], it[i], ts[i], y[i] = int64(s.UserId), int64(s.ItemId), s.Timestamp, s.Label
+	}
+	var cost C.float
+	var ran C.int32_t
+	var used C.int64_t
+	rc := C.ctr_train_keys(e.h, i64(u), i64(it), i64(ts), f32(y), C.int64_t(n), C.int32_t(epochs), C.int32_t(earlyStop), &cost, &ran, &used)
+	return float32(cost), int64(used), e.err(rc)
+}
+
+// SetTableOptimizer selects how embedding rows learn (engine extension; the reference keeps them frozen,
+// din.go:161-169): C.CTR_TABLE_FROZEN | SGD | SGD_DETERMINISTIC | ADAM.  Call before NewEngine's ctr_create in a
+// custom constructor, or use NewEngineWith.
+func NewEngineWith(kind Kind, uP, S, D, cF, batchSize, predBatchSize, tableOpt int, tableLr float32) (*Engine, error) {
+	e := &Engine{}
+	C.ctr_config_default(&e.cfg, C.int(kind))
+	e.cfg.uP, e.cfg.S, e.cfg.D, e.cfg.cF = C.int32_t(uP), C.int32_t(S), C.int32_t(D), C.int32_t(cF)
+	e.cfg.batch, e.cfg.pred_batch = C.int32_t(batchSize), C.int32_t(predBatchSize)
+	e.cfg.table_opt, e.cfg.table_lr = C.int32_t(tableOpt), C.float(tableLr)
+	if rc := C.ctr_create(&e.cfg, &e.h); rc != C.CTR_OK {
+		return nil, fmt.Errorf("ctr_create: %d: %s", int(rc), C.GoString(C.ctr_last_error(nil)))
+	}
+	runtime.SetFinalizer(e, func(e *Engine) { e.Close() })
+	return e, nil
+}
+
+// ---- model/mlp: drop-in for mlp.SimpleMlpFitWrap / SimpleMlpPredWrap (model/mlp/mlp.go:11-65) -----------------
+
+// MlpFitWrap satisfies recommend.Fitter like mlp.SimpleMlpFitWrap{Model: nn.NewMLPClassifier([]int{100}, "relu",
+// "adam", 1e-4)} (main.go:42-52): float32 TrainSample in, float64 training on the device.
+type MlpFitWrap struct {
+	Hidden      []int   // HiddenLayerSizes, default {100}
+	Activation  int     // C.CTR_MLP_RELU (default) | CTR_MLP_LOGISTIC | CTR_MLP_IDENTITY
+	Alpha       float64 // 1e-4
+	MaxIter     int     // 200
+	Adaptive    bool    // LearningRate == "adaptive"
+	Seed        uint32
+}
+
+// MlpPredWrap satisfies recommend.PredictAbstract like mlp.SimpleMlpPredWrap.
+type MlpPredWrap struct {
+	m     *C.ctr_mlp
+	xcols int
+}
+
+func (f *MlpFitWrap) Fit(trainSample *rcmd.TrainSample) (rcmd.PredictAbstract, error) {
+	var cfg C.ctr_mlp_config
+	C.ctr_mlp_config_default(&cfg, C.int32_t(trainSample.XCols))
+	if len(f.Hidden) > 0 {
+		cfg.n_layers = C.int32_t(len(f.Hidden) + 2)
+		for i, u := range f.Hidden {
+			cfg.units[i+1] = C.int32_t(u)
+		}
+		cfg.units[len(f.Hidden)+1] = 1
+	}
+	cfg.hidden_act = C.int32_t(f.Activation)
+	if f.Alpha != 0 {
+		cfg.alpha = C.double(f.Alpha)
+	}
+	if f.MaxIter != 0 {
+		cfg.max_iter = C.int32_t(f.MaxIter)
+	}
+	if f.Adaptive {
+		cfg.adaptive = 1
+	}
+	cfg.seed = C.uint32_t(f.Seed)
+	var m *C.ctr_mlp
+	if rc := C.ctr_mlp_create(&cfg, &m); rc != C.CTR_OK {
+		return nil, fmt.Errorf("ctr_mlp_create: %d: %s", int(rc), C.GoString(C.ctr_mlp_last_error(nil)))
+	}
+	var iters C.int32_t
+	if rc := C.ctr_mlp_fit(m, f32(trainSample.X), f32(trainSample.Y), C.int64_t(trainSample.Rows), C.int32_t(trainSample.XCols), &iters, nil); rc != C.CTR_OK {
+		err := fmt.Errorf("ctr_mlp_fit: %d: %s", int(rc), C.GoString(C.ctr_mlp_last_error(m)))
+		C.ctr_mlp_destroy(m)
+		return nil, err
+	}
+	p := &MlpPredWrap{m: m, xcols: trainSample.XCols}
+	runtime.SetFinalizer(p, func(p *MlpPredWrap) { C.ctr_mlp_destroy(p.m) })
+	return p, nil
+}
+
+// Predict follows SimpleMlpPredWrap.Predict (mlp.go:15-39), including nil on failure.
+func (p *MlpPredWrap) Predict(X tensor.Tensor) tensor.Tensor {
+	n := X.Shape()[0]
+	y := make([]float32, n)
+	if rc := C.ctr_mlp_predict(p.m, f32(X.Data().([]float32)), C.int64_t(n), C.int32_t(p.xcols), f32(y)); rc != C.CTR_OK {
+		return nil
+	}
+	return tensor.NewDense(tensor.Float32, tensor.Shape{n, 1}, tensor.WithBacking(y))
+}
