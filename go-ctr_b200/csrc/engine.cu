@@ -15,6 +15,7 @@
 #include <nvtx3/nvToolsExt.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -290,8 +291,11 @@ void launch_bwd_idx(ctr_handle* h, const RowSrc& r, const BwdOut& o, int B) {
 }
 template <bool PEER>
 void dispatch_fwd_idx(ctr_handle* h, const RowSrc& r, int B) {
-    if (PEER && h->cfg.D == 64) {     // NVLink: wider contiguous segments per load instruction (A/B switch CTR_PEER_FWD_MAP)
-        static const int map = getenv("CTR_PEER_FWD_MAP") ? atoi(getenv("CTR_PEER_FWD_MAP")) : 0;
+    if (PEER && h->cfg.D == 64) {
+        // over NVLink the request size matters more than the shuffle count: 8 lanes x 2 float4 (128-byte contiguous
+        // segments per load instruction) gathers at 582 GB/s, the local kernels' 4 x 4 mapping (64-byte segments) at
+        // 465 GB/s, 16 x 1 (256-byte) at 494 GB/s (profiles/r02/shard_time_2gpu_maps.log).  CTR_PEER_FWD_MAP: 0 = 4x4, 2 = 16x1.
+        static const int map = getenv("CTR_PEER_FWD_MAP") ? atoi(getenv("CTR_PEER_FWD_MAP")) : 1;
         if (map == 1) { launch_fwd_idx<8, 2, 8, PEER>(h, r, B); return; }
         if (map == 2) { launch_fwd_idx<16, 1, 8, PEER>(h, r, B); return; }
     }
@@ -874,50 +878,54 @@ void gaussian_fill(std::vector<float>& w, uint32_t seed, uint32_t stream) {
 
 // item2vec host plan: Huffman tree as dictionary.HuffnamTree builds it (huffman.go:23-57) and every word's
 // root→leaf path as Node.GetPath(maxDepth) returns it (node.go:26-43), as a CSR of (inner node, child code).
+// dictionary.HuffnamTree (huffman.go:23-57) over leaves already in stable count order (`leaves` = word ids sorted by
+// count, ties in id order): merged nodes are created in non-decreasing value order and inserted before every queued
+// node of equal value, so they win ties and equal-valued merged nodes pop newest-first.  O(V).
+// parent / code are indexed by tree node (leaves [0,V), inner nodes V + creation index); node_val [V-1].
+static void i2v_huffman_sorted(const int64_t* cnt_by_word, const int* leaves, int V, std::vector<int>& parent, std::vector<unsigned char>& code,
+                               std::vector<long long>& node_val) {
+    parent.assign((size_t)2 * V - 1, -1); code.assign((size_t)2 * V - 1, 0); node_val.assign((size_t)std::max(V - 1, 1), 0);
+    // merged queue as runs of equal value; inside a run the newest node pops first, runs are in non-decreasing value order
+    std::vector<long long> run_val; std::vector<int> run_begin, run_top;      // run r holds ids mq[run_begin[r] .. run_top[r])
+    std::vector<int> mq; mq.reserve((size_t)V);
+    size_t rh = 0, lh = 0; int next_id = V;
+    for (int made = 0; made < V - 1; made++) {
+        long long pv[2]; int pid[2];
+        for (int k = 0; k < 2; k++) {
+            while (rh + 1 < run_val.size() && run_top[rh] == run_begin[rh]) rh++;          // never step past the last run: it may refill
+            const bool have_m = rh < run_val.size() && run_top[rh] > run_begin[rh];
+            const bool use_m = have_m && (lh >= (size_t)V || run_val[rh] <= cnt_by_word[leaves[lh]]);
+            if (use_m) { pv[k] = run_val[rh]; pid[k] = mq[(size_t)--run_top[rh]]; if (rh + 1 == run_val.size()) mq.resize((size_t)run_top[rh]); }
+            else { pv[k] = cnt_by_word[leaves[lh]]; pid[k] = leaves[lh]; lh++; }
+        }
+        const long long val = pv[0] + pv[1]; const int id = next_id++;
+        node_val[(size_t)(id - V)] = val;
+        code[(size_t)pid[0]] = 0; code[(size_t)pid[1]] = 1; parent[(size_t)pid[0]] = id; parent[(size_t)pid[1]] = id;
+        if (!run_val.empty() && run_val.back() == val && run_top.back() == (int)mq.size()) { mq.push_back(id); run_top.back() = (int)mq.size(); }
+        else if (!run_val.empty() && run_top.back() == run_begin.back() && run_top.back() == (int)mq.size()) {      // reuse the emptied last run
+            run_val.back() = val; mq.push_back(id); run_top.back() = (int)mq.size();
+        } else { run_val.push_back(val); run_begin.push_back((int)mq.size()); mq.push_back(id); run_top.push_back((int)mq.size()); }
+    }
+}
+
+// item2vec host plan (CPU-only entry ctr_i2v_paths): Huffman tree + every word's root→leaf path as Node.GetPath(maxDepth)
+// returns it (node.go:26-43), as a CSR of (inner node, child code).
 static void i2v_build_paths(const std::vector<int64_t>& cnt, int V, int max_depth, std::vector<int64_t>& node_val,
                             std::vector<long long>& poff, std::vector<int>& pnode, std::vector<unsigned char>& pcode) {
-    node_val.assign((size_t)V - 1, 0);
+    std::vector<int> leaves((size_t)V);
+    for (int i = 0; i < V; i++) leaves[(size_t)i] = i;
+    std::stable_sort(leaves.begin(), leaves.end(), [&](int x, int y) { return cnt[(size_t)x] < cnt[(size_t)y]; });
+    std::vector<int> parent; std::vector<unsigned char> code; std::vector<long long> nv;
+    i2v_huffman_sorted(cnt.data(), leaves.data(), V, parent, code, nv);
+    node_val.assign(nv.begin(), nv.begin() + std::max(V - 1, 0));
     poff.assign((size_t)V + 1, 0); pnode.clear(); pcode.clear();
-    ctr_config dummy; (void)dummy;
-    struct { int max_depth; } c{max_depth};
-    // Huffman (huffman.go:23-57): stable order by count; merged nodes are created in non-decreasing value
-    // order and inserted before every queued node of equal value, so they win ties and equal-valued merged
-    // nodes pop newest-first
-    std::vector<int> parent((size_t)2 * V - 1, -1); std::vector<unsigned char> code((size_t)2 * V - 1, 0);
-    {
-        std::vector<int> leaves((size_t)V);
-        for (int i = 0; i < V; i++) leaves[(size_t)i] = i;
-        std::stable_sort(leaves.begin(), leaves.end(), [&](int x, int y) { return cnt[(size_t)x] < cnt[(size_t)y]; });
-        // merged queue as runs of equal value; inside a run the newest node pops first (it was inserted
-        // before the older equal-valued ones), runs themselves are in non-decreasing value order
-        struct Run { int64_t val; std::vector<int> ids; };
-        std::vector<Run> runs; size_t rh = 0;
-        size_t lh = 0; int next_id = V;
-        for (int made = 0; made < V - 1; made++) {
-            std::pair<int64_t, int> pick[2];
-            for (int k = 0; k < 2; k++) {
-                while (rh + 1 < runs.size() && runs[rh].ids.empty()) rh++;          // never step past the last run: it may refill
-                const bool use_m = rh < runs.size() && !runs[rh].ids.empty() && (lh >= (size_t)V || runs[rh].val <= cnt[(size_t)leaves[lh]]);
-                if (use_m) { pick[k] = {runs[rh].val, runs[rh].ids.back()}; runs[rh].ids.pop_back(); }
-                else { pick[k] = {cnt[(size_t)leaves[lh]], leaves[lh]}; lh++; }
-            }
-            const int64_t val = pick[0].first + pick[1].first; const int id = next_id++;
-            node_val[(size_t)(id - V)] = val;
-            code[(size_t)pick[0].second] = 0; code[(size_t)pick[1].second] = 1;
-            parent[(size_t)pick[0].second] = id; parent[(size_t)pick[1].second] = id;
-            if (!runs.empty() && runs.back().val == val) runs.back().ids.push_back(id);
-            else runs.push_back(Run{val, {id}});
-        }
-    }
-    {
-        std::vector<int> chain;
-        for (int w = 0; w < V; w++) {                      // Node.GetPath(maxDepth), node.go:26-43
-            chain.clear();
-            for (int p = w; p != -1; p = parent[(size_t)p]) chain.push_back(p);
-            const int len = (int)chain.size(), depth = std::min(c.max_depth, len);
-            for (int i = 0; i < depth - 1; i++) { pnode.push_back(chain[(size_t)(len - 1 - i)] - V); pcode.push_back(code[(size_t)chain[(size_t)(len - 2 - i)]]); }
-            poff[(size_t)w + 1] = (long long)pnode.size();
-        }
+    std::vector<int> chain;
+    for (int w = 0; w < V; w++) {                          // Node.GetPath(maxDepth), node.go:26-43
+        chain.clear();
+        for (int p = w; p != -1; p = parent[(size_t)p]) chain.push_back(p);
+        const int len = (int)chain.size(), depth = std::min(max_depth, len);
+        for (int i = 0; i < depth - 1; i++) { pnode.push_back(chain[(size_t)(len - 1 - i)] - V); pcode.push_back(code[(size_t)chain[(size_t)(len - 2 - i)]]); }
+        poff[(size_t)w + 1] = (long long)pnode.size();
     }
 }
 
@@ -1796,49 +1804,116 @@ void ctr_i2v_config_default(ctr_i2v_config* c) {
     c->seed = 0; c->device = 0;
 }
 
-int ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, int32_t V, float* emb_out, ctr_i2v_stats* stats) {
-    if (!cfg || !tokens || !emb_out || n < 1 || V < 2) return set_err(nullptr, CTR_EINVAL, "bad item2vec arguments");
+namespace {
+struct I2vDist { int rank = 0, world = 1; void* nccl = nullptr; long sync_every = 0; };
+
+// embedding.TrainEmbedding on the device.  Stream-proportional work (dictionary counts, MinCount filter) and the
+// per-word Huffman paths are built on the GPU; the host only runs the O(V) two-queue Huffman merge over the
+// count-sorted leaves.  dist (world > 1): every rank trains on its own shard of the stream with a full replica of
+// both vector tables; dictionary counts are all-reduced (identical tree everywhere) and the replicas are averaged
+// every sync_every positions (local SGD / model averaging — the reference's own trainer is Hogwild over goroutines,
+// word2vec.go:165-169; across GPUs the racy shared memory becomes periodic averaging).
+int i2v_train_impl(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, int32_t V, float* emb_out, ctr_i2v_stats* stats, I2vDist* dist) {
+    if (!cfg || !tokens || !emb_out || n < 1 || V < 2 || n > 0x7fffffffLL) return set_err(nullptr, CTR_EINVAL, "bad item2vec arguments");
     const ctr_i2v_config& c = *cfg;
     const int D = c.dim, W = c.window;
     if (D < 4 || D > 128 || (D & (D - 1)) || W < 1 || c.iter < 1 || c.max_depth < 2 || c.update_lr_batch < 1)
         return set_err(nullptr, CTR_EINVAL, "item2vec: dim must be a power of two in [4,128], window/iter >= 1");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_err(nullptr, CTR_ENODEV, "no CUDA device: this engine has no CPU fallback"); }
+    const int world = dist ? dist->world : 1;
+    const bool seq = c.reserved[0] == 1;
+    if (seq && world > 1) return set_err(nullptr, CTR_EINVAL, "the sequential float64 mode is single-GPU");
 #define CI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = set_err(nullptr, CTR_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); goto done; } } while (0)
+#define CN(call) do { int r_ = (call); if (r_ != 0) { rc = set_err(nullptr, CTR_ECOMM, "%s: %s", #call, g_nccl.GetErrorString(r_)); goto done; } } while (0)
     int rc = CTR_OK;
-    // ---- host: dictionary counts, MinCount filter, subsample thresholds, Huffman paths
-    std::vector<int64_t> cnt((size_t)V, 0);
-    for (int64_t i = 0; i < n; i++) { if (tokens[i] < 0 || tokens[i] >= V) return set_err(nullptr, CTR_EINVAL, "token %lld outside [0, vocab)", (long long)i); cnt[(size_t)tokens[i]]++; }
-    std::vector<int> doc; doc.reserve((size_t)n);
-    for (int64_t i = 0; i < n; i++) if (!(0 <= c.min_count && cnt[(size_t)tokens[i]] < c.min_count)) doc.push_back(tokens[i]);   // cpsutil.go:74-78
-    const long nd = (long)doc.size();
-    std::vector<double> z((size_t)V);
-    for (int i = 0; i < V; i++) { double v = cnt[(size_t)i] > 0 ? 1.0 - std::sqrt((double)c.subsample / (double)cnt[(size_t)i]) : 0.0; z[(size_t)i] = v < 0 ? 0 : v; }
-    std::vector<int64_t> node_val; std::vector<long long> poff; std::vector<int> pnode; std::vector<unsigned char> pcode;
-    i2v_build_paths(cnt, V, c.max_depth, node_val, poff, pnode, pcode);
-    std::vector<float> lut(1000);
-    for (int i = 0; i < 1000; i++) { double e = std::exp(((double)i / 1000.0 * 2.0 - 1.0) * 6.0); lut[(size_t)i] = (float)(e / (e + 1.0)); }
-    // ---- device
-    int *d_doc = nullptr, *d_pnode = nullptr; double* d_z = nullptr; long long* d_poff = nullptr; unsigned char* d_pcode = nullptr;
-    float *d_syn0 = nullptr, *d_syn1 = nullptr, *d_lr = nullptr, *d_nsc = nullptr, *d_wsc = nullptr; unsigned long long* d_cnt = nullptr;
+    int *d_tok = nullptr, *d_doc = nullptr, *d_pnode = nullptr, *d_sid = nullptr, *d_sid2 = nullptr, *d_parent = nullptr, *d_bad = nullptr;
+    unsigned long long *d_cnt64 = nullptr, *d_skey = nullptr, *d_skey2 = nullptr, *d_ctr = nullptr, *d_misc = nullptr;
+    unsigned char *d_keep = nullptr, *d_pcode = nullptr, *d_code = nullptr;
+    long long *d_poff = nullptr, *d_nval = nullptr; long* d_nd = nullptr;
+    double* d_z = nullptr; float *d_syn0 = nullptr, *d_syn1 = nullptr, *d_lr = nullptr, *d_nsc = nullptr, *d_wsc = nullptr;
+    void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
     float ms_total = 0; int launches = 0; unsigned long long hc[3] = {0, 0, 0};
     {
         CI(cudaSetDevice(c.device));
         cudaDeviceProp prop{}; CI(cudaGetDeviceProperties(&prop, c.device));
         if (prop.major != 10) { rc = set_err(nullptr, CTR_ENODEV, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor); goto done; }
+        const int G = prop.multiProcessorCount * 8;
         CI(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); CI(cudaEventCreate(&e0)); CI(cudaEventCreate(&e1));
-        CI(cudaMalloc(&d_doc, sizeof(int) * (size_t)std::max<long>(nd, 1))); CI(cudaMalloc(&d_z, sizeof(double) * (size_t)V));
-        CI(cudaMalloc(&d_poff, sizeof(long long) * ((size_t)V + 1))); CI(cudaMalloc(&d_pnode, sizeof(int) * std::max<size_t>(pnode.size(), 1)));
-        CI(cudaMalloc(&d_pcode, std::max<size_t>(pcode.size(), 1))); CI(cudaMalloc(&d_syn0, sizeof(float) * (size_t)V * D));
-        CI(cudaMalloc(&d_syn1, sizeof(float) * (size_t)(V - 1) * D)); CI(cudaMalloc(&d_cnt, 3 * sizeof(unsigned long long)));
-        const long nchunks = nd / c.update_lr_batch + 2;
-        CI(cudaMalloc(&d_lr, sizeof(float) * (size_t)nchunks));
-        if (nd > 0) CI(cudaMemcpyAsync(d_doc, doc.data(), sizeof(int) * (size_t)nd, cudaMemcpyHostToDevice, st));
-        CI(cudaMemcpyAsync(d_z, z.data(), sizeof(double) * (size_t)V, cudaMemcpyHostToDevice, st));
-        CI(cudaMemcpyAsync(d_poff, poff.data(), sizeof(long long) * ((size_t)V + 1), cudaMemcpyHostToDevice, st));
-        if (!pnode.empty()) { CI(cudaMemcpyAsync(d_pnode, pnode.data(), sizeof(int) * pnode.size(), cudaMemcpyHostToDevice, st)); CI(cudaMemcpyAsync(d_pcode, pcode.data(), pcode.size(), cudaMemcpyHostToDevice, st)); }
-        if (c.reserved[0] == 1) {
+        // ---- dictionary counts over the whole stream (dictionary.go:70-81), on the device
+        CI(cudaMalloc(&d_tok, sizeof(int) * (size_t)n)); CI(cudaMalloc(&d_doc, sizeof(int) * (size_t)n)); CI(cudaMalloc(&d_keep, (size_t)n));
+        CI(cudaMalloc(&d_cnt64, sizeof(unsigned long long) * (size_t)V)); CI(cudaMalloc(&d_bad, sizeof(int))); CI(cudaMalloc(&d_nd, sizeof(long)));
+        CI(cudaMalloc(&d_misc, 4 * sizeof(unsigned long long)));
+        CI(cudaMemcpyAsync(d_tok, tokens, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CI(cudaMemsetAsync(d_cnt64, 0, sizeof(unsigned long long) * (size_t)V, st)); CI(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+        k_i2v_count<<<G, 256, 0, st>>>(d_tok, (long)n, V, d_cnt64, d_bad); launches++;
+        unsigned long long n_global = (unsigned long long)n;
+        long nd_max_global = 0;
+        if (world > 1) {
+            CN(g_nccl.AllReduce(d_cnt64, d_cnt64, (size_t)V, kNcclUint64, kNcclSum, dist->nccl, st));
+            CI(cudaMemcpyAsync(d_misc, &n_global, sizeof n_global, cudaMemcpyHostToDevice, st));
+            CN(g_nccl.AllReduce(d_misc, d_misc, 1, kNcclUint64, kNcclSum, dist->nccl, st));
+            CI(cudaMemcpyAsync(&n_global, d_misc, sizeof n_global, cudaMemcpyDeviceToHost, st));
+        }
+        // ---- the training document: words rarer than MinCount are dropped (memory.go:53-62), order kept
+        k_i2v_keep<<<G, 256, 0, st>>>(d_tok, (long)n, d_cnt64, c.min_count, d_keep); launches++;
+        cub::DeviceSelect::Flagged(nullptr, tmp_bytes, d_tok, d_keep, d_doc, d_nd, (int)n, st);
+        {
+            size_t b2 = 0, b3 = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, b2, d_skey, d_skey2, d_sid, d_sid2, V, 0, 64, st);
+            cub::DeviceScan::ExclusiveSum(nullptr, b3, d_poff, d_poff, V + 1, st);
+            tmp_bytes = std::max(tmp_bytes, std::max(b2, b3));
+        }
+        CI(cudaMalloc(&d_tmp, tmp_bytes));
+        { size_t tb = tmp_bytes; cub::DeviceSelect::Flagged(d_tmp, tb, d_tok, d_keep, d_doc, d_nd, (int)n, st); launches++; }
+        long nd = 0; int bad = 0;
+        CI(cudaMemcpyAsync(&nd, d_nd, sizeof nd, cudaMemcpyDeviceToHost, st)); CI(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, st));
+        CI(cudaStreamSynchronize(st));
+        if (bad) { rc = set_err(nullptr, CTR_EINVAL, "a token lies outside [0, vocab)"); goto done; }
+        nd_max_global = nd;
+        if (world > 1) {
+            unsigned long long v = (unsigned long long)nd;
+            CI(cudaMemcpyAsync(d_misc, &v, sizeof v, cudaMemcpyHostToDevice, st));
+            CN(g_nccl.AllReduce(d_misc, d_misc, 1, kNcclUint64, kNcclMax, dist->nccl, st));
+            CI(cudaMemcpyAsync(&v, d_misc, sizeof v, cudaMemcpyDeviceToHost, st)); CI(cudaStreamSynchronize(st));
+            nd_max_global = (long)v;
+        }
+        // concurrency: (centre, context) pairs in flight ~ vocabulary / 4, at most the whole machine
+        const int rpw = 32 / (D / 4);
+        const long max_warps = (long)prop.multiProcessorCount * 8 * 8;
+        const long warps = std::max<long>(1, std::min<long>(std::min<long>(max_warps, (std::max<long>(nd, 1) + 63) / 64), std::max<long>(1, (long)V / 4 / rpw)));
+        const int grid = (int)((warps + 7) / 8);
+        const double Ceff = (double)grid * 8 * rpw;
+        // ---- per-word tables + count-sorted leaves (stable: ties stay in id order, like the reference's sort)
+        CI(cudaMalloc(&d_z, sizeof(double) * (size_t)V)); CI(cudaMalloc(&d_wsc, sizeof(float) * (size_t)V));
+        CI(cudaMalloc(&d_skey, sizeof(unsigned long long) * (size_t)V)); CI(cudaMalloc(&d_skey2, sizeof(unsigned long long) * (size_t)V));
+        CI(cudaMalloc(&d_sid, sizeof(int) * (size_t)V)); CI(cudaMalloc(&d_sid2, sizeof(int) * (size_t)V));
+        k_i2v_word_tables<<<G, 256, 0, st>>>(d_cnt64, V, (double)c.subsample, Ceff, (double)n_global, d_z, d_wsc, d_skey, d_sid); launches++;
+        { size_t tb = tmp_bytes; cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_skey, d_skey2, d_sid, d_sid2, V, 0, 64, st); launches++; }
+        std::vector<int64_t> cnt((size_t)V); std::vector<int> leaves((size_t)V);
+        CI(cudaMemcpyAsync(cnt.data(), d_cnt64, sizeof(int64_t) * (size_t)V, cudaMemcpyDeviceToHost, st));
+        CI(cudaMemcpyAsync(leaves.data(), d_sid2, sizeof(int) * (size_t)V, cudaMemcpyDeviceToHost, st));
+        CI(cudaStreamSynchronize(st));
+        // ---- host: the Huffman merge (huffman.go:23-57), O(V)
+        std::vector<int> parent; std::vector<unsigned char> code; std::vector<long long> node_val;
+        i2v_huffman_sorted(cnt.data(), leaves.data(), V, parent, code, node_val);
+        // ---- paths (node.go:26-43) on the device
+        CI(cudaMalloc(&d_parent, sizeof(int) * parent.size())); CI(cudaMalloc(&d_code, code.size())); CI(cudaMalloc(&d_nval, sizeof(long long) * node_val.size()));
+        CI(cudaMalloc(&d_poff, sizeof(long long) * ((size_t)V + 1))); CI(cudaMalloc(&d_nsc, sizeof(float) * node_val.size()));
+        CI(cudaMemcpyAsync(d_parent, parent.data(), sizeof(int) * parent.size(), cudaMemcpyHostToDevice, st));
+        CI(cudaMemcpyAsync(d_code, code.data(), code.size(), cudaMemcpyHostToDevice, st));
+        CI(cudaMemcpyAsync(d_nval, node_val.data(), sizeof(long long) * node_val.size(), cudaMemcpyHostToDevice, st));
+        CI(cudaMemsetAsync(d_poff, 0, sizeof(long long) * ((size_t)V + 1), st));
+        k_i2v_paths<<<G, 256, 0, st>>>(d_parent, d_code, V, c.max_depth, 0, d_poff, nullptr, nullptr); launches++;
+        { size_t tb = tmp_bytes; cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_poff, d_poff, V + 1, st); launches++; }
+        long long nsteps = 0;
+        CI(cudaMemcpyAsync(&nsteps, d_poff + V, sizeof nsteps, cudaMemcpyDeviceToHost, st)); CI(cudaStreamSynchronize(st));
+        CI(cudaMalloc(&d_pnode, sizeof(int) * (size_t)std::max<long long>(nsteps, 1))); CI(cudaMalloc(&d_pcode, (size_t)std::max<long long>(nsteps, 1)));
+        k_i2v_paths<<<G, 256, 0, st>>>(d_parent, d_code, V, c.max_depth, 1, d_poff, d_pnode, d_pcode); launches++;
+        k_i2v_node_scale<<<G, 256, 0, st>>>(d_nval, V - 1, Ceff, (double)n_global, d_nsc); launches++;
+        CI(cudaMalloc(&d_ctr, 3 * sizeof(unsigned long long))); CI(cudaMemsetAsync(d_ctr, 0, 3 * sizeof(unsigned long long), st));
+        if (seq) {
             // sequential float64 parity mode (item2vec.cuh): one warp, the reference's single-goroutine order
             double *d64_0 = nullptr, *d64_1 = nullptr, *d_lut64 = nullptr; float* d_out32 = nullptr;
             std::vector<double> lut64(1000);
@@ -1849,17 +1924,16 @@ int ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, i
             if (rc == CTR_OK) {
                 cudaMemcpyAsync(d_lut64, lut64.data(), sizeof(double) * 1000, cudaMemcpyHostToDevice, st);
                 cudaMemsetAsync(d64_1, 0, sizeof(double) * (size_t)std::max(V - 1, 1) * D, st);
-                cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), st);
-                k_i2v_init64<<<prop.multiProcessorCount * 8, 256, 0, st>>>(d64_0, (long)V * D, D, c.seed); launches++;
+                k_i2v_init64<<<G, 256, 0, st>>>(d64_0, (long)V * D, D, c.seed); launches++;
                 I2vSeqArgs sa{}; sa.doc = d_doc; sa.nd = nd; sa.n_stream = (long)n; sa.z = d_z; sa.poff = d_poff; sa.pnode = d_pnode; sa.pcode = d_pcode;
                 sa.syn0 = d64_0; sa.syn1 = d64_1; sa.lut = d_lut64; sa.D = D; sa.W = W; sa.upd = c.update_lr_batch; sa.iters = c.iter;
-                sa.init_lr = (double)c.init_lr; sa.min_lr = (double)c.min_lr; sa.seed = c.seed; sa.counters = d_cnt;
+                sa.init_lr = (double)c.init_lr; sa.min_lr = (double)c.min_lr; sa.seed = c.seed; sa.counters = d_ctr;
                 cudaEventRecord(e0, st);
                 k_i2v_seq_f64<<<1, 32, 0, st>>>(sa); launches++;
                 cudaEventRecord(e1, st);
-                k_f64_to_f32_i2v<<<prop.multiProcessorCount * 8, 256, 0, st>>>(d64_0, d_out32, (long)V * D); launches++;
+                k_f64_to_f32_i2v<<<G, 256, 0, st>>>(d64_0, d_out32, (long)V * D); launches++;
                 cudaMemcpyAsync(emb_out, d_out32, sizeof(float) * (size_t)V * D, cudaMemcpyDeviceToHost, st);
-                cudaMemcpyAsync(hc, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st);
+                cudaMemcpyAsync(hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st);
                 if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = set_err(nullptr, CTR_ECUDA, "item2vec sequential mode: %s", cudaGetErrorString(cudaGetLastError()));
                 else {
                     cudaEventElapsedTime(&ms_total, e0, e1);
@@ -1872,54 +1946,59 @@ int ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, i
             for (void* p : {(void*)d64_0, (void*)d64_1, (void*)d_lut64, (void*)d_out32}) if (p) cudaFree(p);
             goto done;
         }
+        // ---- vector tables: syn0 = (U-0.5)/dim (word2vec.go:103-111), inner nodes zero (huffman.go:40)
+        std::vector<float> lut(1000);
+        for (int i = 0; i < 1000; i++) { double e = std::exp(((double)i / 1000.0 * 2.0 - 1.0) * 6.0); lut[(size_t)i] = (float)(e / (e + 1.0)); }
         CI(cudaMemcpyToSymbolAsync(c_i2v_lut, lut.data(), sizeof(float) * 1000, 0, cudaMemcpyHostToDevice, st));
-        CI(cudaMemsetAsync(d_syn1, 0, sizeof(float) * (size_t)(V - 1) * D, st));       // huffman.go:40
-        CI(cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), st));
-        k_i2v_init<<<prop.multiProcessorCount * 8, 256, 0, st>>>(d_syn0, (long)V * D, D, c.seed); launches++;
-        // concurrency: (centre, context) pairs in flight ~ vocabulary / 4, at most the whole machine
-        const int rpw = 32 / (D / 4);
-        const long max_warps = (long)prop.multiProcessorCount * 8 * 8;
-        const long warps = std::max<long>(1, std::min<long>(std::min<long>(max_warps, (nd + 63) / 64), std::max<long>(1, (long)V / 4 / rpw)));
-        const int grid = (int)((warps + 7) / 8);
-        const double Ceff = (double)grid * 8 * rpw;
-        {
-            double total = 0; for (int i = 0; i < V; i++) total += (double)cnt[(size_t)i];
-            std::vector<float> nsc((size_t)V - 1), wsc((size_t)V);
-            for (int i = 0; i < V - 1; i++) nsc[(size_t)i] = (float)(1.0 / std::max(1.0, Ceff * (double)node_val[(size_t)i] / total));
-            for (int i = 0; i < V; i++) wsc[(size_t)i] = (float)(1.0 / std::max(1.0, Ceff * (double)cnt[(size_t)i] / total));
-            CI(cudaMalloc(&d_nsc, sizeof(float) * ((size_t)V - 1))); CI(cudaMalloc(&d_wsc, sizeof(float) * (size_t)V));
-            CI(cudaMemcpyAsync(d_nsc, nsc.data(), sizeof(float) * ((size_t)V - 1), cudaMemcpyHostToDevice, st));
-            CI(cudaMemcpyAsync(d_wsc, wsc.data(), sizeof(float) * (size_t)V, cudaMemcpyHostToDevice, st));
-            CI(cudaStreamSynchronize(st));
-        }
+        CI(cudaMalloc(&d_syn0, sizeof(float) * (size_t)V * D)); CI(cudaMalloc(&d_syn1, sizeof(float) * (size_t)(V - 1) * D));
+        CI(cudaMemsetAsync(d_syn1, 0, sizeof(float) * (size_t)(V - 1) * D, st));
+        k_i2v_init<<<G, 256, 0, st>>>(d_syn0, (long)V * D, D, c.seed); launches++;
+        const long nchunks = nd_max_global / c.update_lr_batch + 2;
+        CI(cudaMalloc(&d_lr, sizeof(float) * (size_t)nchunks));
         std::vector<float> lr_tab((size_t)nchunks);
         double lr = c.init_lr;                                                           // w.currentlr persists across iterations
+        // segments: one per iteration on a single GPU; every sync_every positions when replicas have to be averaged
+        const long seg = (world > 1 && dist->sync_every > 0) ? dist->sync_every : std::max<long>(nd_max_global, 1);
         for (int it = 0; it < c.iter; it++) {
-            for (long k = 0; k < nchunks; k++) {                                         // observe(), word2vec.go:223-233
+            for (long k = 0; k < nchunks; k++) {                                         // observe(), word2vec.go:223-233 (positions of all ranks advance together)
                 lr_tab[(size_t)k] = (float)lr;
-                const double seen = (double)(k + 1) * c.update_lr_batch;
-                if (seen <= (double)nd) lr = lr < (double)c.min_lr ? (double)c.min_lr : (double)c.init_lr * (1.0 - seen / (double)n);
+                const double seen = (double)(k + 1) * c.update_lr_batch * world;
+                if ((double)(k + 1) * c.update_lr_batch <= (double)nd_max_global) lr = lr < (double)c.min_lr ? (double)c.min_lr : (double)c.init_lr * (1.0 - seen / (double)n_global);
             }
             CI(cudaMemcpyAsync(d_lr, lr_tab.data(), sizeof(float) * (size_t)nchunks, cudaMemcpyHostToDevice, st));
             I2vArgs a{}; a.doc = d_doc; a.nd = nd; a.z = d_z; a.poff = d_poff; a.pnode = d_pnode; a.pcode = d_pcode; a.syn0 = d_syn0; a.syn1 = d_syn1;
-            a.D = D; a.W = W; a.lr_tab = d_lr; a.upd = c.update_lr_batch; a.seed = c.seed; a.iter = it; a.counters = d_cnt;
+            a.D = D; a.W = W; a.lr_tab = d_lr; a.upd = c.update_lr_batch; a.seed = c.seed; a.iter = it; a.counters = d_ctr;
             a.node_scale = d_nsc; a.word_scale = d_wsc;
             static const bool no_hot = getenv("CTR_I2V_NO_HOT") != nullptr;
             a.hot_n = no_hot ? 0 : std::min(kI2vHot, V - 1); a.hot_base = V - 1 - a.hot_n;
             const size_t sm = (size_t)std::max(a.hot_n, 1) * D * sizeof(float);
             CI(cudaEventRecord(e0, st));
-            switch (D / 4) {
-                case 1: k_i2v_skipgram_hs<1><<<grid, 256, sm, st>>>(a); break;   case 2: k_i2v_skipgram_hs<2><<<grid, 256, sm, st>>>(a); break;
-                case 4: k_i2v_skipgram_hs<4><<<grid, 256, sm, st>>>(a); break;   case 8: k_i2v_skipgram_hs<8><<<grid, 256, sm, st>>>(a); break;
-                case 16: k_i2v_skipgram_hs<16><<<grid, 256, sm, st>>>(a); break; default: k_i2v_skipgram_hs<32><<<grid, 256, sm, st>>>(a); break;
+            for (long p0 = 0; p0 < std::max<long>(nd_max_global, 1); p0 += seg) {
+                a.pos_begin = p0; a.pos_end = std::min<long>(nd, p0 + seg);
+                if (a.pos_end > a.pos_begin) {
+                    switch (D / 4) {
+                        case 1: k_i2v_skipgram_hs<1><<<grid, 256, sm, st>>>(a); break;   case 2: k_i2v_skipgram_hs<2><<<grid, 256, sm, st>>>(a); break;
+                        case 4: k_i2v_skipgram_hs<4><<<grid, 256, sm, st>>>(a); break;   case 8: k_i2v_skipgram_hs<8><<<grid, 256, sm, st>>>(a); break;
+                        case 16: k_i2v_skipgram_hs<16><<<grid, 256, sm, st>>>(a); break; default: k_i2v_skipgram_hs<32><<<grid, 256, sm, st>>>(a); break;
+                    }
+                    launches++;
+                }
+                if (world > 1) {      // model averaging: every replica continues from the mean of all replicas
+                    CN(g_nccl.GroupStart());
+                    CN(g_nccl.AllReduce(d_syn0, d_syn0, (size_t)V * D, kNcclFloat32, kNcclSum, dist->nccl, st));
+                    CN(g_nccl.AllReduce(d_syn1, d_syn1, (size_t)(V - 1) * D, kNcclFloat32, kNcclSum, dist->nccl, st));
+                    CN(g_nccl.GroupEnd());
+                    k_i2v_scale<<<G, 256, 0, st>>>(d_syn0, (long)V * D, 1.0f / (float)world);
+                    k_i2v_scale<<<G, 256, 0, st>>>(d_syn1, (long)(V - 1) * D, 1.0f / (float)world);
+                    launches += 3;
+                }
             }
-            launches++;
             CI(cudaGetLastError());
             CI(cudaEventRecord(e1, st)); CI(cudaStreamSynchronize(st));                   // lr_tab is reused by the next iteration
             float ms = 0; CI(cudaEventElapsedTime(&ms, e0, e1)); ms_total += ms;
         }
         CI(cudaMemcpyAsync(emb_out, d_syn0, sizeof(float) * (size_t)V * D, cudaMemcpyDeviceToHost, st));
-        CI(cudaMemcpyAsync(hc, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st));
+        CI(cudaMemcpyAsync(hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
         CI(cudaStreamSynchronize(st));
         if (stats) {
             stats->doc_len = nd; stats->trained_positions = (int64_t)hc[0]; stats->pairs = (int64_t)hc[1]; stats->node_visits = (int64_t)hc[2];
@@ -1928,10 +2007,36 @@ int ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, i
     }
 done:
 #undef CI
-    for (void* p : {(void*)d_doc, (void*)d_z, (void*)d_poff, (void*)d_pnode, (void*)d_pcode, (void*)d_syn0, (void*)d_syn1, (void*)d_lr, (void*)d_cnt, (void*)d_nsc, (void*)d_wsc}) if (p) cudaFree(p);
+#undef CN
+    for (void* p : {(void*)d_tok, (void*)d_doc, (void*)d_keep, (void*)d_cnt64, (void*)d_bad, (void*)d_nd, (void*)d_misc, (void*)d_z, (void*)d_wsc, (void*)d_skey, (void*)d_skey2,
+                    (void*)d_sid, (void*)d_sid2, (void*)d_parent, (void*)d_code, (void*)d_nval, (void*)d_poff, (void*)d_nsc, (void*)d_pnode, (void*)d_pcode, (void*)d_ctr,
+                    (void*)d_syn0, (void*)d_syn1, (void*)d_lr, d_tmp}) if (p) cudaFree(p);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
+    return rc;
+}
+}  // namespace
+
+int ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, int32_t V, float* emb_out, ctr_i2v_stats* stats) {
+    return i2v_train_impl(cfg, tokens, n, V, emb_out, stats, nullptr);
+}
+
+// BASELINE configs[4] (item2vec over 8 GPUs): one process per GPU, each with its own shard of the item stream.
+int ctr_i2v_train_dist(const ctr_i2v_config* cfg, const int32_t* tokens_shard, int64_t n_shard, int32_t V, float* emb_out, ctr_i2v_stats* stats,
+                       int32_t rank, int32_t world, const void* nccl_id, int32_t id_bytes, int64_t sync_every) {
+    if (world < 1 || rank < 0 || rank >= world) return set_err(nullptr, CTR_EINVAL, "bad rank/world");
+    if (world == 1) return i2v_train_impl(cfg, tokens_shard, n_shard, V, emb_out, stats, nullptr);
+    if (!nccl_id || id_bytes != 128 || !cfg) return set_err(nullptr, CTR_EINVAL, "unique id must be 128 bytes");
+    std::string err;
+    if (!nccl_load(&err)) return set_err(nullptr, CTR_ECOMM, "%s", err.c_str());
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return set_err(nullptr, CTR_ECUDA, "cudaSetDevice(%d)", cfg->device);
+    I2vDist d; d.rank = rank; d.world = world; d.sync_every = sync_every > 0 ? (long)sync_every : 4L << 20;
+    Uid u; memcpy(&u, nccl_id, 128);
+    int r = g_nccl.CommInitRank(&d.nccl, world, u, rank);
+    if (r != 0) return set_err(nullptr, CTR_ECOMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    const int rc = i2v_train_impl(cfg, tokens_shard, n_shard, V, emb_out, stats, &d);
+    g_nccl.CommDestroy(d.nccl);
     return rc;
 }
 

@@ -36,6 +36,7 @@ struct I2vArgs {
     uint32_t seed; int iter;
     unsigned long long* counters;         // [0] trained positions, [1] (centre, context) pairs, [2] node visits
     int hot_base, hot_n;                  // inner nodes [hot_base, hot_base + hot_n) = the top of the Huffman tree
+    long pos_begin, pos_end;              // this launch trains the centre positions [pos_begin, pos_end) of the document
 };
 
 // The top of the tree is on every path: the root alone would take one red.add per (pair, 16 bytes) on the same
@@ -53,13 +54,13 @@ k_i2v_skipgram_hs(I2vArgs a) {
     const int lane = threadIdx.x & 31, lir = lane % LPR, sub = lane / LPR;
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     const long gwarp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long niter = (a.nd + nwarps - 1) / nwarps;
+    const long niter = (a.pos_end - a.pos_begin + nwarps - 1) / nwarps;
     unsigned long long n_tr = 0, n_pair = 0, n_node = 0;
     for (int i = threadIdx.x; i < a.hot_n * D; i += blockDim.x) s_acc[i] = 0.0f;
     __syncthreads();
     for (long it = 0; it < niter; it++) {
-        const long pos = it * nwarps + gwarp;
-        bool train = pos < a.nd;
+        const long pos = a.pos_begin + it * nwarps + gwarp;
+        bool train = pos < a.pos_end;
         int id = 0;
         if (train) {
             id = a.doc[pos];
@@ -216,6 +217,74 @@ __global__ void k_i2v_init64(double* __restrict__ syn0, long n, int D, uint32_t 
 }
 __global__ void k_f64_to_f32_i2v(const double* __restrict__ a, float* __restrict__ b, long n) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) b[i] = (float)a[i];
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// Dictionary / Huffman plan on the device (the host used to spend 85 % of the end-to-end time here).  What stays on the
+// host is the O(V) two-queue merge over the count-sorted leaves — everything proportional to the stream length
+// (counting, the MinCount filter) or to V * depth (the per-word root->leaf paths) runs here.
+// -------------------------------------------------------------------------------------------------------------------
+// dictionary.Add (dictionary.go:70-81): occurrences per word id.  Warp-aggregated: lanes holding the same id add once.
+__global__ void __launch_bounds__(256)
+k_i2v_count(const int* __restrict__ tok, long n, int V, unsigned long long* __restrict__ cnt, int* __restrict__ bad) {
+    for (long i0 = (blockIdx.x * (long)blockDim.x + threadIdx.x); i0 < ((n + 31) & ~31L); i0 += (long)gridDim.x * blockDim.x) {
+        const bool in = i0 < n;
+        const int id = in ? tok[i0] : -1;
+        if (in && (id < 0 || id >= V)) { *bad = 1; }
+        const bool ok = in && id >= 0 && id < V;
+        const unsigned peers = __match_any_sync(0xffffffffu, ok ? id : -1);
+        if (ok && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cnt + id, (unsigned long long)__popc(peers));
+    }
+}
+// keep[i] = 1 when the word survives the MinCount filter (memory.go:53-62, cpsutil.go:74-78)
+__global__ void __launch_bounds__(256)
+k_i2v_keep(const int* __restrict__ tok, long n, const unsigned long long* __restrict__ cnt, int min_count, unsigned char* __restrict__ keep) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        keep[i] = !(0 <= min_count && cnt[tok[i]] < (unsigned long long)min_count);
+}
+// subsample threshold z = max(0, 1 - sqrt(t / count)) (subsample.go:34-38), staleness scale of a word, sort keys
+__global__ void __launch_bounds__(256)
+k_i2v_word_tables(const unsigned long long* __restrict__ cnt, int V, double subsample, double ceff, double total,
+                  double* __restrict__ z, float* __restrict__ word_scale, unsigned long long* __restrict__ sort_key, int* __restrict__ sort_val) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
+        const double c = (double)cnt[i];
+        const double v = c > 0.0 ? 1.0 - sqrt(subsample / c) : 0.0;
+        z[i] = v < 0.0 ? 0.0 : v;
+        if (word_scale) word_scale[i] = (float)(1.0 / fmax(1.0, ceff * c / total));
+        if (sort_key) { sort_key[i] = cnt[i]; sort_val[i] = i; }
+    }
+}
+__global__ void __launch_bounds__(256)
+k_i2v_node_scale(const long long* __restrict__ node_val, int nn, double ceff, double total, float* __restrict__ node_scale) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x)
+        node_scale[i] = (float)(1.0 / fmax(1.0, ceff * (double)node_val[i] / total));
+}
+// Node.GetPath(maxDepth) (node.go:26-43) from the parent / code arrays of the tree: pass 0 writes the number of
+// (inner node, child code) steps of every word, pass 1 (after an exclusive scan) the steps in root -> leaf order.
+__global__ void __launch_bounds__(256)
+k_i2v_paths(const int* __restrict__ parent, const unsigned char* __restrict__ code, int V, int max_depth, int pass,
+            long long* __restrict__ poff, int* __restrict__ pnode, unsigned char* __restrict__ pcode) {
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < V; w += gridDim.x * blockDim.x) {
+        int len = 0;
+        for (int p = w; p != -1; p = parent[p]) len++;                         // leaf .. root, both included
+        const int depth = max_depth < len ? max_depth : len;
+        const int steps = depth > 0 ? depth - 1 : 0;
+        if (pass == 0) { poff[w] = steps; continue; }
+        // chain[len-1-i] for i < steps = the i-th node from the root: reached after len-1-i parent hops from the leaf
+        long long o = poff[w];
+        // walk once from the leaf, emitting when the position from the root is < steps
+        int p = w, child = -1;
+        for (int h = 0; h <= len - 1; h++) {                                   // h hops done: p = chain[h]
+            const int i_from_root = len - 1 - h;                               // p is chain[len-1-i] with i = i_from_root
+            if (h > 0 && i_from_root < steps) { pnode[o + i_from_root] = p - V; pcode[o + i_from_root] = code[child]; }
+            child = p; p = parent[p];
+        }
+    }
+}
+// element-wise mean of `world` replicas after an all-reduce(sum): x *= 1/world
+__global__ void __launch_bounds__(256)
+k_i2v_scale(float* __restrict__ x, long n, float s) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] *= s;
 }
 
 // syn0 = (U[0,1) - 0.5) / dim (word2vec.go:103-111) with the counter RNG

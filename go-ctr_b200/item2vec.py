@@ -14,7 +14,7 @@ import numpy as np
 
 from . import engine as _e
 
-__all__ = ["i2v_paths", "I2vConfig", "I2vStats", "i2v_default_config", "i2v_train_ids", "TrainEmbedding", "EmbeddingModel",
+__all__ = ["i2v_paths", "I2vConfig", "I2vStats", "i2v_default_config", "i2v_train_ids", "i2v_train_dist", "TrainEmbedding", "EmbeddingModel",
            "Embedding", "SaveVectors", "LoadVectors", "ParseLine"]
 
 
@@ -61,6 +61,21 @@ def i2v_train_ids(tokens, vocab, cfg=None, **kw):
     st = I2vStats()
     rc = L.ctr_i2v_train(C.byref(cfg), tok.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(tok.size), C.c_int32(vocab),
                          emb.ctypes.data_as(C.POINTER(C.c_float)), C.byref(st))
+    if rc != 0:
+        raise _e.CtrError(rc, L.ctr_last_error(None).decode())
+    return emb, st
+
+
+def i2v_train_dist(tokens_shard, vocab, rank, world, nccl_id, sync_every=0, cfg=None, **kw):
+    """One rank of the multi-GPU trainer (ctr_i2v_train_dist): this rank's shard of the stream in, the averaged table out."""
+    L = _e.load_library()
+    cfg = cfg or i2v_default_config(**kw)
+    tok = np.ascontiguousarray(tokens_shard, np.int32)
+    emb = np.empty((vocab, cfg.dim), np.float32)
+    st = I2vStats()
+    rc = L.ctr_i2v_train_dist(C.byref(cfg), tok.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(tok.size), C.c_int32(vocab),
+                              emb.ctypes.data_as(C.POINTER(C.c_float)), C.byref(st), C.c_int32(rank), C.c_int32(world),
+                              C.c_char_p(nccl_id), C.c_int32(len(nccl_id)), C.c_int64(sync_every))
     if rc != 0:
         raise _e.CtrError(rc, L.ctr_last_error(None).decode())
     return emb, st

@@ -260,6 +260,17 @@ void ctr_i2v_config_default(ctr_i2v_config* cfg);
 int  ctr_i2v_paths(const int64_t* count, int32_t vocab, int32_t max_depth, int64_t* path_off, int32_t* path_node, uint8_t* path_code, int64_t cap);
 int  ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, int32_t vocab,
                    float* emb_out, ctr_i2v_stats* stats);
+/* BASELINE configs[4] shape: the item stream sharded over `world` processes (one per GPU), every rank passes ITS shard.
+ * Dictionary counts are all-reduced (NCCL) so every rank builds the identical Huffman tree; every rank trains a full
+ * replica of both vector tables on its shard and the replicas are averaged (all-reduce) every sync_every centre
+ * positions (0 = 4 Mi) — the reference's trainer is Hogwild over goroutines in one address space (word2vec.go:165-169);
+ * across GPUs the shared memory becomes periodic model averaging.  The learning rate follows the GLOBAL position count.
+ * emb_out receives the averaged table on every rank; id = ncclUniqueId bytes from ctr_comm_unique_id on rank 0.
+ * ctr_i2v_config.reserved[0] = 1 (single GPU only): sequential float64 parity mode — one warp walks the document in
+ * order, reproducing the CPU restatement of the reference bit for bit (tests/test_gpu_i2v.py). */
+int  ctr_i2v_train_dist(const ctr_i2v_config* cfg, const int32_t* tokens_shard, int64_t n_shard, int32_t vocab,
+                        float* emb_out, ctr_i2v_stats* stats, int32_t rank, int32_t world,
+                        const void* nccl_id, int32_t id_bytes, int64_t sync_every);
 
 /* ---- model/mlp: the float64 MLP classifier of the reference's default path (BASELINE configs[0]; SURVEY.md §8a row
  * a11) — main.go:42-52 → model/mlp/mlp.go:45-65 (SimpleMlpFitWrap.Fit / SimpleMlpPredWrap.Predict: float32 samples →
