@@ -205,61 +205,85 @@ def cpu_baseline(w, seconds=10.0):
 
 
 def run_item2vec(args):
-    """BASELINE config 5 (item2vec SkipGram-HS, window 5): a step = one pass of ctr_i2v_train over a bounded
-    synthetic token stream.  value = trained-document tokens / device time of the training kernels;
-    e2e = stream tokens / wall time of the whole call (host dictionary + Huffman build, H2D, training, D2H
-    of the embedding table).  The only throughput the reference publishes is for this loop: 555k words/s
-    on an Apple M1 Max (README.md:140)."""
+    """BASELINE configs[4] (item2vec SkipGram-HS, window 5): a step = one pass of the trainer over the synthetic item
+    stream — `--i2v-tokens` tokens PER GPU (weak scaling; 8 x 125 M = the 1 B-token stream of configs[4]).  value = stream
+    tokens of all ranks / device time of the training segments (max over ranks; includes the replica averaging for N > 1);
+    e2e = stream tokens / wall time of the whole call (device-side dictionary / filter / path build, host Huffman merge,
+    H2D of the tokens, training, D2H of the table).  The only throughput the reference publishes is for this loop: 555 k
+    words/s on an Apple M1 Max (README.md:140)."""
     import go_ctr_b200 as g
     from oracle import oracle as orc
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     V, n, D = args.i2v_vocab, args.i2v_tokens, args.i2v_dim
-    rng = np.random.default_rng(42)
-    # Zipf(1.0)-like item popularity over V items, ids by first appearance are not required by the engine
-    raw = (np.floor(np.exp(rng.random(n) * np.log(V))).astype(np.int64) - 1).clip(0, V - 1)
-    uniq, toks = np.unique(raw, return_inverse=True)              # the dictionary holds only words that occur (dictionary.go:70-81)
-    toks = toks.astype(np.int32); V = int(uniq.size)
+    rng = np.random.default_rng(42 + rank)
+    # Zipf(1.0)-like item popularity over V items (log-uniform ranks); ids are popularity ranks
+    toks = (np.floor(np.exp(rng.random(n) * np.log(V))).astype(np.int64) - 1).clip(0, V - 1).astype(np.int32)
     hbm_peak, peak_src = load_peaks()
     if args.impl == "reference":
+        if rank != 0:
+            return
         m = min(n, args.i2v_cpu_tokens)
         cfg = orc.i2v_cfg(dim=D, window=5, iters=1, seed=1, rng_mode=0)
         t0 = time.perf_counter(); emb, trained = orc.i2v_train(cfg, toks[:m], V); dt = time.perf_counter() - t0
         v = m / dt
-        print(json.dumps({"impl": "reference", "metric": "item2vec_words_per_sec", "value": v, "unit": "words/s", "n_gpus": 1, "steps": 1, "warmup": 0,
+        print(json.dumps({"impl": "reference", "metric": "item2vec_words_per_sec", "value": v, "unit": "words/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
                           "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": v / 555000.0, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "item2vec", "vocab": V, "dim": D, "window": 5, "sample": "%d tokens, single thread" % m},
-                          "cpu_baseline": {"value": v, "unit": "words/s", "cores": 1, "kind": "port", "sample": "%d tokens of the same stream" % m},
+                          "config": {"workload": "item2vec", "vocab": V, "dim": D, "window": 5, "tokens_per_gpu": n},
+                          "cpu_baseline": {"value": v, "unit": "words/s", "cores": 1, "kind": "port", "sample": "%d tokens of the same stream, single-threaded float64 port" % m},
                           "e2e": {"value": v, "unit": "words/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = g.i2v_default_config(dim=D, window=5, iter=1, seed=1, device=local)
     best = None
-    for i in range(max(1, args.warmup if args.warmup < 3 else 1) + max(1, min(args.steps, 3))):
+    for i in range(2 + max(0, min(args.steps, 2) - 1)):
+        nid = [None]
+        if world > 1:
+            if rank == 0:
+                nid[0] = g.Engine(g.engine.default_config(g.MODEL_YOUTUBE, batch=1, pred_batch=1, device=local)).comm_unique_id()
+            dist.broadcast_object_list(nid, src=0)
+            dist.barrier()
         t0 = time.perf_counter()
-        emb, st = g.i2v_train_ids(toks, V, dim=D, window=5, iter=1, seed=1)
+        if world > 1:
+            emb, st = g.i2v_train_dist(toks, V, rank, world, nid[0], sync_every=args.i2v_sync, cfg=cfg)
+        else:
+            emb, st = g.i2v_train_ids(toks, V, cfg=cfg)
         wall = time.perf_counter() - t0
-        if i >= 1 and (best is None or st.ms_device < best[0].ms_device):
-            best = (st, wall)
-    st, wall = best
-    value = st.doc_len / (st.ms_device * 1e-3)
+        ms = st.ms_device
+        if world > 1:
+            t = torch.tensor([ms, wall], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms, wall = float(t[0]), float(t[1])
+        if i >= 1 and (best is None or ms < best[1]):
+            best = (st, ms, wall)
+    st, ms, wall = best
+    value = n * world / (ms * 1e-3)
     ach = st.algorithmic_bytes / (st.ms_device * 1e-3) / 1e9
-    line = {"metric": "item2vec_words_per_sec", "value": value, "unit": "words/s", "n_gpus": 1, "steps": 1, "warmup": 1, "ms_per_step": st.ms_device,
+    line = {"metric": "item2vec_words_per_sec", "value": value, "unit": "words/s", "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": value / 555000.0, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "item2vec", "note": "BASELINE.json configs[4] on a bounded %d-token sample of the stream, 1 GPU" % n, "vocab": V, "dim": D, "window": 5,
-                       "optimizer": "hierarchical softmax", "ids": "zipf(1.0)", "l2": "vector tables (%.0f MB) exceed L2; no flush" % (2.0 * V * D * 4 / 1e6),
+            "config": {"workload": "item2vec", "note": "BASELINE.json configs[4]: %d tokens per GPU (%d in total)" % (n, n * world), "vocab": V, "dim": D, "window": 5,
+                       "tokens_per_gpu": n, "optimizer": "hierarchical softmax", "ids": "zipf(1.0)", "l2": "vector tables (%.0f MB) exceed L2; no flush" % (2.0 * V * D * 4 / 1e6),
+                       "placement": "single GPU" if world == 1 else "a full replica of both tables per GPU; counts all-reduced, replicas averaged every %d positions (NCCL)" % (args.i2v_sync or (4 << 20)),
                        "vs_baseline_note": "published 555k words/s is MovieLens-10M on an Apple M1 Max (README.md:140), different data and dim"},
-            "e2e": {"value": n / wall, "unit": "words/s", "h2d_bytes_per_step": int(n * 4), "d2h_bytes_per_step": int(V * D * 4)},
+            "e2e": {"value": n * world / wall, "unit": "words/s", "h2d_bytes_per_step": int(n * 4), "d2h_bytes_per_step": int(V * D * 4)},
             "gpu_launches": int(st.launches),
             "roofline": {"bound": "hbm", "kernel": "k_i2v_skipgram_hs", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": st.algorithmic_bytes, "ms_per_launch": st.ms_device,
                          "pairs": int(st.pairs), "node_visits": int(st.node_visits),
-                         "note": "Zipf item popularity: most node/context rows are served by L2 and the top Huffman nodes by shared memory "
+                         "note": "rank 0's kernel; Zipf item popularity: most node/context rows are served by L2 and the top Huffman nodes by shared memory "
                                  "(ncu: DRAM traffic << algorithmic bytes, profiles/r01/ncu_item2vec_v2.md) - this is SURVEY 8(d)'s algorithmic-bytes figure, "
                                  "not a DRAM reading; the kernel is L2-latency / issue bound"},
             "stats": {"doc_len": int(st.doc_len), "trained_positions": int(st.trained_positions)}}
-    if not args.no_cpu_baseline:
-        m = min(n, args.i2v_cpu_tokens)
-        cfg = orc.i2v_cfg(dim=D, window=5, iters=1, seed=1, rng_mode=0)
-        t0 = time.perf_counter(); orc.i2v_train(cfg, toks[:m], V); dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": m / dt, "unit": "words/s", "cores": 1, "kind": "port", "sample": "%d tokens of the same stream, single-threaded float64 port" % m}
-    print(json.dumps(line))
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            m = min(n, args.i2v_cpu_tokens)
+            ocfg = orc.i2v_cfg(dim=D, window=5, iters=1, seed=1, rng_mode=0)
+            t0 = time.perf_counter(); orc.i2v_train(ocfg, toks[:m], V); dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": m / dt, "unit": "words/s", "cores": 1, "kind": "port", "sample": "%d tokens of the same stream, single-threaded float64 port" % m}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
 
 
 def main():
@@ -273,6 +297,7 @@ def main():
     ap.add_argument("--i2v-tokens", type=int, default=50_000_000)
     ap.add_argument("--i2v-dim", type=int, default=64)
     ap.add_argument("--i2v-cpu-tokens", type=int, default=2_000_000)
+    ap.add_argument("--i2v-sync", type=int, default=0, help="item2vec, N > 1: positions between replica averagings (0 = 4 Mi)")
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
     ap.add_argument("--table-opt", default="sgd", choices=["sgd", "det", "frozen", "adam"])
     ap.add_argument("--gemm", default="auto", choices=["auto", "fp32", "tcgen05"])

@@ -94,3 +94,40 @@ def test_two_gpu_step_equals_single_gpu_global_batch(tmp_path, policy, hot):
     np.testing.assert_allclose(got_emb, want_emb, rtol=2e-3, atol=2e-5)
     p = np.concatenate([np.load(tmp_path / "p0.npy"), np.load(tmp_path / "p1.npy")])
     np.testing.assert_allclose(p, ref.predict_idx(*batches[0][:3]), rtol=2e-3, atol=1e-5)
+
+
+def _i2v_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from tests.test_oracle_i2v import planted_corpus
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank)
+    toks, remap, nc, per = planted_corpus(np.random.default_rng(2))
+    shard = np.array_split(toks, world)[rank]
+    ids = [g.Engine(g.engine.default_config(g.MODEL_YOUTUBE, batch=1, pred_batch=1, device=rank)).comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    cfg = g.i2v_default_config(dim=16, window=5, iter=3, seed=5, device=rank)
+    emb, st = g.i2v_train_dist(shard, nc * per, rank, world, ids[0], sync_every=2000, cfg=cfg)
+    np.save(os.path.join(out_dir, "i2v%d.npy" % rank), emb)
+    np.save(os.path.join(out_dir, "i2v_doc%d.npy" % rank), np.array([st.doc_len, st.trained_positions]))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_two_gpu_item2vec_replicas_average_to_one_table_of_equal_quality(tmp_path):
+    """ctr_i2v_train_dist: each rank trains its half of the stream, dictionary counts are all-reduced (one Huffman tree),
+    replicas are averaged every 2000 positions: both ranks return the identical table, and its neighbour structure is as
+    good as the sequential float64 oracle's on the whole stream."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import oracle as orc
+    from tests.test_oracle_i2v import neighbour_purity, planted_corpus
+    mp.spawn(_i2v_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    e0, e1 = np.load(tmp_path / "i2v0.npy"), np.load(tmp_path / "i2v1.npy")
+    assert e0.tobytes() == e1.tobytes()
+    toks, remap, nc, per = planted_corpus(np.random.default_rng(2))
+    d0, d1 = np.load(tmp_path / "i2v_doc0.npy"), np.load(tmp_path / "i2v_doc1.npy")
+    assert d0[0] + d1[0] == toks.size                                   # every rank filtered with the GLOBAL counts
+    oemb, _ = orc.i2v_train(orc.i2v_cfg(dim=16, window=5, iters=3, seed=5, rng_mode=1), toks, nc * per)
+    pg, po = neighbour_purity(e0, remap, nc, per), neighbour_purity(oemb, remap, nc, per)
+    assert pg > 0.9 and abs(pg - po) < 0.08, (pg, po)
