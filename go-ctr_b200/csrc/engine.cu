@@ -165,6 +165,9 @@ struct ctr_handle {
     unsigned long long idm_cap[2] = {0, 0}; int64_t idm_n[2] = {0, 0};
     long long *k_keys = nullptr, *k_host = nullptr; int* k_flags = nullptr;   // staging for ctr_batch_predict_keys (device, pinned host)
 
+    // grow-only device scratch of the host-buffer entry points (gather / window / id lookup): no cudaMalloc on the serving path
+    void* scratch[3] = {nullptr, nullptr, nullptr}; size_t scratch_cap[3] = {0, 0, 0};
+
     unsigned long long* umma_dbg = nullptr;     // CTR_UMMA_TIMELINE=1: timeline buffer of the last umma launch
 
     Comm comm;
@@ -210,6 +213,18 @@ template <typename T>
 int dalloc(ctr_handle* h, T** p, size_t n, bool zero = true) {
     CU(h, cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
     if (zero) CU(h, cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream));
+    return CTR_OK;
+}
+
+// device scratch slot `i` with at least `bytes` (contents undefined); grows geometrically, freed with the handle
+int scratch_get(ctr_handle* h, int i, size_t bytes, void** out) {
+    if (h->scratch_cap[i] < bytes) {
+        if (h->scratch[i]) { cudaStreamSynchronize(h->stream); cudaFree(h->scratch[i]); h->scratch[i] = nullptr; h->scratch_cap[i] = 0; }
+        const size_t cap = std::max(bytes, h->scratch_cap[i] * 2);
+        CU(h, cudaMalloc(&h->scratch[i], cap));
+        h->scratch_cap[i] = cap;
+    }
+    *out = h->scratch[i];
     return CTR_OK;
 }
 
@@ -400,12 +415,13 @@ int make_map(ctr_handle* h, CUtensorMap* m, const float* base, uint64_t rows, ui
     return CTR_OK;
 }
 
+constexpr size_t kUmmaEpiBytes = (size_t)umma::kEpiWarps * umma::kEpiStageBytes + 32;     // staged-epilogue tiles
 int umma_stages(int bn) {
     size_t st = (size_t)umma::kABytes * 2 + (size_t)bn * 128 * 2;
-    return (int)std::min<size_t>(4, ((size_t)227 * 1024 - 2048) / st);
+    return (int)std::min<size_t>(4, ((size_t)227 * 1024 - 2048 - kUmmaEpiBytes) / st);
 }
 size_t umma_smem(int bn, int stages) {
-    return (size_t)stages * ((size_t)umma::kABytes * 2 + (size_t)bn * 128 * 2) + 8 * (3 * stages + 4) + 16 + 1024;
+    return (size_t)stages * ((size_t)umma::kABytes * 2 + (size_t)bn * 128 * 2) + 8 * (3 * stages + 4) + 16 + 1024 + kUmmaEpiBytes;
 }
 
 bool umma_supported(const ctr_handle* h) {
@@ -469,6 +485,8 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
     const int grid = std::min(tiles, h->num_sms);
     const size_t smem = umma_smem(a.bn, a.stages);
     a.dbg = h->umma_dbg;
+    static const bool epi_old = getenv("CTR_UMMA_EPI_OLD") != nullptr;
+    a.staged_epi = epi_old ? 0 : 1;
     int rc = launch(h, name, [&] { umma::k_umma_gemm<EPI, true><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a); });
     if (rc == CTR_OK && h->umma_dbg) {
         std::vector<unsigned long long> t(8192);
@@ -882,14 +900,21 @@ void gaussian_fill(std::vector<float>& w, uint32_t seed, uint32_t stream) {
 // count, ties in id order): merged nodes are created in non-decreasing value order and inserted before every queued
 // node of equal value, so they win ties and equal-valued merged nodes pop newest-first.  O(V).
 // parent / code are indexed by tree node (leaves [0,V), inner nodes V + creation index); node_val [V-1].
-static void i2v_huffman_sorted(const int64_t* cnt_by_word, const int* leaves, int V, std::vector<int>& parent, std::vector<unsigned char>& code,
-                               std::vector<long long>& node_val) {
+// Ids that never occur (count 0) are not dictionary words in the reference (the dictionary is built from the stream,
+// dictionary.go:70-81).  Here they go through the literal procedure like every other leaf (they chain into a comb of
+// zero-valued nodes below the lightest real word, which leaves every real word's path what the procedure gives it), but
+// no PATH is built for them — they are never trained and walking a comb as deep as their number is quadratic.
+// Returns the number of inner nodes created.
+static int i2v_huffman_sorted(const int64_t* cnt_by_word, const int* leaves, int V, std::vector<int>& parent, std::vector<unsigned char>& code,
+                              std::vector<long long>& node_val) {
     parent.assign((size_t)2 * V - 1, -1); code.assign((size_t)2 * V - 1, 0); node_val.assign((size_t)std::max(V - 1, 1), 0);
+    const size_t first = 0;
+    const int Vp = V;
     // merged queue as runs of equal value; inside a run the newest node pops first, runs are in non-decreasing value order
     std::vector<long long> run_val; std::vector<int> run_begin, run_top;      // run r holds ids mq[run_begin[r] .. run_top[r])
     std::vector<int> mq; mq.reserve((size_t)V);
-    size_t rh = 0, lh = 0; int next_id = V;
-    for (int made = 0; made < V - 1; made++) {
+    size_t rh = 0, lh = first; int next_id = V;
+    for (int made = 0; made < Vp - 1; made++) {
         long long pv[2]; int pid[2];
         for (int k = 0; k < 2; k++) {
             while (rh + 1 < run_val.size() && run_top[rh] == run_begin[rh]) rh++;          // never step past the last run: it may refill
@@ -906,6 +931,7 @@ static void i2v_huffman_sorted(const int64_t* cnt_by_word, const int* leaves, in
             run_val.back() = val; mq.push_back(id); run_top.back() = (int)mq.size();
         } else { run_val.push_back(val); run_begin.push_back((int)mq.size()); mq.push_back(id); run_top.push_back((int)mq.size()); }
     }
+    return std::max(Vp - 1, 0);
 }
 
 // item2vec host plan (CPU-only entry ctr_i2v_paths): Huffman tree + every word's root→leaf path as Node.GetPath(maxDepth)
@@ -921,6 +947,7 @@ static void i2v_build_paths(const std::vector<int64_t>& cnt, int V, int max_dept
     poff.assign((size_t)V + 1, 0); pnode.clear(); pcode.clear();
     std::vector<int> chain;
     for (int w = 0; w < V; w++) {                          // Node.GetPath(maxDepth), node.go:26-43
+        if (cnt[(size_t)w] == 0) { poff[(size_t)w + 1] = (long long)pnode.size(); continue; }     // never occurs: no path
         chain.clear();
         for (int p = w; p != -1; p = parent[(size_t)p]) chain.push_back(p);
         const int len = (int)chain.size(), depth = std::min(max_depth, len);
@@ -1013,6 +1040,7 @@ void ctr_destroy(ctr_handle* h) {
                     (void*)h->dUb, (void*)h->dIt, (void*)h->keys, (void*)h->keys2, (void*)h->pos, (void*)h->pos2, h->sort_tmp,
                     (void*)h->d_cost, (void*)h->s_user, (void*)h->s_item, (void*)h->s_hist, (void*)h->s_label, (void*)h->dXd, (void*)h->dYd, (void*)h->hot_acc, (void*)h->emb_m, (void*)h->emb_v})
         if (p) cudaFree(p);
+    for (int i = 0; i < 3; i++) if (h->scratch[i]) cudaFree(h->scratch[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < 2; i++) { if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]); }
@@ -1130,7 +1158,7 @@ int ctr_gather_rows(ctr_handle* h, const int32_t* user_row, const int32_t* item_
     const long xc = (long)c.uP + (long)c.S * c.D + c.D + c.cF;
     float* dout = nullptr;
     const int chunk = h->Bmax;
-    CU(h, cudaMalloc(&dout, (size_t)chunk * xc * sizeof(float)));
+    RET(scratch_get(h, 0, (size_t)chunk * xc * sizeof(float), (void**)&dout));
     int rc = CTR_OK;
     for (int64_t s = 0; s < B && rc == CTR_OK; s += chunk) {
         int nb = (int)std::min<int64_t>(chunk, B - s);
@@ -1142,7 +1170,6 @@ int ctr_gather_rows(ctr_handle* h, const int32_t* user_row, const int32_t* item_
         if (cudaMemcpyAsync(X + s * xc, dout, (size_t)nb * xc * sizeof(float), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
             cudaStreamSynchronize(h->stream) != cudaSuccess) rc = set_err(h, CTR_ECUDA, "gather D2H: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    cudaFree(dout);
     return rc;
 }
 
@@ -1549,16 +1576,15 @@ int ctr_ubcache_window(ctr_handle* h, const int32_t* user_row, const int64_t* ma
     CU(h, cudaSetDevice(h->dev));
     int* du = nullptr; long long* dt = nullptr; int* dh = nullptr;
     int rc = CTR_OK;
-    if (cudaMalloc(&du, sizeof(int) * (size_t)B) != cudaSuccess || cudaMalloc(&dt, sizeof(long long) * (size_t)B) != cudaSuccess ||
-        cudaMalloc(&dh, sizeof(int) * (size_t)B * h->cfg.S) != cudaSuccess) rc = set_err(h, CTR_ENOMEM, "ubcache window buffers");
-    if (rc == CTR_OK) {
+    RET(scratch_get(h, 0, sizeof(int) * (size_t)B, (void**)&du)); RET(scratch_get(h, 1, sizeof(long long) * (size_t)B, (void**)&dt));
+    RET(scratch_get(h, 2, sizeof(int) * (size_t)B * h->cfg.S, (void**)&dh));
+    {
         cudaMemcpyAsync(du, user_row, sizeof(int) * (size_t)B, cudaMemcpyHostToDevice, h->stream);
         cudaMemcpyAsync(dt, max_ts, sizeof(long long) * (size_t)B, cudaMemcpyHostToDevice, h->stream);
         rc = ctr_ubcache_window_dev(h, du, (const int64_t*)dt, B, dh);
         if (rc == CTR_OK && (cudaMemcpyAsync(hist_rows, dh, sizeof(int) * (size_t)B * h->cfg.S, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
                              cudaStreamSynchronize(h->stream) != cudaSuccess)) rc = set_err(h, CTR_ECUDA, "ubcache window copy: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    for (void* p : {(void*)du, (void*)dt, (void*)dh}) if (p) cudaFree(p);
     return rc;
 }
 
@@ -1610,14 +1636,13 @@ int ctr_idmap_lookup(ctr_handle* h, int which, const int64_t* ids, int64_t n, in
     CU(h, cudaSetDevice(h->dev));
     long long* d_ids = nullptr; int* d_rows = nullptr;
     int rc = CTR_OK;
-    if (cudaMalloc(&d_ids, sizeof(long long) * (size_t)n) != cudaSuccess || cudaMalloc(&d_rows, sizeof(int) * (size_t)n) != cudaSuccess) rc = set_err(h, CTR_ENOMEM, "idmap lookup buffers");
-    if (rc == CTR_OK) {
+    RET(scratch_get(h, 0, sizeof(long long) * (size_t)n, (void**)&d_ids)); RET(scratch_get(h, 1, sizeof(int) * (size_t)n, (void**)&d_rows));
+    {
         cudaMemcpyAsync(d_ids, ids, sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, h->stream);
         rc = ctr_idmap_lookup_dev(h, which, (const int64_t*)d_ids, n, d_rows);
         if (rc == CTR_OK && (cudaMemcpyAsync(rows, d_rows, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
                              cudaStreamSynchronize(h->stream) != cudaSuccess)) rc = set_err(h, CTR_ECUDA, "idmap lookup copy: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    for (void* p : {(void*)d_ids, (void*)d_rows}) if (p) cudaFree(p);
     return rc;
 }
 
@@ -1897,7 +1922,8 @@ int i2v_train_impl(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, 
         CI(cudaStreamSynchronize(st));
         // ---- host: the Huffman merge (huffman.go:23-57), O(V)
         std::vector<int> parent; std::vector<unsigned char> code; std::vector<long long> node_val;
-        i2v_huffman_sorted(cnt.data(), leaves.data(), V, parent, code, node_val);
+        const int n_inner = i2v_huffman_sorted(cnt.data(), leaves.data(), V, parent, code, node_val);
+        if (n_inner < 1) { rc = set_err(nullptr, CTR_EINVAL, "item2vec needs at least two distinct words in the stream"); goto done; }
         // ---- paths (node.go:26-43) on the device
         CI(cudaMalloc(&d_parent, sizeof(int) * parent.size())); CI(cudaMalloc(&d_code, code.size())); CI(cudaMalloc(&d_nval, sizeof(long long) * node_val.size()));
         CI(cudaMalloc(&d_poff, sizeof(long long) * ((size_t)V + 1))); CI(cudaMalloc(&d_nsc, sizeof(float) * node_val.size()));
@@ -1905,12 +1931,12 @@ int i2v_train_impl(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, 
         CI(cudaMemcpyAsync(d_code, code.data(), code.size(), cudaMemcpyHostToDevice, st));
         CI(cudaMemcpyAsync(d_nval, node_val.data(), sizeof(long long) * node_val.size(), cudaMemcpyHostToDevice, st));
         CI(cudaMemsetAsync(d_poff, 0, sizeof(long long) * ((size_t)V + 1), st));
-        k_i2v_paths<<<G, 256, 0, st>>>(d_parent, d_code, V, c.max_depth, 0, d_poff, nullptr, nullptr); launches++;
+        k_i2v_paths<<<G, 256, 0, st>>>(d_parent, d_code, d_cnt64, V, c.max_depth, 0, d_poff, nullptr, nullptr); launches++;
         { size_t tb = tmp_bytes; cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_poff, d_poff, V + 1, st); launches++; }
         long long nsteps = 0;
         CI(cudaMemcpyAsync(&nsteps, d_poff + V, sizeof nsteps, cudaMemcpyDeviceToHost, st)); CI(cudaStreamSynchronize(st));
         CI(cudaMalloc(&d_pnode, sizeof(int) * (size_t)std::max<long long>(nsteps, 1))); CI(cudaMalloc(&d_pcode, (size_t)std::max<long long>(nsteps, 1)));
-        k_i2v_paths<<<G, 256, 0, st>>>(d_parent, d_code, V, c.max_depth, 1, d_poff, d_pnode, d_pcode); launches++;
+        k_i2v_paths<<<G, 256, 0, st>>>(d_parent, d_code, d_cnt64, V, c.max_depth, 1, d_poff, d_pnode, d_pcode); launches++;
         k_i2v_node_scale<<<G, 256, 0, st>>>(d_nval, V - 1, Ceff, (double)n_global, d_nsc); launches++;
         CI(cudaMalloc(&d_ctr, 3 * sizeof(unsigned long long))); CI(cudaMemsetAsync(d_ctr, 0, 3 * sizeof(unsigned long long), st));
         if (seq) {
@@ -1970,7 +1996,7 @@ int i2v_train_impl(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, 
             a.D = D; a.W = W; a.lr_tab = d_lr; a.upd = c.update_lr_batch; a.seed = c.seed; a.iter = it; a.counters = d_ctr;
             a.node_scale = d_nsc; a.word_scale = d_wsc;
             static const bool no_hot = getenv("CTR_I2V_NO_HOT") != nullptr;
-            a.hot_n = no_hot ? 0 : std::min(kI2vHot, V - 1); a.hot_base = V - 1 - a.hot_n;
+            a.hot_n = no_hot ? 0 : std::min(kI2vHot, n_inner); a.hot_base = n_inner - a.hot_n;      // the last nodes created = the top of the tree
             const size_t sm = (size_t)std::max(a.hot_n, 1) * D * sizeof(float);
             CI(cudaEventRecord(e0, st));
             for (long p0 = 0; p0 < std::max<long>(nd_max_global, 1); p0 += seg) {

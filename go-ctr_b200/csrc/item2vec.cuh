@@ -262,9 +262,10 @@ k_i2v_node_scale(const long long* __restrict__ node_val, int nn, double ceff, do
 // Node.GetPath(maxDepth) (node.go:26-43) from the parent / code arrays of the tree: pass 0 writes the number of
 // (inner node, child code) steps of every word, pass 1 (after an exclusive scan) the steps in root -> leaf order.
 __global__ void __launch_bounds__(256)
-k_i2v_paths(const int* __restrict__ parent, const unsigned char* __restrict__ code, int V, int max_depth, int pass,
+k_i2v_paths(const int* __restrict__ parent, const unsigned char* __restrict__ code, const unsigned long long* __restrict__ cnt, int V, int max_depth, int pass,
             long long* __restrict__ poff, int* __restrict__ pnode, unsigned char* __restrict__ pcode) {
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < V; w += gridDim.x * blockDim.x) {
+        if (cnt[w] == 0) { if (pass == 0) poff[w] = 0; continue; }             // an id that never occurs has no path (never trained)
         int len = 0;
         for (int p = w; p != -1; p = parent[p]) len++;                         // leaf .. root, both included
         const int depth = max_depth < len ? max_depth : len;

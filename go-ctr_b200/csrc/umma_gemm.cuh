@@ -42,8 +42,13 @@ struct Args {
     const float* H; long ldh;   // UEPI_DSIGMOID: stored post-dropout activation
     float drop_p; uint32_t seed, stream;
     int stages;
+    int staged_epi;             // 1: the epilogue goes through per-warp shared-memory staging (coalesced 128-byte row segments)
     unsigned long long* dbg;    // optional timeline of CTA 0 (globaltimer ns): [it*8 + event], tiles at [4096 + t*4 + e]
 };
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiRowBytes = 144;                                  // 32 floats + 16 bytes of padding: conflict-free float4 access both ways
+constexpr int kEpiStageBytes = 32 * kEpiRowBytes;                  // one warp's 32 x 32 staging tile
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define UDBG(idx) do { if (a.dbg && blockIdx.x == 0 && (idx) < 8192) a.dbg[(idx)] = gtimer(); } while (0)
@@ -149,6 +154,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     auto tfull = [&](int i) { return bars + 8u * (3 * stages + i); };
     auto tempty = [&](int i) { return bars + 8u * (3 * stages + 2 + i); };
     const uint32_t tmem_slot = bars + 8u * (3 * stages + 4);
+    const uint32_t epi_base = (tmem_slot + 16u + 15u) & ~15u;          // kEpiWarps staging tiles (staged epilogue)
     const int acc_stride = bn <= 128 ? 128 : 256;
     const uint32_t ncols = 2u * acc_stride;
 
@@ -260,6 +266,82 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const long gm = (long)tile * kBlockM + row_in_tile;
             const uint32_t trow = tmem_base + (uint32_t)(acc * acc_stride) + ((uint32_t)(q * 32) << 16);
             const uint32_t ctr0 = (uint32_t)((uint64_t)gm * (uint64_t)a.N);
+            if (a.staged_epi) {
+                // Staged epilogue.  tcgen05.ld hands every thread one ROW of the tile, so storing straight from registers
+                // writes 32 different rows per instruction (16 useful bytes of each 128-byte line).  Here a warp transposes
+                // 32 rows x 32 columns through its private shared-memory tile: thread r writes its row as float4s (row pitch
+                // 144 B: the 8 lanes of a quarter-warp cover all 32 banks), then every instruction moves 4 rows x 128
+                // contiguous bytes between shared and global memory — full lines, for the C store and for the H load.
+                const uint32_t stg = epi_base + (uint32_t)(warp - 6) * kEpiStageBytes;
+                const uint32_t my_row = stg + (uint32_t)lane * kEpiRowBytes;
+                const int sub = lane >> 3, c4 = (lane & 7) * 4;                     // coalesced phase: row 4*j + sub, columns c4..c4+3
+                const long tile_row0 = (long)tile * kBlockM + q * 32;
+                const int nch32 = (a.Nz + 31) / 32;
+                const float kp = a.drop_p > 0.0f ? 1.0f - a.drop_p : 1.0f;
+                for (int cj = half; cj < nch32; cj += 2) {
+                    const int c0 = cj * 32;
+                    uint32_t ra[16], rb[16];
+                    tmem_ld16_async(trow + (uint32_t)c0, ra);
+                    if (c0 + 16 < bn) tmem_ld16_async(trow + (uint32_t)(c0 + 16), rb);
+                    if (EPI == UEPI_DSIGMOID) {                                      // H tile → staging, coalesced
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const long gr = tile_row0 + 4 * j + sub;
+                            const float4 t = (gr < a.M && c0 + c4 < a.Nz) ? ldg4(a.H + gr * a.ldh + c0 + c4) : zero4();
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(stg + (uint32_t)(4 * j + sub) * kEpiRowBytes + (uint32_t)c4 * 4u),
+                                         "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+                        }
+                        __syncwarp();
+                    }
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) { v[j] = __uint_as_float(ra[j]); v[16 + j] = (c0 + 16 < bn) ? __uint_as_float(rb[j]) : 0.0f; }
+                    if (EPI == UEPI_DSIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 hq;
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(hq.x), "=f"(hq.y), "=f"(hq.z), "=f"(hq.w) : "r"(my_row + (uint32_t)j * 4u));
+                            const float hs[4] = {hq.x, hq.y, hq.z, hq.w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) { const float hh = hs[e] * kp; v[j + e] *= inv_keep * hh * (1.0f - hh); }   // keep*h*(1-h), h = hd*(1-p)
+                        }
+                        __syncwarp();
+                    } else if (EPI == UEPI_SIGMOID_DROP) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float x = v[j];
+                            float sg = __fdividef(1.0f, 1.0f + __expf(-x));
+                            sg = x > 15.0f ? 1.0f : sg;
+                            sg = x < -88.0f ? 0.0f : sg;
+                            v[j] = sg;
+                        }
+                        if (a.drop_p > 0.0f) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) v[j] *= uniform24(a.seed, a.stream, ctr0 + (uint32_t)(c0 + j)) < keep_thr ? inv_keep : 0.0f;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = (c0 + j < a.N) ? v[j] : 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(my_row + (uint32_t)j * 4u), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const long gr = tile_row0 + 4 * j + sub;
+                        float4 t;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                     : "r"(stg + (uint32_t)(4 * j + sub) * kEpiRowBytes + (uint32_t)c4 * 4u));
+                        if (gr < a.M && c0 + c4 < a.Nz) *reinterpret_cast<float4*>(a.C + gr * a.ldc + c0 + c4) = t;
+                    }
+                    __syncwarp();
+                }
+                tc_fence_before();
+                mbar_arrive(tempty(acc));
+                if (threadIdx.x == 192) UDBG(4096 + tcount * 4 + 1);
+                continue;
+            }
             // one 16-column chunk: registers → fused epilogue → 64 contiguous bytes of this thread's row.
             // Straight-line and branch-free so the 16 elements overlap in the pipes.
             auto process = [&](const uint32_t (&r)[16], int ci) {
