@@ -1,12 +1,11 @@
-"""Host-side statement of the multi-GPU exchange plan the engine's kernels implement
-(go-ctr_b200/csrc/comm_impl.cuh): ITEM_EMB row r lives on rank r % world at local row
-r // world; a batch's (S+1)*B lookups are bucketed by owner, ids go to the owners (all-to-all), rows
-come back, row gradients return the same way.  Written against torch.distributed so the very same
-protocol runs over gloo on CPU (tests/test_shard_gloo.py, world_size 2) — the device code replaces the
-numpy steps with k_owner_count / k_owner_fill / k_gather_local / k_scatter_local and NCCL send/recv.
+"""Semantic model of the row-sharded placement (test infrastructure; SURVEY.md §8e, go-ctr_b200/csrc/comm.cuh):
+ITEM_EMB row r lives on rank r % world at local row r // world; every lookup of a rank's batch is served from the OWNER's
+shard, every row gradient (already scaled by -lr/world) is added into the OWNER's shard.  On the GPUs the kernels do this
+with peer loads / red.add over NVLink mappings, without any exchange phase; here the same data movement is spelled out as
+torch.distributed all-to-alls so that it runs over gloo on CPU with world_size 2 (tests/test_shard_gloo.py): what the
+test pins is the owner mapping and the equivalence "sharded gather / scatter == the single-table gather / scatter-add".
 
-The reference has no distributed code at all; this is new-framework design, kept
-deliberately small."""
+The reference has no distributed code at all."""
 import numpy as np
 
 
@@ -57,14 +56,14 @@ def fetch_rows(dist, torch, shard, hist, item_row, world):
     dist.all_to_all_single(rcnt_t, torch.from_numpy(scnt))
     rcnt = rcnt_t.numpy()
     recv_rows = _all_to_all(dist, torch, send_rows, scnt, rcnt)
-    gathered = shard[recv_rows]                                   # k_gather_local
+    gathered = shard[recv_rows]                                   # the owner's rows (GPU: ld.global from the peer mapping)
     rows_local = _all_to_all(dist, torch, gathered, rcnt, scnt)
     return rows_local, slot, (send_rows, scnt, rcnt, recv_rows)
 
 
 def return_grads(dist, torch, shard, grad_local, plan):
-    """Backward leg: grad_local [n_valid, D] (already scaled by -lr/world) goes back to the owners, who
-    add it into their shard (k_scatter_local)."""
+    """Backward leg: grad_local [n_valid, D] (already scaled by -lr/world) is added into the owners' shards
+    (GPU: red.global.add.v4.f32 into the peer mapping)."""
     send_rows, scnt, rcnt, recv_rows = plan
     g = _all_to_all(dist, torch, grad_local, scnt, rcnt)
     np.add.at(shard, recv_rows, g)
@@ -72,7 +71,8 @@ def return_grads(dist, torch, shard, grad_local, plan):
 
 
 def allreduce_replicated(dist, torch, dense_grads, table_grad, cost_sum):
-    """The replicated placement's one collective (comm_allreduce_grads with the table-shaped buffer, comm_impl.cuh):
+    """The replicated placement's one collective (comm_allreduce_grads with the table-shaped buffer, comm_impl.cuh; the
+    sharded placement all-reduces its replicated hot rows the same way):
     dense gradients, the row-gradient buffer [I, D] and the cost sum, summed over the ranks, in place."""
     bufs = [torch.from_numpy(g) for g in dense_grads] + [torch.from_numpy(table_grad)]
     for t in bufs:

@@ -1,4 +1,4 @@
-"""world_size-2 gloo test (CPU) of the multi-GPU exchange plan: sharded gather == direct gather, and the
+"""world_size-2 gloo test (CPU) of the row-sharded placement's data movement (tests/shard_model.py): sharded gather == direct gather, and the
 gradient return leg == a single-process scatter-add over the concatenated batches."""
 import os
 import socket
@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from go_ctr_b200 import shard as sh
+from tests import shard_model as sh
 
 
 def _free_port():
