@@ -1830,6 +1830,45 @@ void ctr_i2v_config_default(ctr_i2v_config* c) {
 }
 
 namespace {
+// Large transfers between PAGEABLE caller memory and the device (item2vec: the token stream in, the vector table out):
+// two pinned bounce buffers, host-side memcpy by the copy pool overlapping the DMA of the other buffer.
+cudaError_t big_copy(void* dst, const void* src, size_t bytes, bool to_device, cudaStream_t st) {
+    const size_t kChunk = (size_t)32 << 20;
+    if (bytes < ((size_t)8 << 20)) { cudaError_t e = cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st); return e != cudaSuccess ? e : cudaStreamSynchronize(st); }
+    unsigned char* pin[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) { e = cudaHostAlloc(&pin[i], kChunk, cudaHostAllocDefault); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming); }
+    if (e == cudaSuccess) {
+        CopyPool pool(7);
+        const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+        if (to_device) {
+            for (size_t c = 0; c < nchunks && e == cudaSuccess; c++) {
+                const int b = (int)(c & 1); const size_t off = c * kChunk, m = std::min(kChunk, bytes - off);
+                if (c >= 2) e = cudaEventSynchronize(ev[b]);
+                pool.copy(pin[b], (const char*)src + off, m);
+                if (e == cudaSuccess) e = cudaMemcpyAsync((char*)dst + off, pin[b], m, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        } else {
+            // DMA chunk c+1 while the pool copies chunk c out of its bounce buffer
+            if (nchunks > 0) { e = cudaMemcpyAsync(pin[0], src, std::min(kChunk, bytes), cudaMemcpyDeviceToHost, st); if (e == cudaSuccess) e = cudaEventRecord(ev[0], st); }
+            for (size_t c = 0; c < nchunks && e == cudaSuccess; c++) {
+                const int b = (int)(c & 1); const size_t off = c * kChunk, m = std::min(kChunk, bytes - off);
+                if (c + 1 < nchunks) {
+                    const size_t off2 = (c + 1) * kChunk, m2 = std::min(kChunk, bytes - off2);
+                    e = cudaMemcpyAsync(pin[b ^ 1], (const char*)src + off2, m2, cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess) e = cudaEventRecord(ev[b ^ 1], st);
+                }
+                if (e == cudaSuccess) e = cudaEventSynchronize(ev[b]);
+                if (e == cudaSuccess) pool.copy((char*)dst + off, pin[b], m);
+            }
+        }
+    }
+    for (int i = 0; i < 2; i++) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+    return e;
+}
+
 struct I2vDist { int rank = 0, world = 1; void* nccl = nullptr; long sync_every = 0; };
 
 // embedding.TrainEmbedding on the device.  Stream-proportional work (dictionary counts, MinCount filter) and the
@@ -1870,7 +1909,7 @@ int i2v_train_impl(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, 
         CI(cudaMalloc(&d_tok, sizeof(int) * (size_t)n)); CI(cudaMalloc(&d_doc, sizeof(int) * (size_t)n)); CI(cudaMalloc(&d_keep, (size_t)n));
         CI(cudaMalloc(&d_cnt64, sizeof(unsigned long long) * (size_t)V)); CI(cudaMalloc(&d_bad, sizeof(int))); CI(cudaMalloc(&d_nd, sizeof(long)));
         CI(cudaMalloc(&d_misc, 4 * sizeof(unsigned long long)));
-        CI(cudaMemcpyAsync(d_tok, tokens, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CI(big_copy(d_tok, tokens, sizeof(int) * (size_t)n, true, st));
         CI(cudaMemsetAsync(d_cnt64, 0, sizeof(unsigned long long) * (size_t)V, st)); CI(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
         k_i2v_count<<<G, 256, 0, st>>>(d_tok, (long)n, V, d_cnt64, d_bad); launches++;
         unsigned long long n_global = (unsigned long long)n;
@@ -2023,7 +2062,8 @@ int i2v_train_impl(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, 
             CI(cudaEventRecord(e1, st)); CI(cudaStreamSynchronize(st));                   // lr_tab is reused by the next iteration
             float ms = 0; CI(cudaEventElapsedTime(&ms, e0, e1)); ms_total += ms;
         }
-        CI(cudaMemcpyAsync(emb_out, d_syn0, sizeof(float) * (size_t)V * D, cudaMemcpyDeviceToHost, st));
+        CI(cudaStreamSynchronize(st));
+        CI(big_copy(emb_out, d_syn0, sizeof(float) * (size_t)V * D, false, st));
         CI(cudaMemcpyAsync(hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
         CI(cudaStreamSynchronize(st));
         if (stats) {
