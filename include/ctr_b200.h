@@ -65,9 +65,11 @@ typedef struct {
     float   table_lr;         /* SGD step for embedding rows (engine extension) */
     int32_t gemm;             /* CTR_GEMM_* */
     int32_t device;           /* CUDA device ordinal */
-    int32_t rank, world;      /* one handle per GPU; ITEM_EMB is row-sharded (owner(row) = row % world) or, when small, replicated */
-    int32_t reserved[8];      /* tuning knobs, 0 = automatic: [0] hot rows with replica accumulators (< 0: none);
-                                 [1] ITEM_EMB placement under world > 1: 1 = always shard, 2 = always replicate
+    int32_t rank, world;      /* one handle (process) per GPU; large ITEM_* tables are row-sharded (owner(row) = row % world, world in
+                                 {2,4,8}: peers read / update the owner's HBM over NVLink), small ones replicated */
+    int32_t reserved[8];      /* tuning knobs, 0 = automatic: [0] hot rows (ids [0, n): keep rows ordered by popularity) with replica
+                                 accumulators — and, on row-sharded tables, a replica on every rank (< 0: none; default 32768);
+                                 [1] ITEM_EMB / ITEM_FEAT placement under world > 1: 1 = always shard, 2 = always replicate
                                  (default: replicate tables <= 32 MB, shard larger ones) */
 } ctr_config;
 
@@ -99,7 +101,9 @@ int ctr_get_weights(ctr_handle* h, float* mlp0, float* mlp1, float* mlp2, float*
 /* Feature / embedding tables resident in HBM: replaces UserFeatureCache / ItemFeatureCache /
  * itemEmbeddingMap (rcmd.go:30-36, 473-505).  rows is [nrows, width] row-major.  With world > 1,
  * ITEM_EMB upload takes the FULL table on every rank and keeps rows r % world == rank — or all of them when the
- * table is small enough to be replicated (<= 32 MB, see ctr_config.reserved[1]); download mirrors that. */
+ * table is small enough to be replicated (<= 32 MB, see ctr_config.reserved[1]); download mirrors that (a sharded
+ * table's download fills this rank's rows only).  ITEM_FEAT follows the same rule; USER_FEAT is always replicated.
+ * Row ids the entry points receive are range-checked on the device: an id outside [0, rows) reads as a missing row. */
 int ctr_table_upload(ctr_handle* h, int which, const float* rows, int64_t nrows, int32_t width);
 int ctr_table_download(ctr_handle* h, int which, float* rows, int64_t nrows, int32_t width);
 /* Synthetic table generated on the device with the counter RNG (benchmarks with 10M-100M rows,
@@ -158,7 +162,9 @@ int ctr_predict_idx(ctr_handle* h, const int32_t* user_row, const int32_t* item_
 
 /* Same step with DEVICE-resident index / label buffers; asynchronous on the engine stream, no host
  * sync (stats->cost is not filled; read it with ctr_last_cost after ctr_sync).  Used when the caller
- * keeps the sample stream in HBM (bench.py's `value` leg; the device-side ubcache row f2). */
+ * keeps the sample stream in HBM (bench.py's `value` leg; the device-side ubcache row f2).
+ * The *_dev entry points, ctr_sync and ctr_last_cost do not take the handle's mutex: drive a handle's device-side
+ * entry points from one thread (the host-buffer entry points serialise themselves). */
 int ctr_train_step_idx_dev(ctr_handle* h, const int32_t* d_user_row, const int32_t* d_item_row,
                            const int32_t* d_hist_rows, const float* d_label, int32_t B);
 int ctr_predict_idx_dev(ctr_handle* h, const int32_t* d_user_row, const int32_t* d_item_row,
