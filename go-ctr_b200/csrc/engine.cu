@@ -761,8 +761,17 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         a.lr = c.lr; a.l2 = c.l2; a.inv_batch = ab > 1 ? 1.0f / (float)ab : 1.0f; a.b1 = c.beta1; a.b2 = c.beta2; a.eps = c.eps;
         a.c1 = (float)(1.0 - std::pow((double)c.beta1, (double)t));
         a.c2 = (float)(1.0 - std::pow((double)c.beta2, (double)t));
+        const bool split_in_adam = um && h->um.ready;
+        if (split_in_adam) {     // the next step's K-major TF32 operand copies come straight out of the optimiser (same layouts as umma_split_weights)
+            auto& u = h->um;
+            a.sp[0][0] = SplitOut{u.Wt0[0], u.Wt0[1], (long)h->Kp, 1, 0, in};                     // W0ᵀ [H0, in]
+            a.sp[0][1] = SplitOut{u.W0s[0], u.W0s[1], (long)h->H0p, 0, c.uP, 2 * c.D};            // W0[uP:uP+2D, :]
+            a.sp[1][0] = SplitOut{u.Wt1[0], u.Wt1[1], (long)h->H0p, 1, 0, c.H0};                  // W1ᵀ [H1, H0]
+            a.sp[1][1] = SplitOut{u.W1s[0], u.W1s[1], (long)h->H1p, 0, 0, c.H0};                  // W1  [H0, H1]
+            a.nsp[0] = a.nsp[1] = 2;
+        }
         RET(launch(h, "adam_dense", [&] { k_adam<<<h->num_sms, 256, 0, h->stream>>>(a); }));
-        h->um.dirty = true;
+        h->um.dirty = !split_in_adam;
         h->step++;
     }
     return CTR_OK;

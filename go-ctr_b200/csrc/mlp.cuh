@@ -244,8 +244,12 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
 // One launch covers all four tensors (logical [rows, cols] inside padded storage with stride ld).
 // -------------------------------------------------------------------------------------------------
 struct AdamTensor { float* w; float* g; float* m; float* v; int rows, cols; long ld; };
+// TF32 hi/lo operand copy of a weight tensor, written by the optimiser itself (the tcgen05 GEMMs of the next step read
+// them; no separate split launch): element (r, c) goes to [c*old + r] (transpose) or [r*old + c], rows [r0, r0+nr) only
+struct SplitOut { float* hi; float* lo; long old; int transpose, r0, nr; };
 struct AdamArgs {
     AdamTensor t[4]; int nt;
+    SplitOut sp[4][2]; int nsp[4];
     float lr, l2, inv_batch, b1, b2, eps, c1, c2;
     float gscale;       // 1/world after the all-reduce(sum) of the ranks' local-mean gradients, else 1
 };
@@ -263,8 +267,17 @@ __global__ void __launch_bounds__(256) k_adam(AdamArgs a) {
             float m = a.b1 * t.m[off] + (1.0f - a.b1) * g;
             float v = a.b2 * t.v[off] + (1.0f - a.b2) * (g * g);
             t.m[off] = m; t.v[off] = v;
-            t.w[off] = w - a.lr * (m / a.c1) / (sqrtf(v / a.c2) + a.eps);
+            const float wn = w - a.lr * (m / a.c1) / (sqrtf(v / a.c2) + a.eps);
+            t.w[off] = wn;
             t.g[off] = 0.0f;
+            for (int k = 0; k < a.nsp[ti]; k++) {
+                const SplitOut& so = a.sp[ti][k];
+                const int r = (int)(i / t.cols) - so.r0, c = (int)(i % t.cols);
+                if (r < 0 || r >= so.nr) continue;
+                const float hi = __uint_as_float(__float_as_uint(wn) & 0xFFFFE000u);
+                const long o = so.transpose ? (long)c * so.old + r : (long)r * so.old + c;
+                so.hi[o] = hi; so.lo[o] = wn - hi;
+            }
         }
     }
 }

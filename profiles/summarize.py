@@ -52,6 +52,14 @@ def launches(path, out):
         f.write('| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n')
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('| %s | %d | %.1f | %.1f | %.3f |\n' % (k, n, t, t / n, t / tot))
+        # the train step's own kernels (set-up: table fill, id maps, L2 flush fills, key resolve are not part of a step)
+        step = collections.OrderedDict((k, v) for k, v in agg.items() if any(k.startswith(p) for p in
+                                       ('k_attn', 'umma::', 'k_head', 'k_hot_apply', 'k_adam', 'k_peer_barrier', 'k_apply_table', 'k_segment', 'k_scatter_keys')))
+        if step:
+            st = sum(a[1] for a in step.values())
+            f.write('\n## share inside the train step (set-up kernels excluded)\n\n| kernel | launches | avg us | share of step |\n|---|---|---|---|\n')
+            for k, (n, t) in sorted(step.items(), key=lambda kv: -kv[1][1]):
+                f.write('| %s | %d | %.1f | %.3f |\n' % (k, n, t / n, t / st))
 
 
 if __name__ == '__main__':
