@@ -329,7 +329,7 @@ def main():
     hbm_peak, peak_src = load_peaks()
     dev = torch.device("cuda", local)
 
-    def build_engine(w, B, placement=0, world_=None, rank_=None, table_opt=None, dropout=None):
+    def build_engine(w, B, placement=0, world_=None, rank_=None, table_opt=None, dropout=None, hot=None):
         wd = world if world_ is None else world_; rk = rank if rank_ is None else rank_
         model = g.MODEL_DIN_COS if w["model"] == "din" else g.MODEL_YOUTUBE
         topt = {"sgd": g.TABLE_SGD, "det": g.TABLE_SGD_DETERMINISTIC, "frozen": g.TABLE_FROZEN, "adam": g.TABLE_ADAM}[table_opt or args.table_opt]
@@ -338,6 +338,10 @@ def main():
         cfg = g.engine.default_config(model, uP=w["uP"], S=w["S"], D=w["D"], cF=w["cF"], batch=B, pred_batch=B,
                                       table_opt=topt, table_lr=0.05, gemm=gm, device=local, rank=rk, world=wd, seed=1, **kw)
         cfg.reserved[1] = placement          # ITEM_* under world > 1: 0 = by size (> 32 MB shards), 1 = row-sharded, 2 = replicated
+        # popular-row handling (replica accumulators; on sharded tables also a replica of rows [0, 32768) on every rank with an
+        # all-reduce of their gradient sums): a uniform id stream has no popular rows — switched off there, default for Zipf ids
+        zipf_ids = w["zipf"] if hot is None else hot
+        cfg.reserved[0] = 0 if zipf_ids else -1
         eng = g.Engine(cfg)
         if wd > 1:
             ids = [None]
@@ -575,7 +579,7 @@ def main():
     rl, kern, nv = roofline_of(w, prof_leg, psteps, B, traffic_key=wname if world == 1 else None)
     value = B * world * args.steps / (leg["ms"] * 1e-3)
     cfg = config_of(args, w, wname, world)
-    engine_cfg = dict(table_opt=args.table_opt, gemm=args.gemm,
+    engine_cfg = dict(table_opt=args.table_opt, gemm=args.gemm, popular_rows="off (uniform ids)" if not w["zipf"] else "rows [0, 32768)",
                placement=("single GPU: the whole table in one HBM (%.1f GB ITEM_EMB + %.1f GB ITEM_FEAT)" % (w["I"] * w["D"] * 4 / 1e9, w["I"] * 56 * 4 / 1e9) if world == 1 else
                           "1 process per GPU; ITEM_EMB / ITEM_FEAT rows sharded row%world; gather and red.add go to the owner's HBM over NVLink peer mappings "
                           "(VMM allocations shared as fds), 2 device-side barriers + 1 NCCL all-reduce (dense gradients) per step" if sharded else
@@ -594,11 +598,14 @@ def main():
     line["e2e_detail"] = e2e
     if not args.no_side_legs:
         side = {}
-        # Zipf(1.05) item popularity on the same table: hot rows are gathered / updated by every sample
-        zl = timed_leg(eng, w, B, max(5, args.steps // 4), 3, clocks=False, zipf=True, seed=300)
-        side["zipf_ids"] = {"what": "same engine and table, item / history ids drawn Zipf(1.05)", "value": B * world * max(5, args.steps // 4) / (zl["ms"] * 1e-3),
-                            "unit": "samples/s", "ms_per_step": zl["ms"] / max(5, args.steps // 4)}
         del eng
+        torch.cuda.empty_cache()
+        # Zipf(1.05) item popularity on the same table (popular-row handling on): hot rows are gathered / updated by every sample
+        eng_z = build_engine(w, B, hot=True)
+        zl = timed_leg(eng_z, w, B, max(5, args.steps // 4), 3, clocks=False, zipf=True, seed=300)
+        side["zipf_ids"] = {"what": "same table, item / history ids drawn Zipf(1.05); rows [0, 32768) handled as popular rows", "value": B * world * max(5, args.steps // 4) / (zl["ms"] * 1e-3),
+                            "unit": "samples/s", "ms_per_step": zl["ms"] / max(5, args.steps // 4)}
+        del eng_z
         torch.cuda.empty_cache()
         if world > 1 and sharded:
             # BASELINE configs[3] read literally: GLOBAL batch 65536 over the N GPUs (strong-scaling point of the same table)

@@ -6,6 +6,7 @@
 // "embedding not found → zeros" (rcmd.go:501-505,519-521).
 #pragma once
 #include "common.cuh"
+#include "ubcache.cuh"
 
 namespace ctr {
 
@@ -97,9 +98,7 @@ k_keys_resolve(const unsigned long long* __restrict__ ukeys, const int* __restri
             if (end > beg) {
                 long long mt = keys3[2 * (long)B + b];
                 if (mt == 0) mt = ub_ts[beg];
-                long long lo = beg, hi = end;
-                while (lo < hi) { const long long mid = (lo + hi) >> 1; if (ub_ts[mid] <= mt) hi = mid; else lo = mid + 1; }
-                first = lo;
+                first = ub_first_leq(ub_ts, beg, end, mt, lane);
             }
         }
         const long long avail = end - first;

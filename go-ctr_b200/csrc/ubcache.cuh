@@ -8,7 +8,19 @@
 
 namespace ctr {
 
-// one warp per sample: lane-parallel lower bound over the (descending) timestamps, then a coalesced
+// First index in [beg, end) whose timestamp is <= mt (timestamps descend), or end.  Warp-cooperative: a few
+// binary steps (uniform across the warp) narrow the range to 32 entries, then ONE coalesced load + ballot finishes —
+// 3 dependent memory round trips for a 100-event history instead of 7.
+__device__ __forceinline__ long long ub_first_leq(const long long* __restrict__ ts, long long beg, long long end, long long mt, int lane) {
+    long long lo = beg, hi = end;                        // invariant: answer in [lo, hi]
+    while (hi - lo > 32) { const long long mid = (lo + hi) >> 1; if (ts[mid] <= mt) hi = mid; else lo = mid + 1; }
+    const long long i = lo + lane;
+    const bool hit = i < hi && ts[i] <= mt;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    return m ? lo + (__ffs(m) - 1) : hi;
+}
+
+// one warp per sample: lower bound over the (descending) timestamps, then a coalesced
 // write of up to S item rows
 __global__ void __launch_bounds__(256)
 k_ub_window(const long long* __restrict__ off, const long long* __restrict__ ts, const int* __restrict__ items,
@@ -24,10 +36,7 @@ k_ub_window(const long long* __restrict__ off, const long long* __restrict__ ts,
         if (end > beg) {
             long long mt = max_ts[b];
             if (mt == 0) mt = ts[beg];                                      // cache.go:72-74
-            // ts is descending: find the first index with ts <= mt (binary search, uniform across the warp)
-            long long lo = beg, hi = end;
-            while (lo < hi) { const long long mid = (lo + hi) >> 1; if (ts[mid] <= mt) hi = mid; else lo = mid + 1; }
-            first = lo;
+            first = ub_first_leq(ts, beg, end, mt, lane);      // every lane of the warp takes this branch (u, beg, end are warp-uniform)
         }
         const long long avail = end - first;
         for (int s = lane; s < S; s += 32) hist[(long)b * S + s] = s < avail ? items[first + s] : -1;

@@ -490,7 +490,7 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t ncols = 512;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; s++) { mbar_init(full(s), 1); mbar_init(conv(s), 128); mbar_init(empty(s), 1); }
+        for (int s = 0; s < stages; s++) { mbar_init(full(s), 1); mbar_init(conv(s), 384); mbar_init(empty(s), 1); }
         mbar_init(tdone, 1);
         fence_barrier_init();
     }
@@ -542,7 +542,9 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             umma_commit(tdone);
         }
-    } else if (warp < 6) {                                          // converters: TF32 round-to-nearest in place
+    } else {
+        // converters: TF32 round-to-nearest in place.  All twelve remaining warps convert (the eight epilogue warps have
+        // nothing else to do until the accumulators are complete): the rounding pass, not the MMAs, paces the main loop.
         const int c = threadIdx.x - 64;
         const int n16 = (int)((aBytes + bBytes) / 16u);
         for (int it = 0; it < nkb; it++) {
@@ -550,17 +552,17 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             mbar_wait(full(s), ph);
             const uint32_t pa = sA(s), pb = sB(s);
             const int na16 = (int)(aBytes / 16u);
-            for (int i0 = c; i0 < n16; i0 += 128 * 4) {
+            for (int i0 = c; i0 < n16; i0 += 384 * 4) {
                 float4 x[4]; uint32_t ad[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const int i = i0 + 128 * u;
+                    const int i = i0 + 384 * u;
                     ad[u] = i < na16 ? pa + 16u * i : pb + 16u * (i - na16);
                     if (i < n16) asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "r"(ad[u]));
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (i0 + 128 * u < n16)
+                    if (i0 + 384 * u < n16)
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ad[u]), "f"(tf32_rn(x[u].x)), "f"(tf32_rn(x[u].y)),
                                      "f"(tf32_rn(x[u].z)), "f"(tf32_rn(x[u].w)) : "memory");
                 }
@@ -568,8 +570,7 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             fence_proxy_async();
             mbar_arrive(conv(s));
         }
-    } else {                                                        // epilogue warps 6..13: C += accumulators
-        if (nkb > 0) {
+        if (warp >= 6 && nkb > 0) {                                 // epilogue warps 6..13: C += accumulators
             const int q = warp & 3, half = (warp - 6) >> 2;
             mbar_wait(tdone, 0);
             tc_fence_after();
