@@ -439,14 +439,13 @@ struct BwdOut {
     float  neg_lr;      // -table_lr
     float* hot_acc;     // [hot_reps, hot_rows, D] replica accumulators (sums of -lr * gradient)
     int    hot_rows, hot_reps;
-    unsigned char* hot_dirty;   // [hot_rows] set when a batch touched the row: the fold kernel skips the clean ones
     float* scatter_base;    // where row gradients are added (row idx * lde): the table itself, or the per-lookup
                             // gradient buffer of the sharded path
 };
 
 // destination of one row's (already -lr scaled) gradient: a hot-row replica accumulator or the table row
 __device__ __forceinline__ float* scatter_dst(const RowSrc& r, const Dims& d, const BwdOut& o, int idx, int rep) {
-    if (idx < o.hot_rows) { o.hot_dirty[idx] = 1; return o.hot_acc + ((long)rep * o.hot_rows + idx) * d.D; }
+    if (idx < o.hot_rows) return o.hot_acc + ((long)rep * o.hot_rows + idx) * d.D;
     return o.scatter_base + (long)idx * r.lde;
 }
 
@@ -756,11 +755,10 @@ k_attn_bwd_idx(RowSrc r, Dims d, const float* __restrict__ att,
 // (the accumulators already hold -lr * gradient, so scale = 1)
 __global__ void __launch_bounds__(256)
 k_hot_apply(float* __restrict__ emb, long lde, float* __restrict__ hot_acc, int hot_rows, int hot_reps,
-            int D, float neg_lr, const unsigned char* __restrict__ dirty) {
+            int D, float neg_lr) {
     const long n4 = (long)hot_rows * (D / 4);
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         const long row = i / (D / 4); const int c = (int)(i % (D / 4)) * 4;
-        if (!dirty[row]) continue;                 // uniform ids over a big table touch a handful of the hot rows per step
         float4 s = zero4();
         for (int rep = 0; rep < hot_reps; rep++) {
             float4* p = reinterpret_cast<float4*>(hot_acc + ((long)rep * hot_rows + row) * D + c);

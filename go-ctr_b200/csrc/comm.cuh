@@ -54,7 +54,7 @@ struct Comm {
     // replicated hot rows of a sharded ITEM_EMB: rows [0, hot_k) live on every rank (hot_tab), their -lr/world scaled
     // gradient sums (hot_sum) are all-reduced with the dense gradients — a Zipf-popular row is neither pulled over
     // NVLink by every sample nor hammered by every rank's red.add
-    int hot_k = 0; float* hot_tab = nullptr; float* hot_sum = nullptr; float* hot_acc = nullptr; int hot_reps = 0; unsigned char* hot_dirty = nullptr;
+    int hot_k = 0; float* hot_tab = nullptr; float* hot_sum = nullptr; float* hot_acc = nullptr; int hot_reps = 0;
 };
 
 }  // namespace ctr

@@ -156,14 +156,12 @@ int comm_hot_setup(ctr_handle* h) {
     if (want < 0) want = 0;
     want = (int)std::min<int64_t>(want, h->tab_rows[CTR_TABLE_ITEM_EMB]);
     for (float** p : {&cm.hot_tab, &cm.hot_sum, &cm.hot_acc}) if (*p) { cudaFree(*p); *p = nullptr; }
-    if (cm.hot_dirty) { cudaFree(cm.hot_dirty); cm.hot_dirty = nullptr; }
     cm.hot_k = want; cm.hot_reps = 0;
     if (want == 0) return CTR_OK;
     if (h->tab_ld[CTR_TABLE_ITEM_EMB] != D) return set_err(h, CTR_EINVAL, "replicated hot rows need D %% 4 == 0");
     RET(dalloc(h, &cm.hot_tab, (size_t)want * D, false)); RET(dalloc(h, &cm.hot_sum, (size_t)want * D));
     cm.hot_reps = (int)std::min<size_t>(16, std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)want * D * sizeof(float))));
     RET(dalloc(h, &cm.hot_acc, (size_t)cm.hot_reps * want * D));
-    RET(dalloc(h, &cm.hot_dirty, (size_t)want));
     RowSrc r{}; r.lde = D; r.wmask = cm.world - 1; r.wshift = cm.wshift; r.world = cm.world;
     for (int j = 0; j < cm.world; j++) r.peer_emb[j] = cm.peer_emb[j];
     RET(launch(h, "hot_rows_pull", [&] { k_hot_pull<<<h->num_sms * 4, 256, 0, h->stream>>>(r, cm.hot_tab, want, D); }));
@@ -325,8 +323,7 @@ static int comm_init(ctr_handle* h, const void* id, int32_t id_bytes) {
 static void comm_destroy(ctr_handle* h) {
     Comm& cm = h->comm;
     comm_close_peers(h);
-    for (void* p : {(void*)cm.table_grad, (void*)cm.rows_cache, cm.d_xchg, (void*)cm.hot_tab, (void*)cm.hot_sum, (void*)cm.hot_acc, (void*)cm.hot_dirty}) if (p) cudaFree(p);
-    cm.hot_dirty = nullptr;
+    for (void* p : {(void*)cm.table_grad, (void*)cm.rows_cache, cm.d_xchg, (void*)cm.hot_tab, (void*)cm.hot_sum, (void*)cm.hot_acc}) if (p) cudaFree(p);
     cm.hot_tab = cm.hot_sum = cm.hot_acc = nullptr; cm.hot_k = 0;
     vmm_free(&cm.arena_vmm);
     if (cm.lsock >= 0) { close(cm.lsock); cm.lsock = -1; }

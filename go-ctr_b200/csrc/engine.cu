@@ -119,7 +119,7 @@ struct ctr_handle {
     unsigned *keys = nullptr, *keys2 = nullptr, *pos = nullptr, *pos2 = nullptr;
     void* sort_tmp = nullptr; size_t sort_tmp_bytes = 0; size_t keys_cap = 0;
     double* d_cost = nullptr;
-    float* hot_acc = nullptr; int hot_rows = 0, hot_reps = 0; unsigned char* hot_dirty = nullptr;
+    float* hot_acc = nullptr; int hot_rows = 0, hot_reps = 0;
     float *emb_m = nullptr, *emb_v = nullptr;      // CTR_TABLE_ADAM: first / second moments of ITEM_EMB, same layout as the table
     // staging for host-pointer entry points
     int *s_user = nullptr, *s_item = nullptr, *s_hist = nullptr; float* s_label = nullptr;
@@ -562,13 +562,11 @@ int ensure_hot(ctr_handle* h) {
     want = (int)std::min<int64_t>(want, rows);
     if (h->hot_acc && h->hot_rows == want) return CTR_OK;
     if (h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; }
-    if (h->hot_dirty) { cudaFree(h->hot_dirty); h->hot_dirty = nullptr; }
     h->hot_rows = want; h->hot_reps = 0;
     if (want == 0) return CTR_OK;
     const size_t row_bytes = (size_t)h->cfg.D * sizeof(float);
     int reps = (int)std::min<size_t>(32, std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)want * row_bytes)));
     h->hot_reps = reps;
-    RET(dalloc(h, &h->hot_dirty, (size_t)want));
     return dalloc(h, &h->hot_acc, (size_t)reps * want * h->cfg.D);
 }
 
@@ -708,23 +706,21 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         bo.neg_lr = (adam_rows ? 1.0f : -c.table_lr) * o.grad_scale;
         bo.scatter_base = o.table_grad ? o.table_grad : h->tab[CTR_TABLE_ITEM_EMB];
         const bool hot = bo.sgd && vec_ok(h, r) && !o.comm;
-        if (hot) { RET(ensure_hot(h)); bo.hot_acc = h->hot_acc; bo.hot_rows = h->hot_rows; bo.hot_reps = h->hot_reps; bo.hot_dirty = h->hot_dirty; }
+        if (hot) { RET(ensure_hot(h)); bo.hot_acc = h->hot_acc; bo.hot_rows = h->hot_rows; bo.hot_reps = h->hot_reps; }
         const bool peer_hot = o.peer && bo.sgd && h->comm.hot_k > 0;
-        if (peer_hot) { bo.hot_acc = h->comm.hot_acc; bo.hot_rows = h->comm.hot_k; bo.hot_reps = h->comm.hot_reps; bo.hot_dirty = h->comm.hot_dirty; }
+        if (peer_hot) { bo.hot_acc = h->comm.hot_acc; bo.hot_rows = h->comm.hot_k; bo.hot_reps = h->comm.hot_reps; }
         // sharded tables: nobody's red.add may land in a row before every rank's forward has read it
         if (o.peer && bo.sgd) RET(comm_barrier(h));
         RET(attn_backward(h, r, bo, B));
         if (peer_hot)      // replica accumulators of the replicated hot rows → this rank's gradient sum (all-reduced below)
             RET(launch(h, "hot_rows_fold", [&] {
-                k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(h->comm.hot_sum, c.D, h->comm.hot_acc, h->comm.hot_k, h->comm.hot_reps, c.D, 1.0f, h->comm.hot_dirty);
+                k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(h->comm.hot_sum, c.D, h->comm.hot_acc, h->comm.hot_k, h->comm.hot_reps, c.D, 1.0f);
             }));
-        if (peer_hot) CU(h, cudaMemsetAsync(h->comm.hot_dirty, 0, (size_t)h->comm.hot_k, h->stream));
         if (hot && h->hot_rows > 0)
             RET(launch(h, "hot_rows_apply", [&] {
                 k_hot_apply<<<h->num_sms * 4, 256, 0, h->stream>>>(bo.scatter_base, h->tab_ld[CTR_TABLE_ITEM_EMB], h->hot_acc,
-                                                                h->hot_rows, h->hot_reps, c.D, 1.0f, h->hot_dirty);
+                                                                h->hot_rows, h->hot_reps, c.D, 1.0f);
             }));
-        if (hot && h->hot_rows > 0) CU(h, cudaMemsetAsync(h->hot_dirty, 0, (size_t)h->hot_rows, h->stream));
         if (learn_rows && sorted_rows && !fused_only) RET(deterministic_table_update(h, r, B, o.adam_batch > 0 ? o.adam_batch : B));
     }
     if (o.update) {
@@ -821,7 +817,6 @@ int table_alloc(ctr_handle* h, int which, int64_t nrows, int32_t width) {
     if (which == CTR_TABLE_ITEM_EMB) {
         h->comm.replicate = h->comm.world > 1 && !shard;
         if (h->hot_acc) { cudaFree(h->hot_acc); h->hot_acc = nullptr; h->hot_rows = 0; }
-        if (h->hot_dirty) { cudaFree(h->hot_dirty); h->hot_dirty = nullptr; }
         for (float** p : {&h->emb_m, &h->emb_v}) if (*p) { cudaFree(*p); *p = nullptr; }       // a new table starts a new solver state
     }
     if (which != CTR_TABLE_USER_FEAT) h->tab_gen++;           // peers hold mappings of the old allocation
@@ -1052,7 +1047,7 @@ void ctr_destroy(ctr_handle* h) {
     if (h->Gflat) cudaFree(h->Gflat);
     for (void* p : {(void*)h->X0, (void*)h->H0d, (void*)h->H1d, (void*)h->P, (void*)h->Z, (void*)h->dZ1, (void*)h->dZ0, (void*)h->dX,
                     (void*)h->dUb, (void*)h->dIt, (void*)h->keys, (void*)h->keys2, (void*)h->pos, (void*)h->pos2, h->sort_tmp,
-                    (void*)h->d_cost, (void*)h->s_user, (void*)h->s_item, (void*)h->s_hist, (void*)h->s_label, (void*)h->dXd, (void*)h->dYd, (void*)h->hot_acc, (void*)h->hot_dirty, (void*)h->emb_m, (void*)h->emb_v})
+                    (void*)h->d_cost, (void*)h->s_user, (void*)h->s_item, (void*)h->s_hist, (void*)h->s_label, (void*)h->dXd, (void*)h->dYd, (void*)h->hot_acc, (void*)h->emb_m, (void*)h->emb_v})
         if (p) cudaFree(p);
     for (int i = 0; i < 3; i++) if (h->scratch[i]) cudaFree(h->scratch[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
