@@ -248,7 +248,7 @@ def run_item2vec(args):
             dist.barrier()
         t0 = time.perf_counter()
         if world > 1:
-            emb, st = g.i2v_train_dist(toks, V, rank, world, nid[0], sync_every=args.i2v_sync, cfg=cfg)
+            emb, st = g.i2v_train_dist(toks, V, rank, world, nid[0], sync_every=args.i2v_sync, cfg=cfg, want_table=(rank == 0))   # the averaged table goes to the host once
         else:
             emb, st = g.i2v_train_ids(toks, V, cfg=cfg)
         wall = time.perf_counter() - t0

@@ -1887,7 +1887,7 @@ struct I2vDist { int rank = 0, world = 1; void* nccl = nullptr; long sync_every 
 // every sync_every positions (local SGD / model averaging — the reference's own trainer is Hogwild over goroutines,
 // word2vec.go:165-169; across GPUs the racy shared memory becomes periodic averaging).
 int i2v_train_impl(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, int32_t V, float* emb_out, ctr_i2v_stats* stats, I2vDist* dist) {
-    if (!cfg || !tokens || !emb_out || n < 1 || V < 2 || n > 0x7fffffffLL) return set_err(nullptr, CTR_EINVAL, "bad item2vec arguments");
+    if (!cfg || !tokens || (!emb_out && !dist) || n < 1 || V < 2 || n > 0x7fffffffLL) return set_err(nullptr, CTR_EINVAL, "bad item2vec arguments");
     const ctr_i2v_config& c = *cfg;
     const int D = c.dim, W = c.window;
     if (D < 4 || D > 128 || (D & (D - 1)) || W < 1 || c.iter < 1 || c.max_depth < 2 || c.update_lr_batch < 1)
@@ -2072,7 +2072,7 @@ int i2v_train_impl(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, 
             float ms = 0; CI(cudaEventElapsedTime(&ms, e0, e1)); ms_total += ms;
         }
         CI(cudaStreamSynchronize(st));
-        CI(big_copy(emb_out, d_syn0, sizeof(float) * (size_t)V * D, false, st));
+        if (emb_out) CI(big_copy(emb_out, d_syn0, sizeof(float) * (size_t)V * D, false, st));
         CI(cudaMemcpyAsync(hc, d_ctr, sizeof hc, cudaMemcpyDeviceToHost, st));
         CI(cudaStreamSynchronize(st));
         if (stats) {

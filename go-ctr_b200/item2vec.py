@@ -66,15 +66,16 @@ def i2v_train_ids(tokens, vocab, cfg=None, **kw):
     return emb, st
 
 
-def i2v_train_dist(tokens_shard, vocab, rank, world, nccl_id, sync_every=0, cfg=None, **kw):
-    """One rank of the multi-GPU trainer (ctr_i2v_train_dist): this rank's shard of the stream in, the averaged table out."""
+def i2v_train_dist(tokens_shard, vocab, rank, world, nccl_id, sync_every=0, cfg=None, want_table=True, **kw):
+    """One rank of the multi-GPU trainer (ctr_i2v_train_dist): this rank's shard of the stream in, the averaged table out
+    (want_table=False: this rank skips the copy of the table to the host and returns None for it)."""
     L = _e.load_library()
     cfg = cfg or i2v_default_config(**kw)
     tok = np.ascontiguousarray(tokens_shard, np.int32)
-    emb = np.empty((vocab, cfg.dim), np.float32)
+    emb = np.empty((vocab, cfg.dim), np.float32) if want_table else None
     st = I2vStats()
     rc = L.ctr_i2v_train_dist(C.byref(cfg), tok.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(tok.size), C.c_int32(vocab),
-                              emb.ctypes.data_as(C.POINTER(C.c_float)), C.byref(st), C.c_int32(rank), C.c_int32(world),
+                              emb.ctypes.data_as(C.POINTER(C.c_float)) if want_table else None, C.byref(st), C.c_int32(rank), C.c_int32(world),
                               C.c_char_p(nccl_id), C.c_int32(len(nccl_id)), C.c_int64(sync_every))
     if rc != 0:
         raise _e.CtrError(rc, L.ctr_last_error(None).decode())

@@ -271,7 +271,8 @@ int  ctr_i2v_train(const ctr_i2v_config* cfg, const int32_t* tokens, int64_t n, 
  * replica of both vector tables on its shard and the replicas are averaged (all-reduce) every sync_every centre
  * positions (0 = 4 Mi) — the reference's trainer is Hogwild over goroutines in one address space (word2vec.go:165-169);
  * across GPUs the shared memory becomes periodic model averaging.  The learning rate follows the GLOBAL position count.
- * emb_out receives the averaged table on every rank; id = ncclUniqueId bytes from ctr_comm_unique_id on rank 0.
+ * emb_out receives the averaged table (identical on every rank; ranks that do not need it may pass NULL and save the
+ * 4·vocab·dim-byte copy to the host); id = ncclUniqueId bytes from ctr_comm_unique_id on rank 0.
  * ctr_i2v_config.reserved[0] = 1 (single GPU only): sequential float64 parity mode — one warp walks the document in
  * order, reproducing the CPU restatement of the reference bit for bit (tests/test_gpu_i2v.py). */
 int  ctr_i2v_train_dist(const ctr_i2v_config* cfg, const int32_t* tokens_shard, int64_t n_shard, int32_t vocab,
