@@ -136,6 +136,8 @@ struct ctr_handle {
     int *kt_user = nullptr, *kt_item = nullptr; long long* kt_ts = nullptr; float* kt_label = nullptr; size_t kt_cap = 0;
     int *kt_flag = nullptr, *kt_pos = nullptr; void* kt_scan_tmp = nullptr; size_t kt_scan_bytes = 0; size_t kt_chunk = 0;
     unsigned long long* kt_count = nullptr;
+    static constexpr int kCnt = 8;                       // pinned ring of survivor counts read back chunk by chunk
+    unsigned long long* kt_count_host = nullptr; cudaEvent_t kt_counted[kCnt] = {};
     // dense-X residency
     float* dXd = nullptr; float* dYd = nullptr; size_t dXd_cap = 0, dYd_cap = 0;
 
@@ -485,6 +487,8 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
     const int grid = std::min(tiles, h->num_sms);
     const size_t smem = umma_smem(a.bn, a.stages);
     a.dbg = h->umma_dbg;
+    static const int pf = getenv("CTR_UMMA_PF") ? atoi(getenv("CTR_UMMA_PF")) : 0;     // measured: no gain (profiles/r02/EXPERIMENTS.md)
+    a.pf = std::max(0, std::min(pf, 64));
     static const bool epi_old = getenv("CTR_UMMA_EPI_OLD") != nullptr;
     a.staged_epi = epi_old ? 0 : 1;
     int rc = launch(h, name, [&] { umma::k_umma_gemm<EPI, true><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a); });
@@ -510,7 +514,27 @@ int umma_dw(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtens
     const int total_kb = (a.K + 31) / 32;
     const int grid = std::max(1, std::min(total_kb, h->num_sms));
     const size_t smem = (size_t)a.stages * ((size_t)8 * 4096 + (size_t)a.nb * 4096) + 8 * (3 * a.stages + 2) + 16 + 1024;
-    return launch(h, name, [&] { umma::k_umma_dw<<<grid, 448, smem, h->stream>>>(mA, mB, a); });
+    static const int pf = getenv("CTR_UMMA_DW_PF") ? atoi(getenv("CTR_UMMA_DW_PF")) : 0;
+    a.pf = std::max(0, std::min(pf, 16));
+    static const bool norot = getenv("CTR_DW_NO_ROTATE") != nullptr;
+    a.rotate = norot ? 0 : 1;
+    a.tl = h->umma_dbg;
+    int rc = launch(h, name, [&] { umma::k_umma_dw<<<grid, 448, smem, h->stream>>>(mA, mB, a); });
+    if (rc == CTR_OK && h->umma_dbg) {
+        std::vector<unsigned long long> t(64);
+        cudaStreamSynchronize(h->stream);
+        cudaMemcpy(t.data(), h->umma_dbg, 64 * 8, cudaMemcpyDeviceToHost);
+        cudaMemset(h->umma_dbg, 0, 64 * 8);
+        FILE* f = fopen("gpurun_out/umma_timeline.txt", "a");
+        if (f) {
+            fprintf(f, "# %s K=%d na=%d nb=%d stages=%d pf=%d grid=%d\n", name, a.K, a.na, a.nb, a.stages, a.pf, grid);
+            fprintf(f, "first_box_landed %llu accumulators_done %llu kernel_end %llu  mma_batches:", t[1] - t[0], t[2] - t[0], t[3] - t[0]);
+            for (int i = 8; i < 64 && t[i]; i++) fprintf(f, " %llu", t[i] - t[0]);
+            fprintf(f, "\n");
+            fclose(f);
+        }
+    }
+    return rc;
 }
 
 // the weight-gradient GEMMs run on tcgen05 when the padded widths fit 8 column blocks and the batch
@@ -649,7 +673,11 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         HeadArgs a{}; a.H1d = h->H1d; a.ldh = h->H1p; a.H1 = c.H1; a.H1p = h->H1p; a.w2 = h->W[2];
         a.y = bwd ? o.d_label : nullptr; a.B = B; a.nvalid = r.nvalid; a.drop_p = d1;
         a.p = h->P; a.logit = h->Z; a.dZ1 = bwd ? h->dZ1 : nullptr; a.lddz = h->H1p; a.dW2 = h->G[2]; a.cost_sum = h->d_cost;
-        RET(launch(h, bwd ? "head_fwd_bwd" : "head_fwd", [&] { k_head<<<grid_for_warps(h, B), 256, 0, h->stream>>>(a); }));
+        // few, long-lived blocks: every block ends with H1 same-address atomics (dW2) and one on the cost — with one block per
+        // 64 rows those serialised in L2 (~27 cycles each per address) and cost more than the 50 MB the kernel streams
+        static const int hb = getenv("CTR_HEAD_BLOCKS") ? atoi(getenv("CTR_HEAD_BLOCKS")) : 2;
+        const int hgrid = std::max(1, std::min((B + 63) / 64, h->num_sms * std::max(1, hb)));
+        RET(launch(h, bwd ? "head_fwd_bwd" : "head_fwd", [&] { k_head<<<hgrid, 256, 0, h->stream>>>(a); }));
     }
     if (!bwd) return CTR_OK;
 
@@ -1056,6 +1084,8 @@ void ctr_destroy(ctr_handle* h) {
     for (void* p : {(void*)h->feed_dev[0], (void*)h->feed_dev[1], (void*)h->d_costs, (void*)h->kt_user, (void*)h->kt_item, (void*)h->kt_ts, (void*)h->kt_label,
                     (void*)h->kt_flag, (void*)h->kt_pos, h->kt_scan_tmp, (void*)h->kt_count}) if (p) cudaFree(p);
     for (int i = 0; i < ctr_handle::kPin; i++) { if (h->feed_pin[i]) cudaFreeHost(h->feed_pin[i]); if (h->pin_free[i]) cudaEventDestroy(h->pin_free[i]); }
+    if (h->kt_count_host) cudaFreeHost(h->kt_count_host);
+    for (int i = 0; i < ctr_handle::kCnt; i++) if (h->kt_counted[i]) cudaEventDestroy(h->kt_counted[i]);
     delete h->pool; h->pool = nullptr;
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -1378,7 +1408,11 @@ int ctr_train_keys(ctr_handle* h, const int64_t* user_ids, const int64_t* item_i
         RET(dalloc(h, &h->kt_user, cap)); RET(dalloc(h, &h->kt_item, cap)); RET(dalloc(h, &h->kt_ts, cap)); RET(dalloc(h, &h->kt_label, cap));
         h->kt_cap = cap;
     }
-    const size_t chunk = std::min<size_t>((size_t)n, h->feed_bytes / 28);       // keys per staging slot
+    // One GPU: the first epoch STREAMS — small chunks, and the steps over the samples already resident are queued while
+    // the host stages the next chunk (the survivor count of chunk c-1 comes back through a pinned ring).  Several ranks:
+    // every step is collective, so the ranks first agree on the batch count (resolve everything, then train).
+    const bool streaming = epochs > 0 && h->comm.world == 1;
+    const size_t chunk = std::min<size_t>((size_t)n, streaming ? std::min<size_t>(h->feed_bytes / 28, (size_t)2 * B) : h->feed_bytes / 28);   // keys per staging slot
     if (h->kt_chunk < chunk) {
         for (void* p : {(void*)h->kt_flag, (void*)h->kt_pos, h->kt_scan_tmp}) if (p) cudaFree(p);
         h->kt_flag = h->kt_pos = nullptr; h->kt_scan_tmp = nullptr;
@@ -1388,10 +1422,26 @@ int ctr_train_keys(ctr_handle* h, const int64_t* user_ids, const int64_t* item_i
         h->kt_chunk = chunk;
     }
     if (!h->kt_count) RET(dalloc(h, &h->kt_count, 1));
+    if (!h->kt_count_host) {
+        CU(h, cudaHostAlloc(&h->kt_count_host, sizeof(unsigned long long) * ctr_handle::kCnt, cudaHostAllocDefault));
+        for (int i = 0; i < ctr_handle::kCnt; i++) CU(h, cudaEventCreateWithFlags(&h->kt_counted[i], cudaEventDisableTiming));
+    }
     CU(h, cudaMemsetAsync(h->kt_count, 0, sizeof(unsigned long long), h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    // ---- keys → (user row, item row, ts, label), unresolvable samples dropped, order kept
+    // one step of model.Train's loop over the resident samples [b*B, b*B + B) of which `have` exist so far
+    auto run_batch = [&](int64_t b, int64_t have) -> int {
+        const int64_t start = std::min<int64_t>(b * B, have);
+        const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(B, have - start));
+        if (h->ub_off && nv > 0) RET(ctr_ubcache_window_dev(h, h->kt_user + start, (const int64_t*)(h->kt_ts + start), nv, h->s_hist));
+        else if (nv > 0) CU(h, cudaMemsetAsync(h->s_hist, 0xff, sizeof(int) * (size_t)nv * S, h->stream));   // no UserBehavior provider → empty history (rcmd.go:498,509)
+        return train_step_dev(h, h->kt_user + start, h->kt_item + start, h->s_hist, h->kt_label + start, B, nv);
+    };
+    // ---- keys → (user row, item row, ts, label), unresolvable samples dropped, order kept.  The resolve kernels of a
+    // chunk follow its H2D on the COPY stream, so they (and the staging of the next chunk) overlap the train steps
+    // running on the engine stream; the engine stream waits for a chunk's event before it reads that chunk's samples.
+    cudaStream_t rs = h->copy_stream;
     int64_t nchunks = ((int64_t)n + (int64_t)chunk - 1) / (int64_t)chunk;
+    int64_t queued = 0;                                       // first-epoch batches already on the engine stream (streaming)
     for (int64_t c = 0; c < nchunks; c++) {
         const int slot = (int)(c & 1), ps = (int)(c % ctr_handle::kPin);
         const int64_t start = c * (int64_t)chunk; const size_t m = (size_t)std::min<int64_t>((int64_t)chunk, n - start);
@@ -1399,29 +1449,38 @@ int ctr_train_keys(ctr_handle* h, const int64_t* user_ids, const int64_t* item_i
         unsigned char* pin = h->feed_pin[ps];
         h->pool->copy(pin, user_ids + start, m * 8); h->pool->copy(pin + m * 8, item_ids + start, m * 8);
         h->pool->copy(pin + m * 16, ts + start, m * 8); h->pool->copy(pin + m * 24, label + start, m * 4);
-        if (c >= 2) CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
-        CU(h, cudaMemcpyAsync(h->feed_dev[slot], pin, m * 28, cudaMemcpyHostToDevice, h->copy_stream));
-        CU(h, cudaEventRecord(h->pin_free[ps], h->copy_stream));
-        CU(h, cudaEventRecord(h->ev_copied[slot], h->copy_stream));
-        CU(h, cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
+        CU(h, cudaMemcpyAsync(h->feed_dev[slot], pin, m * 28, cudaMemcpyHostToDevice, rs));     // after resolve(c-2), which read this slot (stream order)
+        CU(h, cudaEventRecord(h->pin_free[ps], rs));
         const long long* dk = (const long long*)h->feed_dev[slot];
         const int grid = (int)std::max<size_t>(1, std::min<size_t>((m + 255) / 256, (size_t)h->num_sms * 8));
         RET(launch(h, "keys_rows", [&] {
-            k_keys_rows<<<grid, 256, 0, h->stream>>>(h->idm_keys[0], h->idm_vals[0], h->idm_cap[0] - 1, h->idm_keys[1], h->idm_vals[1], h->idm_cap[1] - 1,
-                                                    dk, dk + m, (long)m, h->kt_flag);
+            k_keys_rows<<<grid, 256, 0, rs>>>(h->idm_keys[0], h->idm_vals[0], h->idm_cap[0] - 1, h->idm_keys[1], h->idm_vals[1], h->idm_cap[1] - 1,
+                                             dk, dk + m, (long)m, h->kt_flag);
         }));
-        RET(launch(h, "cub_exclusive_scan", [&] { cub::DeviceScan::ExclusiveSum(h->kt_scan_tmp, h->kt_scan_bytes, h->kt_flag, h->kt_pos, (int)(m + 1), h->stream); }));
+        RET(launch(h, "cub_exclusive_scan", [&] { cub::DeviceScan::ExclusiveSum(h->kt_scan_tmp, h->kt_scan_bytes, h->kt_flag, h->kt_pos, (int)(m + 1), rs); }));
         RET(launch(h, "keys_compact", [&] {
-            k_keys_compact<<<grid, 256, 0, h->stream>>>(h->idm_keys[0], h->idm_vals[0], h->idm_cap[0] - 1, h->idm_keys[1], h->idm_vals[1], h->idm_cap[1] - 1,
-                                                       dk, dk + m, dk + 2 * m, (const float*)(dk + 3 * m), (long)m, h->kt_flag, h->kt_pos, h->kt_count,
-                                                       h->kt_user, h->kt_item, h->kt_ts, h->kt_label);
+            k_keys_compact<<<grid, 256, 0, rs>>>(h->idm_keys[0], h->idm_vals[0], h->idm_cap[0] - 1, h->idm_keys[1], h->idm_vals[1], h->idm_cap[1] - 1,
+                                                dk, dk + m, dk + 2 * m, (const float*)(dk + 3 * m), (long)m, h->kt_flag, h->kt_pos, h->kt_count,
+                                                h->kt_user, h->kt_item, h->kt_ts, h->kt_label);
         }));
-        RET(launch(h, "keys_advance", [&] { k_keys_advance<<<1, 1, 0, h->stream>>>(h->kt_pos + m, h->kt_count); }));
-        CU(h, cudaEventRecord(h->ev_consumed[slot], h->stream));
+        RET(launch(h, "keys_advance", [&] { k_keys_advance<<<1, 1, 0, rs>>>(h->kt_pos + m, h->kt_count); }));
+        if (streaming) {
+            const int cs = (int)(c % ctr_handle::kCnt);
+            CU(h, cudaMemcpyAsync(h->kt_count_host + cs, h->kt_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, rs));
+            CU(h, cudaEventRecord(h->kt_counted[cs], rs));
+            if (c >= 1) {       // survivors up to chunk c-1: queue their full batches while chunk c resolves
+                const int pc = (int)((c - 1) % ctr_handle::kCnt);
+                CU(h, cudaEventSynchronize(h->kt_counted[pc]));
+                const int64_t have = (int64_t)h->kt_count_host[pc];
+                if ((queued + 1) * (int64_t)B <= have) CU(h, cudaStreamWaitEvent(h->stream, h->kt_counted[pc], 0));
+                while ((queued + 1) * (int64_t)B <= have) { RET(run_batch(queued, have)); queued++; }
+            }
+        }
     }
+    CU(h, cudaStreamSynchronize(rs));                          // every sample resolved; the engine stream may still be training
     unsigned long long used = 0;
-    CU(h, cudaMemcpyAsync(&used, h->kt_count, sizeof used, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemcpyAsync(&used, h->kt_count, sizeof used, cudaMemcpyDeviceToHost, rs));
+    CU(h, cudaStreamSynchronize(rs));
     if (rows_used) *rows_used = (int64_t)used;
     // ---- model.Train's loop over the resident samples.  world > 1: every step is collective, so all ranks run the
     // batch count of the rank with the most samples (ranks that ran out train on all-padding batches)
@@ -1431,13 +1490,7 @@ int ctr_train_keys(ctr_handle* h, const int64_t* user_ids, const int64_t* item_i
     const int64_t batches = nmax / B + (nmax % B != 0);     // model.go:96-99
     float best = INFINITY, cost = 0.0f; int no_improve = 0, ep = 0;
     for (ep = 0; ep < epochs; ep++) {
-        for (int64_t b = 0; b < batches; b++) {
-            const int64_t start = std::min<int64_t>(b * B, (int64_t)used);
-            const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(B, (int64_t)used - start));
-            if (h->ub_off && nv > 0) RET(ctr_ubcache_window_dev(h, h->kt_user + start, (const int64_t*)(h->kt_ts + start), nv, h->s_hist));
-            else if (nv > 0) CU(h, cudaMemsetAsync(h->s_hist, 0xff, sizeof(int) * (size_t)nv * S, h->stream));   // no UserBehavior provider → empty history (rcmd.go:498,509)
-            RET(train_step_dev(h, h->kt_user + start, h->kt_item + start, h->s_hist, h->kt_label + start, B, nv));
-        }
+        for (int64_t b = (ep == 0 ? queued : 0); b < batches; b++) RET(run_batch(b, (int64_t)used));
         RET(read_cost(h, B * h->comm.world, &cost));       // cost of the epoch's last batch, model.go:198
         if (cost < best) { best = cost; no_improve = 0; } else no_improve++;
         if (early_stop != 0 && no_improve >= early_stop) { ep++; break; }   // model.go:206-209

@@ -167,62 +167,86 @@ struct HeadArgs {
 };
 
 __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
-    __shared__ float s_dw2[8][128];     // per-warp partials, H1 <= 128
+    __shared__ float s_dw2[8][128];     // per-warp partials, H1p <= 128
     __shared__ double s_cost[8];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     const bool train = a.dZ1 != nullptr;
-    float w2r[4], dw2r[4];
+    // 8 lanes per row (float4 columns l8, l8+8, l8+16, l8+24), 4 rows per warp instruction, R such groups in flight:
+    // every load / store instruction moves full 128-byte segments of 4 rows and a row sum needs 3 shuffles, not 5
+    const int l8 = lane & 7, sub = lane >> 3;
+    float4 w2v[4], dw2v[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) { int k = lane + 32 * j; w2r[j] = k < a.H1 ? __ldg(a.w2 + k) : 0.0f; dw2r[j] = 0.0f; }
+    for (int j = 0; j < 4; j++) {
+        const int c = (l8 + 8 * j) * 4;
+        w2v[j].x = c + 0 < a.H1 ? __ldg(a.w2 + c + 0) : 0.0f; w2v[j].y = c + 1 < a.H1 ? __ldg(a.w2 + c + 1) : 0.0f;
+        w2v[j].z = c + 2 < a.H1 ? __ldg(a.w2 + c + 2) : 0.0f; w2v[j].w = c + 3 < a.H1 ? __ldg(a.w2 + c + 3) : 0.0f;
+        dw2v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     double cost = 0.0;
     const float invB = 1.0f / (float)a.B;
-    // R consecutive rows per warp and step: their loads are issued together and the R reductions interleave
-    // (one row at a time left a single 384-byte request in flight per warp: latency-bound at ~30 us)
-    constexpr int R = 4;
-    for (int b0 = (blockIdx.x * (blockDim.x >> 5) + wib) * R; b0 < a.B; b0 += nwarps * R) {
-        float h[R][4], z[R];
+    constexpr int R = 2;
+    for (long b0 = (long)(blockIdx.x * (blockDim.x >> 5) + wib) * (4 * R); b0 < a.B; b0 += (long)nwarps * (4 * R)) {
+        float4 h[R][4]; float z[R];
 #pragma unroll
         for (int i = 0; i < R; i++) {
-            z[i] = 0.0f;
+            const long b = b0 + 4 * i + sub;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int k = lane + 32 * j;
-                h[i][j] = (k < a.H1 && b0 + i < a.B) ? __ldg(a.H1d + (long)(b0 + i) * a.ldh + k) : 0.0f;
+                const int c = (l8 + 8 * j) * 4;
+                h[i][j] = (c < a.H1p && b < a.B) ? ldg4(a.H1d + b * a.ldh + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
         for (int i = 0; i < R; i++) {
+            float t = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 4; j++) z[i] = fmaf(h[i][j], w2r[j], z[i]);
+            for (int j = 0; j < 4; j++) {
+                t = fmaf(h[i][j].x, w2v[j].x, t); t = fmaf(h[i][j].y, w2v[j].y, t);
+                t = fmaf(h[i][j].z, w2v[j].z, t); t = fmaf(h[i][j].w, w2v[j].w, t);
+            }
+            z[i] = t;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 4; o > 0; o >>= 1) {
 #pragma unroll
             for (int i = 0; i < R; i++) z[i] += __shfl_xor_sync(0xffffffffu, z[i], o);
         }
 #pragma unroll
         for (int i = 0; i < R; i++) {
-            const int b = b0 + i;
-            if (b >= a.B) break;
+            const long b = b0 + 4 * i + sub;
+            if (b >= a.B) continue;
             const float p = sigmoid32(z[i]);
-            if (lane == 0) { a.p[b] = p; if (a.logit) a.logit[b] = z[i]; }
+            if (l8 == 0) { a.p[b] = p; if (a.logit) a.logit[b] = z[i]; }
             if (!train) continue;
             const float y = (b < a.nvalid) ? __ldg(a.y + b) : 0.0f;
-            if (lane == 0) cost += (double)(logf(p) * y + logf(1.0f - p) * (1.0f - y));
+            if (l8 == 0) cost += (double)(logf(p) * y + logf(1.0f - p) * (1.0f - y));
             const float dz2 = (p - y) * invB;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int k = lane + 32 * j;
-                if (k < a.H1) a.dZ1[(long)b * a.lddz + k] = dz2 * w2r[j] * dsigmoid_drop(h[i][j], a.drop_p);
-                else if (k < a.H1p) a.dZ1[(long)b * a.lddz + k] = 0.0f;
-                dw2r[j] = fmaf(h[i][j], dz2, dw2r[j]);
+                const int c = (l8 + 8 * j) * 4;
+                if (c < a.H1p) {
+                    float4 d;       // columns >= H1 have w2 = 0: the padding of dZ1 stays zero
+                    d.x = dz2 * w2v[j].x * dsigmoid_drop(h[i][j].x, a.drop_p); d.y = dz2 * w2v[j].y * dsigmoid_drop(h[i][j].y, a.drop_p);
+                    d.z = dz2 * w2v[j].z * dsigmoid_drop(h[i][j].z, a.drop_p); d.w = dz2 * w2v[j].w * dsigmoid_drop(h[i][j].w, a.drop_p);
+                    *reinterpret_cast<float4*>(a.dZ1 + b * a.lddz + c) = d;
+                }
+                dw2v[j].x = fmaf(h[i][j].x, dz2, dw2v[j].x); dw2v[j].y = fmaf(h[i][j].y, dz2, dw2v[j].y);
+                dw2v[j].z = fmaf(h[i][j].z, dz2, dw2v[j].z); dw2v[j].w = fmaf(h[i][j].w, dz2, dw2v[j].w);
             }
         }
     }
     if (!train) return;
 #pragma unroll
-    for (int j = 0; j < 4; j++) s_dw2[wib][lane + 32 * j] = dw2r[j];
+    for (int j = 0; j < 4; j++) {       // the warp's four row groups → one partial per column
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            dw2v[j].x += __shfl_xor_sync(0xffffffffu, dw2v[j].x, o); dw2v[j].y += __shfl_xor_sync(0xffffffffu, dw2v[j].y, o);
+            dw2v[j].z += __shfl_xor_sync(0xffffffffu, dw2v[j].z, o); dw2v[j].w += __shfl_xor_sync(0xffffffffu, dw2v[j].w, o);
+        }
+        if (sub == 0) *reinterpret_cast<float4*>(&s_dw2[wib][(l8 + 8 * j) * 4]) = dw2v[j];
+    }
+    cost += __shfl_xor_sync(0xffffffffu, cost, 8); cost += __shfl_xor_sync(0xffffffffu, cost, 16);     // the l8 == 0 lanes of the four groups
     if (lane == 0) s_cost[wib] = cost;
     __syncthreads();
     const int nw = blockDim.x >> 5;

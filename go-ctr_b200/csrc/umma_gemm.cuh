@@ -43,6 +43,7 @@ struct Args {
     float drop_p; uint32_t seed, stream;
     int stages;
     int staged_epi;             // 1: the epilogue goes through per-warp shared-memory staging (coalesced 128-byte row segments)
+    int pf;                     // activation k-blocks requested into L2 ahead of the shared-memory ring (0 = off)
     unsigned long long* dbg;    // optional timeline of CTA 0 (globaltimer ns): [it*8 + event], tiles at [4096 + t*4 + e]
 };
 
@@ -80,6 +81,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// L2 prefetch of a box (no shared-memory destination, no barrier): the later tma_load_2d of the same box is an L2 hit
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
@@ -175,10 +180,19 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     if (warp == 0) {
         if (lane == 0) {                                            // ---------------- TMA producer
+            // The ring holds only `stages` (2-3) 16 KB activation boxes per SM — far too few bytes in flight to cover the
+            // loaded HBM latency.  The boxes of the next a.pf k-blocks are therefore requested into L2 ahead of the ring.
+            const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            const uint32_t total = (uint32_t)my_tiles * (uint32_t)num_k;
+            auto prefetch_a = [&](uint32_t j) {
+                if (j < total) tma_prefetch_2d(&tmA, (int)(j % num_k) * kBlockK, ((int)blockIdx.x + (int)(j / num_k) * (int)gridDim.x) * kBlockM);
+            };
+            for (uint32_t j = stages; j < (uint32_t)(stages + a.pf); j++) prefetch_a(j);
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < num_k; kb++, it++) {
                     const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
+                    if (a.pf) prefetch_a(it + stages + a.pf);
                     mbar_wait(empty(s), ph ^ 1u);
                     mbar_expect_tx(full(s), (uint32_t)kABytes + bBytes * (SPLIT3 ? 2u : 1u));
                     UDBG(it * 8 + 0);
@@ -458,6 +472,9 @@ struct DwArgs {
     int M, N;                   // valid rows / cols of C
     float* C; long ldc;
     int stages;
+    int pf;                     // k-blocks requested into L2 ahead of the ring (0 = off)
+    int rotate;                 // epilogue: CTA-dependent starting chunk (spreads the same-address red traffic)
+    unsigned long long* tl;     // optional timeline of CTA 0 (globaltimer ns): start, first box landed, every 4th MMA batch, accumulators done, epilogue done
     int dbg;                    // probe only: 1 = epilogue adds 1.0, 2 = K-major descriptors, 3 = swap LBO/SBO, 4 = no swizzle-atom K offset
 };
 
@@ -510,6 +527,8 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+#define DWDBG(idx) do { if (a.tl && blockIdx.x == 0 && (idx) < 64) a.tl[(idx)] = gtimer(); } while (0)
+    if (threadIdx.x == 0) DWDBG(0);
     // this CTA's slice of the batch, in 32-sample k-blocks
     const int total_kb = (a.K + 31) / 32;
     const int per = (total_kb + gridDim.x - 1) / gridDim.x;
@@ -519,8 +538,16 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     if (warp == 0) {
         if (lane == 0) {
+            auto prefetch_ab = [&](int j) {
+                if (j >= nkb) return;
+                const int prow = (kb0 + j) * 32;
+                for (int q = 0; q < a.na; q++) tma_prefetch_2d(&tmA, 32 * q, prow);
+                for (int q = 0; q < a.nb; q++) tma_prefetch_2d(&tmB, 32 * q, prow);
+            };
+            for (int j = stages; j < stages + a.pf; j++) prefetch_ab(j);
             for (int it = 0; it < nkb; it++) {
                 const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
+                if (a.pf) prefetch_ab(it + stages + a.pf);
                 mbar_wait(empty(s), ph ^ 1u);
                 mbar_expect_tx(full(s), aBytes + bBytes);
                 const int row = (kb0 + it) * 32;
@@ -548,6 +575,7 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (two_halves) umma_tf32(tmem_base + 256u, dA1 + ko, dB + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(empty(s));
+                DWDBG(8 + it);
             }
             umma_commit(tdone);
         }
@@ -559,6 +587,7 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int it = 0; it < nkb; it++) {
             const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
             mbar_wait(full(s), ph);
+            if (c == 0 && it == 0) DWDBG(1);
             const uint32_t pa = sA(s), pb = sB(s);
             const int na16 = (int)(aBytes / 16u);
             for (int i0 = c; i0 < n16; i0 += 384 * 4) {
@@ -582,12 +611,20 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (warp >= 6 && nkb > 0) {                                 // epilogue warps 6..13: C += accumulators
             const int q = warp & 3, half = (warp - 6) >> 2;
             mbar_wait(tdone, 0);
+            if (threadIdx.x == 192) DWDBG(2);
             tc_fence_after();
             const int nchunks = bn / 16;
-            for (int h = 0; h < (two_halves ? 2 : 1); h++) {
+            // every CTA adds the same [M, N] block: walking it in the same order would put all 148 CTAs on the same
+            // addresses at the same moment (same-address red ops serialise in L2), so each CTA starts at its own chunk
+            const int nh = two_halves ? 2 : 1;
+            const int per_half = (nchunks - half + 1) / 2;                   // chunks half, half + 2, ... of this warp
+            const int rot = a.rotate ? (int)blockIdx.x : 0;
+            for (int hh = 0; hh < nh; hh++) {
+                const int h = (hh + rot) % nh;
                 const int m = h * 128 + q * 32 + lane;
                 const uint32_t trow = tmem_base + (uint32_t)(h * 256) + ((uint32_t)(q * 32) << 16);
-                for (int ci = half; ci < nchunks; ci += 2) {
+                for (int kk = 0; kk < per_half; kk++) {
+                    const int ci = half + 2 * ((kk + rot / nh) % per_half);
                     uint32_t r[16];
                     tmem_ld16_async(trow + (uint32_t)(ci * 16), r);
                     tmem_ld_wait();
@@ -604,6 +641,7 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) DWDBG(3);
     if (warp == 2) tmem_dealloc(tmem_base, ncols);
 }
 

@@ -20,6 +20,16 @@
 #include <omp.h>
 #endif
 
+/* Scratch that lives across steps: a step of 65 536 samples uses ~350 MB of activations; fresh mmap'd pages every step
+ * would make 128 threads queue on page faults.  Test infrastructure: one caller at a time. */
+#define NSCRATCH 16
+static struct { void* p; size_t cap; } g_scr[NSCRATCH];
+static void* scratch(int slot, size_t bytes, int zero) {
+    if (g_scr[slot].cap < bytes) { free(g_scr[slot].p); g_scr[slot].p = malloc(bytes); g_scr[slot].cap = g_scr[slot].p ? bytes : 0; }
+    if (zero && g_scr[slot].p) memset(g_scr[slot].p, 0, bytes);
+    return g_scr[slot].p;
+}
+
 static inline float sig32(float x) { return x < -88.0f ? 0.0f : x > 15.0f ? 1.0f : 1.0f / (1.0f + expf(-x)); }
 
 /* C[M,N] = A[M,K] · B[K,N] (all row-major).  Row blocks of 4 x column panels of 32: the 4x32 accumulator tile
@@ -68,7 +78,7 @@ static void sgemm_tn(int M, int N, int K, const float* A, long lda, const float*
     T = omp_get_max_threads();
 #endif
     if (T > 64) T = 64;
-    float* part = (float*)calloc((size_t)T * M * N, sizeof(float));
+    float* part = (float*)scratch(0, sizeof(float) * (size_t)T * M * N, 0);
 #pragma omp parallel num_threads(T)
     {
         int tid = 0;
@@ -76,6 +86,7 @@ static void sgemm_tn(int M, int N, int K, const float* A, long lda, const float*
         tid = omp_get_thread_num();
 #endif
         float* P = part + (size_t)tid * M * N;
+        memset(P, 0, sizeof(float) * (size_t)M * N);
         const long k0 = (long)K * tid / T, k1 = (long)K * (tid + 1) / T;
         for (long k = k0; k < k1; k++) {
             const float* a = A + k * lda; const float* b = B + k * ldb;
@@ -95,7 +106,6 @@ static void sgemm_tn(int M, int N, int K, const float* A, long lda, const float*
             for (int t = 0; t < T; t++) s += part[((size_t)t * M + i) * N + j];
             C[(long)i * ldc + j] = s;
         }
-    free(part);
 }
 
 /* One train step (forward, BCE, backward, Adam on the dense weights, Hogwild SGD on the touched rows).
@@ -112,14 +122,14 @@ float orc_fast_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_st
     (void)n_items;
     const int uP = c->uP, S = c->S, D = c->D, cF = c->cF, H0 = c->H0, H1 = c->H1, in = uP + 2 * D + cF;
     const float invS = 1.0f / (float)S;
-    float* X0 = (float*)malloc(sizeof(float) * (size_t)B * in);
-    float* A = (float*)malloc(sizeof(float) * (size_t)B * S);           /* gate values a_s (din.go:273) */
-    float* H0d = (float*)malloc(sizeof(float) * (size_t)B * H0);        /* post-dropout activations */
-    float* H1d = (float*)malloc(sizeof(float) * (size_t)B * H1);
-    float* dZ1 = (float*)malloc(sizeof(float) * (size_t)B * H1);
-    float* dZ0 = (float*)malloc(sizeof(float) * (size_t)B * H0);
-    float* dX = (float*)malloc(sizeof(float) * (size_t)B * 2 * D);
-    float* P = (float*)malloc(sizeof(float) * (size_t)B);
+    float* X0 = (float*)scratch(1, sizeof(float) * (size_t)B * in, 0);
+    float* A = (float*)scratch(2, sizeof(float) * (size_t)B * S, 0);           /* gate values a_s (din.go:273) */
+    float* H0d = (float*)scratch(3, sizeof(float) * (size_t)B * H0, 0);        /* post-dropout activations */
+    float* H1d = (float*)scratch(4, sizeof(float) * (size_t)B * H1, 0);
+    float* dZ1 = (float*)scratch(5, sizeof(float) * (size_t)B * H1, 0);
+    float* dZ0 = (float*)scratch(6, sizeof(float) * (size_t)B * H0, 0);
+    float* dX = (float*)scratch(7, sizeof(float) * (size_t)B * 2 * D, 0);
+    float* P = (float*)scratch(8, sizeof(float) * (size_t)B, 0);
     const uint32_t step = (uint32_t)st->t;
     /* ---- gather + attention forward (rcmd.go:462-536, din.go:224-301 / dnn.go:164-170) */
 #pragma omp parallel for schedule(static)
@@ -260,6 +270,6 @@ float orc_fast_train_step_idx(const orc_cfg* c, const orc_solver* s, orc_adam_st
     orc_adam_step(W1, g1, st->m1, st->v1, (long)H0 * H1, st->t, s->lr, s->l2, (float)B, s->b1, s->b2, s->eps);
     orc_adam_step(W2, g2v, st->m2, st->v2, H1, st->t, s->lr, s->l2, (float)B, s->b1, s->b2, s->eps);
     if (c->model != ORC_YOUTUBE) orc_adam_step(att, ga, st->ma, st->va, S, st->t, s->lr, s->l2, (float)B, s->b1, s->b2, s->eps);
-    free(X0); free(A); free(H0d); free(H1d); free(dZ1); free(dZ0); free(dX); free(P); free(g0); free(g1); free(g2v); free(ga);
+    free(g0); free(g1); free(g2v); free(ga);
     return -(float)(cost / (double)B);
 }
