@@ -1,6 +1,10 @@
-"""Markdown summary of the committed bench lines: python profiles/r02/make_table.py  (reads profiles/r02/bench_n*_final.json)"""
+"""Markdown summary of the committed bench lines (reads profiles/r02/bench_n*_final.json).
+  python profiles/r02/make_table.py           prints the table
+  python profiles/r02/make_table.py --write   also rewrites the block between the `results:begin/end` markers of DESIGN.md and README.md"""
+import io
 import json
 import os
+import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -40,8 +44,22 @@ def main():
     d = load(1)
     if d and "cpu_baseline" in d:
         c = d["cpu_baseline"]
-        print("\nCPU arm (`cpu_fast.c`, %d threads): %.0f samples/s on the same 65 536-sample step; 1 thread: %.0f samples/s." % (c["cores"], c["value"], c.get("one_thread_value", 0)))
+        print("\nCPU arm (`cpu_fast.c`, %d threads — the fastest count on the box's %s usable CPUs): %.0f samples/s on the same 65 536-sample step; 1 thread: %.0f samples/s."
+              % (c["cores"], c.get("usable_threads", "?"), c["value"], c.get("one_thread_value", 0)))
 
 
 if __name__ == "__main__":
-    main()
+    if "--write" in sys.argv:
+        buf = io.StringIO(); old = sys.stdout; sys.stdout = buf
+        main()
+        sys.stdout = old
+        block = "<!-- results:begin (profiles/r02/make_table.py --write) -->\n" + buf.getvalue().strip() + "\n<!-- results:end -->"
+        root = os.path.dirname(os.path.dirname(HERE))
+        for name in ("DESIGN.md", "README.md"):
+            path = os.path.join(root, name)
+            txt = open(path).read()
+            a, b = txt.index("<!-- results:begin"), txt.index("<!-- results:end -->") + len("<!-- results:end -->")
+            open(path, "w").write(txt[:a] + block + txt[b:])
+        print(block)
+    else:
+        main()
