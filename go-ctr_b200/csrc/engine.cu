@@ -151,6 +151,7 @@ struct ctr_handle {
         bool ready = false;
         bool dirty = true;                 // weights changed since the last split
         int stages_fwd0 = 0, stages_fwd1 = 0, stages_dz0 = 0, stages_dx = 0;
+        int kbk_fwd0 = 32, kbk_fwd1 = 32, kbk_dz0 = 32, kbk_dx = 32;       // K elements per shared-memory stage of each GEMM
         int bn_fwd0 = 0, bn_fwd1 = 0, bn_dx = 0;
         float *Wt0[2] = {}, *Wt1[2] = {}, *W1s[2] = {}, *W0s[2] = {};     // [hi, lo]
         CUtensorMap mA_X0, mA_H0d, mA_dZ1, mA_dZ0;
@@ -398,7 +399,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_map(ctr_handle* h, CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, uint32_t box_k = 32) {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         cudaDriverEntryPointQueryResult q;
@@ -409,7 +410,7 @@ int make_map(ctr_handle* h, CUtensorMap* m, const float* base, uint64_t rows, ui
     }
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstr[1] = {ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)umma::kBlockK, box_rows};
+    cuuint32_t box[2] = {box_k, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -418,12 +419,21 @@ int make_map(ctr_handle* h, CUtensorMap* m, const float* base, uint64_t rows, ui
 }
 
 constexpr size_t kUmmaEpiBytes = (size_t)umma::kEpiWarps * umma::kEpiStageBytes + 32;     // staged-epilogue tiles
-int umma_stages(int bn) {
-    size_t st = (size_t)umma::kABytes * 2 + (size_t)bn * 128 * 2;
-    return (int)std::min<size_t>(4, ((size_t)227 * 1024 - 2048 - kUmmaEpiBytes) / st);
+// K elements per shared-memory stage: 32 (128-byte swizzle rows) or 16 (64-byte rows: half-size stages, twice as many).
+// The main loop is bound by the L2→SM traffic of the weight tiles, not by the ring depth, so the choice
+// matters little: measured, 16 wins by ~2 µs per GEMM for tiles >= 128 columns wide and loses 3.7 µs for the 96-wide one.
+// CTR_UMMA_KBK = 16 | 32 forces one value.
+int umma_kbk_for(int bn) {
+    static const int force = getenv("CTR_UMMA_KBK") ? atoi(getenv("CTR_UMMA_KBK")) : 0;
+    if (force == 16 || force == 32) return force;
+    return bn >= 128 ? 16 : 32;
 }
-size_t umma_smem(int bn, int stages) {
-    return (size_t)stages * ((size_t)umma::kABytes * 2 + (size_t)bn * 128 * 2) + 8 * (3 * stages + 4) + 16 + 1024 + kUmmaEpiBytes;
+size_t umma_stage_bytes(int bn, int kbk) { return ((size_t)umma::kBlockM + (size_t)bn) * kbk * 4 * 2; }      // A + A_lo + B_hi + B_lo
+int umma_stages(int bn, int kbk) {
+    return (int)std::min<size_t>(kbk == 16 ? 6 : 4, ((size_t)227 * 1024 - 2048 - kUmmaEpiBytes) / umma_stage_bytes(bn, kbk));
+}
+size_t umma_smem(int bn, int stages, int kbk) {
+    return (size_t)stages * umma_stage_bytes(bn, kbk) + 8 * (3 * stages + 4) + 16 + 1024 + kUmmaEpiBytes;
 }
 
 bool umma_supported(const ctr_handle* h) {
@@ -435,21 +445,23 @@ int umma_init(ctr_handle* h) {
     const ctr_config& c = h->cfg;
     auto& u = h->um;
     u.bn_fwd0 = h->H0p; u.bn_fwd1 = h->H1p; u.bn_dx = round_up(2 * c.D, 16);
-    u.stages_fwd0 = umma_stages(u.bn_fwd0); u.stages_fwd1 = umma_stages(u.bn_fwd1);
-    u.stages_dz0 = umma_stages(u.bn_fwd0); u.stages_dx = umma_stages(u.bn_dx);
+    u.kbk_fwd0 = u.kbk_dz0 = umma_kbk_for(u.bn_fwd0); u.kbk_fwd1 = umma_kbk_for(u.bn_fwd1); u.kbk_dx = umma_kbk_for(u.bn_dx);
+    u.stages_fwd0 = u.stages_dz0 = umma_stages(u.bn_fwd0, u.kbk_fwd0); u.stages_fwd1 = umma_stages(u.bn_fwd1, u.kbk_fwd1);
+    u.stages_dx = umma_stages(u.bn_dx, u.kbk_dx);
     if (u.stages_fwd0 < 2) return set_err(h, CTR_EINVAL, "tcgen05 GEMM: tile does not fit shared memory");
+    auto ksw = [](int kbk) { return kbk == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B; };
     for (int i = 0; i < 2; i++) {
         RET(dalloc(h, &u.Wt0[i], (size_t)h->H0p * h->Kp)); RET(dalloc(h, &u.Wt1[i], (size_t)h->H1p * h->H0p));
         RET(dalloc(h, &u.W1s[i], (size_t)h->H0p * h->H1p)); RET(dalloc(h, &u.W0s[i], (size_t)u.bn_dx * h->H0p));
-        RET(make_map(h, &u.mB_Wt0[i], u.Wt0[i], h->H0p, h->Kp, h->Kp, u.bn_fwd0));
-        RET(make_map(h, &u.mB_Wt1[i], u.Wt1[i], h->H1p, h->H0p, h->H0p, u.bn_fwd1));
-        RET(make_map(h, &u.mB_W1s[i], u.W1s[i], h->H0p, h->H1p, h->H1p, u.bn_fwd0));
-        RET(make_map(h, &u.mB_W0s[i], u.W0s[i], u.bn_dx, h->H0p, h->H0p, u.bn_dx));
+        RET(make_map(h, &u.mB_Wt0[i], u.Wt0[i], h->H0p, h->Kp, h->Kp, u.bn_fwd0, ksw(u.kbk_fwd0), u.kbk_fwd0));
+        RET(make_map(h, &u.mB_Wt1[i], u.Wt1[i], h->H1p, h->H0p, h->H0p, u.bn_fwd1, ksw(u.kbk_fwd1), u.kbk_fwd1));
+        RET(make_map(h, &u.mB_W1s[i], u.W1s[i], h->H0p, h->H1p, h->H1p, u.bn_fwd0, ksw(u.kbk_dz0), u.kbk_dz0));
+        RET(make_map(h, &u.mB_W0s[i], u.W0s[i], u.bn_dx, h->H0p, h->H0p, u.bn_dx, ksw(u.kbk_dx), u.kbk_dx));
     }
-    RET(make_map(h, &u.mA_X0, h->X0, h->Bmax, h->Kp, h->Kp, umma::kBlockM));
-    RET(make_map(h, &u.mA_H0d, h->H0d, h->Bmax, h->H0p, h->H0p, umma::kBlockM));
-    RET(make_map(h, &u.mA_dZ1, h->dZ1, h->Bmax, h->H1p, h->H1p, umma::kBlockM));
-    RET(make_map(h, &u.mA_dZ0, h->dZ0, h->Bmax, h->H0p, h->H0p, umma::kBlockM));
+    RET(make_map(h, &u.mA_X0, h->X0, h->Bmax, h->Kp, h->Kp, umma::kBlockM, ksw(u.kbk_fwd0), u.kbk_fwd0));
+    RET(make_map(h, &u.mA_H0d, h->H0d, h->Bmax, h->H0p, h->H0p, umma::kBlockM, ksw(u.kbk_fwd1), u.kbk_fwd1));
+    RET(make_map(h, &u.mA_dZ1, h->dZ1, h->Bmax, h->H1p, h->H1p, umma::kBlockM, ksw(u.kbk_dz0), u.kbk_dz0));
+    RET(make_map(h, &u.mA_dZ0, h->dZ0, h->Bmax, h->H0p, h->H0p, umma::kBlockM, ksw(u.kbk_dx), u.kbk_dx));
     // weight-gradient operands: rows limited to the training batch so that TMA zero-fills the K tail
     RET(make_map(h, &u.mK_X0, h->X0, c.batch, h->Kp, h->Kp, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     RET(make_map(h, &u.mK_H0d, h->H0d, c.batch, h->H0p, h->H0p, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
@@ -459,9 +471,12 @@ int umma_init(ctr_handle* h) {
     u.dw_stages1 = (int)std::min<size_t>(4, ((size_t)227 * 1024 - 2048) / ((size_t)8 * 4096 + (size_t)(h->H1p / 32) * 4096));
     CU(h, cudaFuncSetAttribute(umma::k_umma_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const size_t smax = (size_t)227 * 1024;
-    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
-    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
-    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
     if (getenv("CTR_UMMA_TIMELINE")) RET(dalloc(h, &h->umma_dbg, 8192));
     u.ready = true; u.dirty = true;
     return CTR_OK;
@@ -485,13 +500,16 @@ template <int EPI>
 int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtensorMap* mB, umma::Args a) {
     const int tiles = (a.M + umma::kBlockM - 1) / umma::kBlockM;
     const int grid = std::min(tiles, h->num_sms);
-    const size_t smem = umma_smem(a.bn, a.stages);
+    const size_t smem = umma_smem(a.bn, a.stages, a.kbk);
     a.dbg = h->umma_dbg;
     static const int pf = getenv("CTR_UMMA_PF") ? atoi(getenv("CTR_UMMA_PF")) : 0;     // measured: no gain (profiles/r02/EXPERIMENTS.md)
     a.pf = std::max(0, std::min(pf, 64));
     static const bool epi_old = getenv("CTR_UMMA_EPI_OLD") != nullptr;
     a.staged_epi = epi_old ? 0 : 1;
-    int rc = launch(h, name, [&] { umma::k_umma_gemm<EPI, true><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a); });
+    int rc = launch(h, name, [&] {
+        if (a.kbk == 16) umma::k_umma_gemm<EPI, true, 16><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a);
+        else                  umma::k_umma_gemm<EPI, true, 32><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a);
+    });
     if (rc == CTR_OK && h->umma_dbg) {
         std::vector<unsigned long long> t(8192);
         cudaStreamSynchronize(h->stream);
@@ -500,7 +518,7 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
         FILE* f = fopen("gpurun_out/umma_timeline.txt", "a");
         if (f) {
             unsigned long long t0 = t[0];
-            fprintf(f, "# %s M=%d N=%d K=%d bn=%d stages=%d\n", name, a.M, a.N, a.K, a.bn, a.stages);
+            fprintf(f, "# %s M=%d N=%d K=%d bn=%d kbk=%d stages=%d\n", name, a.M, a.N, a.K, a.bn, a.kbk, a.stages);
             for (int it = 0; it < 40 && t[it * 8]; it++)
                 fprintf(f, "it %d tma_issue %llu conv_saw_full %llu conv_done %llu mma_saw %llu mma_issued %llu\n", it, t[it * 8] - t0, t[it * 8 + 1] - t0, t[it * 8 + 2] - t0, t[it * 8 + 3] - t0, t[it * 8 + 4] - t0);
             for (int tc = 0; tc < 5 && t[4096 + tc * 4]; tc++) fprintf(f, "tile %d epi_start %llu epi_done %llu\n", tc, t[4096 + tc * 4] - t0, t[4096 + tc * 4 + 1] - t0);
@@ -650,10 +668,10 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         RET(umma_init(h));
         RET(umma_split_weights(h));
         umma::Args a{}; a.M = B; a.N = c.H0; a.Nz = h->H0p; a.K = h->Kp; a.bn = h->um.bn_fwd0; a.C = h->H0d; a.ldc = h->H0p;
-        a.drop_p = d0; a.seed = c.seed; a.stream = h->step * 4u + 0u; a.stages = h->um.stages_fwd0;
+        a.drop_p = d0; a.seed = c.seed; a.stream = h->step * 4u + 0u; a.stages = h->um.stages_fwd0; a.kbk = h->um.kbk_fwd0;
         RET(umma_gemm<umma::UEPI_SIGMOID_DROP>(h, "umma_fwd0_sigmoid", h->um.mA_X0, h->um.mB_Wt0, a));
         umma::Args b{}; b.M = B; b.N = c.H1; b.Nz = h->H1p; b.K = h->H0p; b.bn = h->um.bn_fwd1; b.C = h->H1d; b.ldc = h->H1p;
-        b.drop_p = d1; b.seed = c.seed; b.stream = h->step * 4u + 1u; b.stages = h->um.stages_fwd1;
+        b.drop_p = d1; b.seed = c.seed; b.stream = h->step * 4u + 1u; b.stages = h->um.stages_fwd1; b.kbk = h->um.kbk_fwd1;
         RET(umma_gemm<umma::UEPI_SIGMOID_DROP>(h, "umma_fwd1_sigmoid", h->um.mA_H0d, h->um.mB_Wt1, b));
     } else {
     {   // h0 = dropout(sigmoid(x·W0))   din.go:307-308
@@ -693,7 +711,7 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
     }
     if (um) {
         umma::Args a{}; a.M = B; a.N = c.H0; a.Nz = h->H0p; a.K = h->H1p; a.bn = h->um.bn_fwd0; a.C = h->dZ0; a.ldc = h->H0p;
-        a.H = h->H0d; a.ldh = h->H0p; a.drop_p = d0; a.stages = h->um.stages_dz0;
+        a.H = h->H0d; a.ldh = h->H0p; a.drop_p = d0; a.stages = h->um.stages_dz0; a.kbk = h->um.kbk_dz0;
         RET(umma_gemm<umma::UEPI_DSIGMOID>(h, "umma_dZ0_dsigmoid", h->um.mA_dZ1, h->um.mB_W1s, a));
     } else {   // dZ0 = (dZ1 · W1ᵀ) ⊙ dsigmoid(h0d)
         GemmArgs g{}; g.A = h->dZ1; g.lda = h->H1p; g.B = h->W[1]; g.ldb = h->H1p; g.C = h->dZ0; g.ldc = h->H0p;
@@ -714,7 +732,7 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
     if (need_attn_bwd) {
         if (um) {
             umma::Args a{}; a.M = B; a.N = 2 * c.D; a.Nz = h->lddx; a.K = h->H0p; a.bn = h->um.bn_dx; a.C = h->dX; a.ldc = h->lddx;
-            a.stages = h->um.stages_dx;
+            a.stages = h->um.stages_dx; a.kbk = h->um.kbk_dx;
             RET(umma_gemm<umma::UEPI_STORE>(h, "umma_dX", h->um.mA_dZ0, h->um.mB_W0s, a));
         } else {   // d concat[:, uP:uP+2D] = dZ0 · W0[uP:uP+2D, :]ᵀ
             GemmArgs g{}; g.A = h->dZ0; g.lda = h->H0p; g.B = h->W[0] + (long)c.uP * h->H0p; g.ldb = h->H0p;

@@ -32,8 +32,7 @@ namespace umma {
 enum { UEPI_STORE = 0, UEPI_SIGMOID_DROP = 1, UEPI_DSIGMOID = 2 };
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 32;                    // fp32 elements = 128 bytes = one swizzle row
-constexpr int kABytes = kBlockM * kBlockK * 4; // 16 KB
+// K per shared-memory stage is a template parameter of k_umma_gemm (KBK = 32 or 16 fp32: one 128- or 64-byte swizzle row)
 
 struct Args {
     int M, N, Nz, K;            // K multiple of 32; columns [N, Nz) of C written as zeros
@@ -43,6 +42,7 @@ struct Args {
     float drop_p; uint32_t seed, stream;
     int stages;
     int staged_epi;             // 1: the epilogue goes through per-warp shared-memory staging (coalesced 128-byte row segments)
+    int kbk;                    // K elements per shared-memory stage (32 or 16): selects the kernel instantiation and the maps' box
     int pf;                     // activation k-blocks requested into L2 ahead of the shared-memory ring (0 = off)
     unsigned long long* dbg;    // optional timeline of CTA 0 (globaltimer ns): [it*8 + event], tiles at [4096 + t*4 + e]
 };
@@ -128,16 +128,26 @@ __device__ __forceinline__ uint64_t desc_k_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// Same for SWIZZLE_64B: rows of 64 bytes (16 fp32 of K), 8-row groups 512 bytes apart; layout type 4.
+__device__ __forceinline__ uint64_t desc_k_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+template <int KBK> __device__ __forceinline__ uint64_t desc_k(uint32_t saddr) { return KBK == 32 ? desc_k_sw128(saddr) : desc_k_sw64(saddr); }
 // instruction descriptor: D=F32, A=B=TF32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ size_t stage_bytes(int bn, bool split3) {
-    return (size_t)kABytes * (split3 ? 2 : 1) + (size_t)bn * 128 * (split3 ? 2 : 1);
-}
 
-template <int EPI, bool SPLIT3>
+// KBK: fp32 elements of K per shared-memory stage — 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B:
+// half-size stages, twice as many of them in the same shared memory)
+template <int EPI, bool SPLIT3, int KBK>
 __global__ void __launch_bounds__(448, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
             const __grid_constant__ CUtensorMap tmBlo, Args a) {
@@ -145,8 +155,9 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int bn = a.bn, stages = a.stages;
-    const uint32_t bBytes = (uint32_t)bn * 128u;
-    const uint32_t stBytes = (uint32_t)kABytes * (SPLIT3 ? 2u : 1u) + bBytes * (SPLIT3 ? 2u : 1u);
+    constexpr uint32_t kABytes = (uint32_t)kBlockM * KBK * 4u;
+    const uint32_t bBytes = (uint32_t)bn * (uint32_t)KBK * 4u;
+    const uint32_t stBytes = kABytes * (SPLIT3 ? 2u : 1u) + bBytes * (SPLIT3 ? 2u : 1u);
     // stage s: [A | (Alo) | Bhi | (Blo)]
     auto sA = [&](int s) { return base + (uint32_t)s * stBytes; };
     auto sAlo = [&](int s) { return sA(s) + kABytes; };
@@ -175,7 +186,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int num_k = a.K / kBlockK;
+    const int num_k = a.K / KBK;
     const int num_tiles = (a.M + kBlockM - 1) / kBlockM;
 
     if (warp == 0) {
@@ -185,7 +196,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
             const uint32_t total = (uint32_t)my_tiles * (uint32_t)num_k;
             auto prefetch_a = [&](uint32_t j) {
-                if (j < total) tma_prefetch_2d(&tmA, (int)(j % num_k) * kBlockK, ((int)blockIdx.x + (int)(j / num_k) * (int)gridDim.x) * kBlockM);
+                if (j < total) tma_prefetch_2d(&tmA, (int)(j % num_k) * KBK, ((int)blockIdx.x + (int)(j / num_k) * (int)gridDim.x) * kBlockM);
             };
             for (uint32_t j = stages; j < (uint32_t)(stages + a.pf); j++) prefetch_a(j);
             uint32_t it = 0;
@@ -194,11 +205,11 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
                     if (a.pf) prefetch_a(it + stages + a.pf);
                     mbar_wait(empty(s), ph ^ 1u);
-                    mbar_expect_tx(full(s), (uint32_t)kABytes + bBytes * (SPLIT3 ? 2u : 1u));
+                    mbar_expect_tx(full(s), kABytes + bBytes * (SPLIT3 ? 2u : 1u));
                     UDBG(it * 8 + 0);
-                    tma_load_2d(sA(s), &tmA, full(s), kb * kBlockK, tile * kBlockM);
-                    tma_load_2d(sBhi(s), &tmBhi, full(s), kb * kBlockK, 0);
-                    if (SPLIT3) tma_load_2d(sBlo(s), &tmBlo, full(s), kb * kBlockK, 0);
+                    tma_load_2d(sA(s), &tmA, full(s), kb * KBK, tile * kBlockM);
+                    tma_load_2d(sBhi(s), &tmBhi, full(s), kb * KBK, 0);
+                    if (SPLIT3) tma_load_2d(sBlo(s), &tmBlo, full(s), kb * KBK, 0);
                 }
             }
         }
@@ -216,10 +227,10 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(SPLIT3 ? conv(s) : full(s), ph);
                     UDBG(it * 8 + 3);
                     tc_fence_after();
-                    const uint64_t dAhi = desc_k_sw128(sA(s)), dBhi = desc_k_sw128(sBhi(s));
-                    const uint64_t dAlo = SPLIT3 ? desc_k_sw128(sAlo(s)) : 0, dBlo = SPLIT3 ? desc_k_sw128(sBlo(s)) : 0;
+                    const uint64_t dAhi = desc_k<KBK>(sA(s)), dBhi = desc_k<KBK>(sBhi(s));
+                    const uint64_t dAlo = SPLIT3 ? desc_k<KBK>(sAlo(s)) : 0, dBlo = SPLIT3 ? desc_k<KBK>(sBlo(s)) : 0;
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 8; k++) {         // UMMA_K = 8 tf32 = 32 bytes = +2 in the address field
+                    for (int k = 0; k < KBK / 8; k++) {         // UMMA_K = 8 tf32 = 32 bytes = +2 in the address field
                         const uint64_t ko = (uint64_t)(k * 2);
                         umma_tf32(d_tmem, dAhi + ko, dBhi + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         if (SPLIT3) {
@@ -243,13 +254,14 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(full(s), ph);
                     if (c == 0) UDBG(it * 8 + 1);
                     const uint32_t pa = sA(s), pl = sAlo(s);
-                    float4 x[8];
+                    constexpr int NV = (int)(kABytes / 16u / 128u);     // float4 per thread: 128 threads x NV x 16 B = the A tile; all loads first
+                    float4 x[NV];
 #pragma unroll
-                    for (int i = 0; i < 8; i++)                     // 8 x 128 threads x 16 B = the 16 KB tile; all loads first
+                    for (int i = 0; i < NV; i++)
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
                                      : "r"(pa + 16u * (c + 128 * i)));
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
+                    for (int i = 0; i < NV; i++) {
                         float4 h, l;
                         h.x = __uint_as_float(__float_as_uint(x[i].x) & 0xFFFFE000u); l.x = x[i].x - h.x;
                         h.y = __uint_as_float(__float_as_uint(x[i].y) & 0xFFFFE000u); l.y = x[i].y - h.y;
