@@ -138,6 +138,8 @@ struct ctr_handle {
     unsigned long long* kt_count = nullptr;
     static constexpr int kCnt = 8;                       // pinned ring of survivor counts read back chunk by chunk
     unsigned long long* kt_count_host = nullptr; cudaEvent_t kt_counted[kCnt] = {};
+    // history windows of batch b+1 are cut on their own stream while batch b trains (two buffers)
+    cudaStream_t win_stream = nullptr; int* kt_hist[2] = {}; cudaEvent_t kt_win[2] = {}, kt_used[2] = {};
     // dense-X residency
     float* dXd = nullptr; float* dYd = nullptr; size_t dXd_cap = 0, dYd_cap = 0;
 
@@ -1103,6 +1105,8 @@ void ctr_destroy(ctr_handle* h) {
                     (void*)h->kt_flag, (void*)h->kt_pos, h->kt_scan_tmp, (void*)h->kt_count}) if (p) cudaFree(p);
     for (int i = 0; i < ctr_handle::kPin; i++) { if (h->feed_pin[i]) cudaFreeHost(h->feed_pin[i]); if (h->pin_free[i]) cudaEventDestroy(h->pin_free[i]); }
     if (h->kt_count_host) cudaFreeHost(h->kt_count_host);
+    for (int i = 0; i < 2; i++) { if (h->kt_hist[i]) cudaFree(h->kt_hist[i]); if (h->kt_win[i]) cudaEventDestroy(h->kt_win[i]); if (h->kt_used[i]) cudaEventDestroy(h->kt_used[i]); }
+    if (h->win_stream) cudaStreamDestroy(h->win_stream);
     for (int i = 0; i < ctr_handle::kCnt; i++) if (h->kt_counted[i]) cudaEventDestroy(h->kt_counted[i]);
     delete h->pool; h->pool = nullptr;
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1446,13 +1450,37 @@ int ctr_train_keys(ctr_handle* h, const int64_t* user_ids, const int64_t* item_i
     }
     CU(h, cudaMemsetAsync(h->kt_count, 0, sizeof(unsigned long long), h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    // one step of model.Train's loop over the resident samples [b*B, b*B + B) of which `have` exist so far
+    if (!h->win_stream) {
+        CU(h, cudaStreamCreateWithFlags(&h->win_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            RET(dalloc(h, &h->kt_hist[i], (size_t)h->Bmax * S, false));
+            CU(h, cudaEventCreateWithFlags(&h->kt_win[i], cudaEventDisableTiming)); CU(h, cudaEventCreateWithFlags(&h->kt_used[i], cudaEventDisableTiming));
+        }
+    }
+    // one step of model.Train's loop over the resident samples [b*B, b*B + B) of which `have` exist so far.  The batch's
+    // history windows (GetUserBehavior at the sample's timestamp) are cut on the window stream into one of two buffers,
+    // so the window kernel of batch b+1 runs under the train step of batch b.
+    int64_t nrun = 0;
     auto run_batch = [&](int64_t b, int64_t have) -> int {
         const int64_t start = std::min<int64_t>(b * B, have);
         const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(B, have - start));
-        if (h->ub_off && nv > 0) RET(ctr_ubcache_window_dev(h, h->kt_user + start, (const int64_t*)(h->kt_ts + start), nv, h->s_hist));
-        else if (nv > 0) CU(h, cudaMemsetAsync(h->s_hist, 0xff, sizeof(int) * (size_t)nv * S, h->stream));   // no UserBehavior provider → empty history (rcmd.go:498,509)
-        return train_step_dev(h, h->kt_user + start, h->kt_item + start, h->s_hist, h->kt_label + start, B, nv);
+        const int k = (int)(nrun & 1);
+        int* hist = h->kt_hist[k];
+        if (nv > 0) {
+            if (nrun >= 2) CU(h, cudaStreamWaitEvent(h->win_stream, h->kt_used[k], 0));         // the step two batches back has read this buffer
+            if (h->ub_off) {
+                RET(launch(h, "ubcache_window", [&] {
+                    k_ub_window<<<grid_for_warps(h, nv), 256, 0, h->win_stream>>>(h->ub_off, h->ub_ts, h->ub_items, h->kt_user + start, h->kt_ts + start, nv, S,
+                                                                                 (long)h->ub_users, hist);
+                }));
+            } else CU(h, cudaMemsetAsync(hist, 0xff, sizeof(int) * (size_t)nv * S, h->win_stream));   // no UserBehavior provider → empty history (rcmd.go:498,509)
+            CU(h, cudaEventRecord(h->kt_win[k], h->win_stream));
+            CU(h, cudaStreamWaitEvent(h->stream, h->kt_win[k], 0));
+        }
+        RET(train_step_dev(h, h->kt_user + start, h->kt_item + start, hist, h->kt_label + start, B, nv));
+        CU(h, cudaEventRecord(h->kt_used[k], h->stream));
+        nrun++;
+        return CTR_OK;
     };
     // ---- keys → (user row, item row, ts, label), unresolvable samples dropped, order kept.  The resolve kernels of a
     // chunk follow its H2D on the COPY stream, so they (and the staging of the next chunk) overlap the train steps
