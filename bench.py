@@ -624,7 +624,7 @@ def main():
                           "1 process per GPU; ITEM_EMB (%.0f MB) replicated, row + dense gradients all-reduced (NCCL)" % (w["I"] * w["D"] * 4 / 1e6)))
     line = {"metric": "ctr_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": leg["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (3xTF32 fwd/dgrad GEMMs, 1xTF32-RN wgrad GEMMs, fp32 everything else)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32 (the six GEMMs as error-compensated 3xTF32 on tcgen05, fp32 everything else)", "data": "synthetic",
             "config": cfg, "engine": engine_cfg, "clocks": leg["clocks"], "gpu_launches": int(leg["launches"]), "last_cost": leg["cost"],
             "wall_s_timed_region": leg["wall"], "roofline": rl, "kernels": kern}
     if nv:

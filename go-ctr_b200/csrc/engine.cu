@@ -160,6 +160,7 @@ struct ctr_handle {
         CUtensorMap mB_Wt0[2], mB_Wt1[2], mB_W1s[2], mB_W0s[2];
         CUtensorMap mK_X0, mK_H0d, mK_dZ0, mK_dZ1;      // {32 x 32} boxes over [batch, width] for the weight-gradient GEMMs
         int dw_stages0 = 0, dw_stages1 = 0;
+        int dw_ks = 16, dw_terms = 3;                   // samples per k-block; products per term (3 = error-compensated, fp32-grade)
     } um;
 
     // device-side ubcache (ubcache.cuh)
@@ -442,6 +443,9 @@ bool umma_supported(const ctr_handle* h) {
     return h->H0p <= 256 && h->H1p <= 256 && round_up(2 * h->cfg.D, 16) <= 256 && h->H0p % 16 == 0 && h->H1p % 16 == 0;
 }
 
+// shared memory of one k-block of the weight-gradient GEMM: 8 A blocks + nb B blocks of (ks samples x 128 bytes), twice with lo copies
+template <class U> size_t dw_stage_bytes(const U& u, int nb) { return (size_t)(8 + nb) * u.dw_ks * 128 * (u.dw_terms == 3 ? 2 : 1); }
+
 int umma_init(ctr_handle* h) {
     if (h->um.ready) return CTR_OK;
     const ctr_config& c = h->cfg;
@@ -465,12 +469,16 @@ int umma_init(ctr_handle* h) {
     RET(make_map(h, &u.mA_dZ1, h->dZ1, h->Bmax, h->H1p, h->H1p, umma::kBlockM, ksw(u.kbk_dz0), u.kbk_dz0));
     RET(make_map(h, &u.mA_dZ0, h->dZ0, h->Bmax, h->H0p, h->H0p, umma::kBlockM, ksw(u.kbk_dx), u.kbk_dx));
     // weight-gradient operands: rows limited to the training batch so that TMA zero-fills the K tail
-    RET(make_map(h, &u.mK_X0, h->X0, c.batch, h->Kp, h->Kp, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    RET(make_map(h, &u.mK_H0d, h->H0d, c.batch, h->H0p, h->H0p, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    RET(make_map(h, &u.mK_dZ0, h->dZ0, c.batch, h->H0p, h->H0p, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    RET(make_map(h, &u.mK_dZ1, h->dZ1, c.batch, h->H1p, h->H1p, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    u.dw_stages0 = (int)std::min<size_t>(4, ((size_t)227 * 1024 - 2048) / ((size_t)8 * 4096 + (size_t)(h->H0p / 32) * 4096));
-    u.dw_stages1 = (int)std::min<size_t>(4, ((size_t)227 * 1024 - 2048) / ((size_t)8 * 4096 + (size_t)(h->H1p / 32) * 4096));
+    // weight gradients: error-compensated 3xTF32 like the other GEMMs (hi/lo copies double a stage, so 16-sample
+    // k-blocks); CTR_DW_1XTF32=1 selects the round-1 arithmetic (one TF32-RN product per term, 32-sample k-blocks)
+    static const bool dw1x = getenv("CTR_DW_1XTF32") != nullptr;
+    u.dw_terms = dw1x ? 1 : 3; u.dw_ks = dw1x ? 32 : 16;
+    RET(make_map(h, &u.mK_X0, h->X0, c.batch, h->Kp, h->Kp, u.dw_ks, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    RET(make_map(h, &u.mK_H0d, h->H0d, c.batch, h->H0p, h->H0p, u.dw_ks, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    RET(make_map(h, &u.mK_dZ0, h->dZ0, c.batch, h->H0p, h->H0p, u.dw_ks, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    RET(make_map(h, &u.mK_dZ1, h->dZ1, c.batch, h->H1p, h->H1p, u.dw_ks, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    u.dw_stages0 = (int)std::min<size_t>(6, ((size_t)227 * 1024 - 2048) / dw_stage_bytes(u, h->H0p / 32));
+    u.dw_stages1 = (int)std::min<size_t>(6, ((size_t)227 * 1024 - 2048) / dw_stage_bytes(u, h->H1p / 32));
     CU(h, cudaFuncSetAttribute(umma::k_umma_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const size_t smax = (size_t)227 * 1024;
     CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
@@ -531,9 +539,10 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
 }
 
 int umma_dw(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtensorMap& mB, umma::DwArgs a) {
-    const int total_kb = (a.K + 31) / 32;
+    a.ks = h->um.dw_ks; a.terms = h->um.dw_terms;
+    const int total_kb = (a.K + a.ks - 1) / a.ks;
     const int grid = std::max(1, std::min(total_kb, h->num_sms));
-    const size_t smem = (size_t)a.stages * ((size_t)8 * 4096 + (size_t)a.nb * 4096) + 8 * (3 * a.stages + 2) + 16 + 1024;
+    const size_t smem = (size_t)a.stages * dw_stage_bytes(h->um, a.nb) + 8 * (3 * a.stages + 2) + 16 + 1024;
     static const int pf = getenv("CTR_UMMA_DW_PF") ? atoi(getenv("CTR_UMMA_DW_PF")) : 0;
     a.pf = std::max(0, std::min(pf, 16));
     static const bool norot = getenv("CTR_DW_NO_ROTATE") != nullptr;
@@ -547,7 +556,7 @@ int umma_dw(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtens
         cudaMemset(h->umma_dbg, 0, 64 * 8);
         FILE* f = fopen("gpurun_out/umma_timeline.txt", "a");
         if (f) {
-            fprintf(f, "# %s K=%d na=%d nb=%d stages=%d pf=%d grid=%d\n", name, a.K, a.na, a.nb, a.stages, a.pf, grid);
+            fprintf(f, "# %s K=%d na=%d nb=%d ks=%d terms=%d stages=%d pf=%d grid=%d\n", name, a.K, a.na, a.nb, a.ks, a.terms, a.stages, a.pf, grid);
             fprintf(f, "first_box_landed %llu accumulators_done %llu kernel_end %llu  mma_batches:", t[1] - t[0], t[2] - t[0], t[3] - t[0]);
             for (int i = 8; i < 64 && t[i]; i++) fprintf(f, " %llu", t[i] - t[0]);
             fprintf(f, "\n");

@@ -484,16 +484,18 @@ struct DwArgs {
     int M, N;                   // valid rows / cols of C
     float* C; long ldc;
     int stages;
+    int ks;                     // samples per k-block / TMA box: 32 or 16
+    int terms;                  // 3 = error-compensated 3xTF32 (hi/lo split of both operands, fp32-grade), 1 = one TF32-RN product per term
     int pf;                     // k-blocks requested into L2 ahead of the ring (0 = off)
     int rotate;                 // epilogue: CTA-dependent starting chunk (spreads the same-address red traffic)
     unsigned long long* tl;     // optional timeline of CTA 0 (globaltimer ns): start, first box landed, every 4th MMA batch, accumulators done, epilogue done
     int dbg;                    // probe only: 1 = epilogue adds 1.0, 2 = K-major descriptors, 3 = swap LBO/SBO, 4 = no swizzle-atom K offset
 };
 
-__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr, uint32_t blk_bytes = 4096u) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)(4096 >> 4) << 16;          // LBO: next column block along M/N
+    d |= (uint64_t)(blk_bytes >> 4) << 16;     // LBO: next 32-wide column block along M/N (4096 for 32-sample boxes, 2048 for 16)
     d |= (uint64_t)(512 >> 4) << 32;           // SBO: next group of 4 samples along K
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)1 << 61;                    // SWIZZLE_128B_BASE32B
@@ -514,10 +516,13 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = a.stages;
-    const uint32_t aBytes = (uint32_t)a.na * 4096u, bBytes = (uint32_t)a.nb * 4096u;
-    const uint32_t stBytes = 8u * 4096u + bBytes;                    // A always reserves 8 blocks (two M halves)
+    const uint32_t blk = (uint32_t)a.ks * 128u;                      // one 32-column block of a k-block: ks samples x 128 bytes
+    const uint32_t aBytes = (uint32_t)a.na * blk, bBytes = (uint32_t)a.nb * blk;
+    const bool split = a.terms == 3;
+    const uint32_t hiBytes = 8u * blk + bBytes;                      // A always reserves 8 blocks (two M halves)
+    const uint32_t stBytes = hiBytes * (split ? 2u : 1u);            // stage: [A | B] and, for the 3-term product, [A_lo | B_lo] behind it
     auto sA = [&](int s) { return base + (uint32_t)s * stBytes; };
-    auto sB = [&](int s) { return sA(s) + 8u * 4096u; };
+    auto sB = [&](int s) { return sA(s) + 8u * blk; };
     const uint32_t bars = base + (uint32_t)stages * stBytes;
     auto full = [&](int s) { return bars + 8u * s; };
     auto conv = [&](int s) { return bars + 8u * (stages + s); };
@@ -541,8 +546,8 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 #define DWDBG(idx) do { if (a.tl && blockIdx.x == 0 && (idx) < 64) a.tl[(idx)] = gtimer(); } while (0)
     if (threadIdx.x == 0) DWDBG(0);
-    // this CTA's slice of the batch, in 32-sample k-blocks
-    const int total_kb = (a.K + 31) / 32;
+    // this CTA's slice of the batch, in ks-sample k-blocks
+    const int total_kb = (a.K + a.ks - 1) / a.ks;
     const int per = (total_kb + gridDim.x - 1) / gridDim.x;
     const int kb0 = blockIdx.x * per, kb1 = min(total_kb, kb0 + per);
     const int nkb = max(0, kb1 - kb0);
@@ -552,7 +557,7 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) {
             auto prefetch_ab = [&](int j) {
                 if (j >= nkb) return;
-                const int prow = (kb0 + j) * 32;
+                const int prow = (kb0 + j) * a.ks;
                 for (int q = 0; q < a.na; q++) tma_prefetch_2d(&tmA, 32 * q, prow);
                 for (int q = 0; q < a.nb; q++) tma_prefetch_2d(&tmB, 32 * q, prow);
             };
@@ -562,29 +567,41 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (a.pf) prefetch_ab(it + stages + a.pf);
                 mbar_wait(empty(s), ph ^ 1u);
                 mbar_expect_tx(full(s), aBytes + bBytes);
-                const int row = (kb0 + it) * 32;
-                for (int j = 0; j < a.na; j++) tma_load_2d(sA(s) + 4096u * j, &tmA, full(s), 32 * j, row);
-                for (int j = 0; j < a.nb; j++) tma_load_2d(sB(s) + 4096u * j, &tmB, full(s), 32 * j, row);
+                const int row = (kb0 + it) * a.ks;
+                for (int j = 0; j < a.na; j++) tma_load_2d(sA(s) + blk * j, &tmA, full(s), 32 * j, row);
+                for (int j = 0; j < a.nb; j++) tma_load_2d(sB(s) + blk * j, &tmB, full(s), 32 * j, row);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = a.dbg == 2 ? idesc_tf32(kBlockM, bn) : idesc_tf32_mn(kBlockM, bn);
+            const int ksteps = a.ks / 8;
+            const uint64_t lo_off = (uint64_t)(hiBytes >> 4);            // hi → lo copy of the same operand, in descriptor address units
             for (int it = 0; it < nkb; it++) {
                 const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
                 mbar_wait(conv(s), ph);
                 tc_fence_after();
-                uint64_t dA0 = desc_mn_sw128(sA(s)), dA1 = desc_mn_sw128(sA(s) + 4u * 4096u), dB = desc_mn_sw128(sB(s));
+                uint64_t dA0 = desc_mn_sw128(sA(s), blk), dA1 = desc_mn_sw128(sA(s) + 4u * blk, blk), dB = desc_mn_sw128(sB(s), blk);
                 if (a.dbg == 2) { dA0 = desc_k_sw128(sA(s)); dA1 = desc_k_sw128(sA(s) + 4u * 4096u); dB = desc_k_sw128(sB(s)); }
                 if (a.dbg == 3) {   // LBO <-> SBO
                     auto sw = [](uint64_t d) { return (d & ~((uint64_t)0x3FFF << 16) & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(4096 >> 4) << 32); };
                     dA0 = sw(dA0); dA1 = sw(dA1); dB = sw(dB);
                 }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {                       // 8 samples per k-step = +1024 bytes = +64 in the address field
+                for (int k = 0; k < ksteps; k++) {                  // 8 samples per k-step = +1024 bytes = +64 in the address field
                     const uint64_t ko = (uint64_t)(k * 64);
-                    umma_tf32(tmem_base, dA0 + ko, dB + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    if (two_halves) umma_tf32(tmem_base + 256u, dA1 + ko, dB + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+                    umma_tf32(tmem_base, dA0 + ko, dB + ko, idesc, acc);
+                    if (split) {                                    // + A_lo·B_hi + A_hi·B_lo (A_lo·B_lo is below fp32 resolution)
+                        umma_tf32(tmem_base, dA0 + lo_off + ko, dB + ko, idesc, 1u);
+                        umma_tf32(tmem_base, dA0 + ko, dB + lo_off + ko, idesc, 1u);
+                    }
+                    if (two_halves) {
+                        umma_tf32(tmem_base + 256u, dA1 + ko, dB + ko, idesc, acc);
+                        if (split) {
+                            umma_tf32(tmem_base + 256u, dA1 + lo_off + ko, dB + ko, idesc, 1u);
+                            umma_tf32(tmem_base + 256u, dA1 + ko, dB + lo_off + ko, idesc, 1u);
+                        }
+                    }
                 }
                 umma_commit(empty(s));
                 DWDBG(8 + it);
@@ -592,8 +609,9 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             umma_commit(tdone);
         }
     } else {
-        // converters: TF32 round-to-nearest in place.  All twelve remaining warps convert (the eight epilogue warps have
-        // nothing else to do until the accumulators are complete): the rounding pass, not the MMAs, paces the main loop.
+        // converters.  1 term: TF32 round-to-nearest in place (unbiased single product).  3 terms: hi = the 19 bits the
+        // tensor core reads, written in place, lo = x - hi (exact) into the stage's second half.  All twelve remaining warps
+        // convert (the eight epilogue warps have nothing else to do until the accumulators are complete).
         const int c = threadIdx.x - 64;
         const int n16 = (int)((aBytes + bBytes) / 16u);
         for (int it = 0; it < nkb; it++) {
@@ -612,9 +630,19 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (i0 + 384 * u < n16)
+                    if (i0 + 384 * u >= n16) continue;
+                    if (split) {
+                        float4 hv, lv;
+                        hv.x = __uint_as_float(__float_as_uint(x[u].x) & 0xFFFFE000u); lv.x = x[u].x - hv.x;
+                        hv.y = __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u); lv.y = x[u].y - hv.y;
+                        hv.z = __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u); lv.z = x[u].z - hv.z;
+                        hv.w = __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u); lv.w = x[u].w - hv.w;
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ad[u]), "f"(hv.x), "f"(hv.y), "f"(hv.z), "f"(hv.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ad[u] + hiBytes), "f"(lv.x), "f"(lv.y), "f"(lv.z), "f"(lv.w) : "memory");
+                    } else {
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ad[u]), "f"(tf32_rn(x[u].x)), "f"(tf32_rn(x[u].y)),
                                      "f"(tf32_rn(x[u].z)), "f"(tf32_rn(x[u].w)) : "memory");
+                    }
                 }
             }
             fence_proxy_async();

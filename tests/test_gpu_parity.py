@@ -11,10 +11,11 @@ from tests.util import assert_mostly_close, make_batch, make_tables, scaled_init
 pytestmark = pytest.mark.gpu
 
 SCORE_RTOL = 1e-4       # north_star: "within 1e-4 relative on forward scores"
-# weight gradients: the tcgen05 engine reduces over the batch with ONE TF32 product per term, operands
-# rounded to nearest-even (unbiased, 2^-12 relative per term; see umma_gemm.cuh k_umma_dw) — error is
-# bounded relative to the largest gradient entry, not to each entry
-GRAD_ATOL = 1e-4
+# weight gradients: error-compensated 3xTF32 on the tcgen05 engine (umma_gemm.cuh k_umma_dw), fp32 FFMA otherwise — both
+# are float32-grade sums over the batch, compared with the double-accumulating oracle: the absolute part of the bound is
+# relative to the largest gradient entry (cancellation in small entries), not to each entry
+GRAD_RTOL = 2e-4
+GRAD_ATOL = 1e-5
 
 # (uP, S, D, cF): reference movielens dims (rcmd.go:22-24), north-star dims, the reference test's odd
 # dims (model_test.go:24-28, generic kernels), and a >64 history (index-prefetch fallback)
@@ -71,9 +72,10 @@ def test_gradients(model, shape):
     orc.forward(o0, W, X, orc.make_ranges(ocfg.uP, ocfg.S, ocfg.D, ocfg.cF), ws=ws)
     ref = orc.backward(o0, W, ws, y)
     assert abs(out["cost"] - ref["cost"]) <= 1e-5 * max(1.0, abs(ref["cost"]))
-    for k in ("dW0", "dW1", "dW2", "dIt"):
+    for k in ("dW0", "dW1", "dW2"):
         scale = np.abs(ref[k]).max()
-        np.testing.assert_allclose(out[k], ref[k], rtol=2e-3, atol=GRAD_ATOL * scale + 1e-12, err_msg=k)
+        np.testing.assert_allclose(out[k], ref[k], rtol=GRAD_RTOL, atol=GRAD_ATOL * scale + 1e-12, err_msg=k)
+    np.testing.assert_allclose(out["dIt"], ref["dIt"], rtol=2e-3, atol=1e-4 * np.abs(ref["dIt"]).max() + 1e-12, err_msg="dIt")
     if model != g.MODEL_YOUTUBE:
         np.testing.assert_allclose(out["datt"], ref["datt"], rtol=2e-3, atol=2e-5 * np.abs(ref["datt"]).max() + 1e-12)
     valid = hist >= 0                                   # gradients of padded slots are never scattered

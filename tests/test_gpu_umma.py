@@ -5,7 +5,7 @@ import pytest
 
 import go_ctr_b200 as g
 from oracle import oracle as orc
-from tests.test_gpu_parity import GRAD_ATOL, SCORE_RTOL, SHAPES, setup
+from tests.test_gpu_parity import GRAD_ATOL, GRAD_RTOL, SCORE_RTOL, SHAPES, setup
 from tests.util import assert_mostly_close, make_batch
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
@@ -36,10 +36,13 @@ def test_umma_gradients_match_oracle_and_fp32_engine(model):
     ws = orc.Workspace(o0, len(y))
     orc.forward(o0, W, X, orc.make_ranges(ocfg.uP, ocfg.S, ocfg.D, ocfg.cF), ws=ws)
     ref = orc.backward(o0, W, ws, y)
-    for k in ("dW0", "dW1", "dW2", "dIt"):
+    for k in ("dW0", "dW1", "dW2"):
         scale = np.abs(ref[k]).max()
-        np.testing.assert_allclose(out[k], ref[k], rtol=2e-3, atol=GRAD_ATOL * scale + 1e-12, err_msg=k)
-        np.testing.assert_allclose(out[k], fp32[k], rtol=2e-3, atol=GRAD_ATOL * scale + 1e-12, err_msg=k + " vs fp32 engine")
+        np.testing.assert_allclose(out[k], ref[k], rtol=GRAD_RTOL, atol=GRAD_ATOL * scale + 1e-12, err_msg=k)
+        np.testing.assert_allclose(out[k], fp32[k], rtol=GRAD_RTOL, atol=GRAD_ATOL * scale + 1e-12, err_msg=k + " vs fp32 engine")
+    scale = np.abs(ref["dIt"]).max()
+    np.testing.assert_allclose(out["dIt"], ref["dIt"], rtol=2e-3, atol=1e-4 * scale + 1e-12, err_msg="dIt")
+    np.testing.assert_allclose(out["dIt"], fp32["dIt"], rtol=2e-3, atol=1e-4 * scale + 1e-12, err_msg="dIt vs fp32 engine")
     valid = hist >= 0
     np.testing.assert_allclose(out["dUb"][valid], ref["dUb"][valid], rtol=2e-3, atol=2e-5 * np.abs(ref["dUb"]).max() + 1e-12)
 
@@ -66,5 +69,42 @@ def test_umma_large_batch_matches_fp32_engine():
         eng, cfg, ocfg, W, tabs, (ur, ir, hist, y) = setup(g.MODEL_DIN_COS, "ns", 65536, seed=2, U=5000, I=40000, gemm=gm)
         res.append(eng.debug_grads_idx(ur, ir, hist, y, training=False))
     np.testing.assert_allclose(res[0]["logit"], res[1]["logit"], rtol=2e-5, atol=2e-6)
-    np.testing.assert_allclose(res[0]["dW0"], res[1]["dW0"], rtol=1e-3, atol=1e-5 * np.abs(res[1]["dW0"]).max())
+    np.testing.assert_allclose(res[0]["dW0"], res[1]["dW0"], rtol=2e-4, atol=2e-6 * np.abs(res[1]["dW0"]).max())
     np.testing.assert_allclose(res[0]["dIt"], res[1]["dIt"], rtol=1e-3, atol=1e-5 * np.abs(res[1]["dIt"]).max())
+
+
+@pytest.mark.timeout(300)
+def test_adam_trajectory_of_the_3xtf32_engine_stays_close_to_float32():
+    """All six GEMMs of the tcgen05 engine are error-compensated 3xTF32 (round 1 ran the two weight-gradient GEMMs with
+    ONE TF32 product per term: 1.8e-4 / 1.1e-4 on mlp0 / mlp1 in this very test).  200 Adam steps at the north-star dims
+    (D=64, S=50, batch 512, tables frozen, dropout off) on four implementations of the same step: the double-accumulating
+    checker (the truth), the CPU arm's float32 blocked SGEMM (= the arithmetic the reference's gonum Sgemm does), the
+    engine's exact-fp32 FFMA GEMMs, and the tcgen05 engine.  Adam divides every gradient entry by its own running
+    magnitude, so it amplifies rounding noise in the small entries: plain float32 ends 3e-7..5e-7 of the largest weight
+    away from the truth, the tcgen05 engine must stay within 5e-5 (measured 1.3e-5) and its costs must track to 1e-5."""
+    B, steps = 512, 200
+    kw = dict(dropout0=0.0, dropout1=0.0, table_opt=g.TABLE_FROZEN)
+    um, cfg, ocfg, W, (uf, itf, emb), _ = setup(g.MODEL_DIN_COS, "ns", B, seed=11, **kw, **UM)
+    fp, *_ = setup(g.MODEL_DIN_COS, "ns", B, seed=11, gemm=g.GEMM_FP32, **kw)
+    truth = orc.IdxTrainer(ocfg, orc.default_solver(seed=cfg.seed), W, uf, itf, emb)
+    sgemm = orc.IdxTrainer(ocfg, orc.default_solver(seed=cfg.seed), W, uf, itf, emb)
+    rng = np.random.default_rng(1234)
+    worst_cost = 0.0
+    for step in range(steps):
+        ur, ir, hist, y = make_batch(rng, uf.shape[0], itf.shape[0], B, cfg.S, zipf=True)
+        c_um = um.train_step_idx(ur, ir, hist, y).cost
+        fp.train_step_idx(ur, ir, hist, y)
+        c_tr, _ = truth.step(ur, ir, hist, y, table_lr=0.0)
+        sgemm.step_fast(ur, ir, hist, y, table_lr=0.0, nthreads=4)
+        worst_cost = max(worst_cost, abs(c_um - c_tr) / max(1.0, abs(c_tr)))
+    assert worst_cost <= 1e-5, worst_cost
+
+    def dist(ws):       # per tensor: largest deviation from the truth relative to the tensor's largest weight
+        return [float(np.abs(a - b).max() / np.abs(b).max()) for a, b in zip(ws, truth.W)]
+    d_um, d_fp, d_sg = dist(um.get_weights()), dist(fp.get_weights()), dist(sgemm.W)
+    print("trajectory distance from the double-accumulating truth after %d Adam steps (mlp0, mlp1, mlp2, att0):" % steps)
+    print("  tcgen05 (3xTF32):", d_um, " worst relative cost difference:", worst_cost)
+    print("  engine fp32 FFMA:", d_fp)
+    print("  CPU float32 blocked SGEMM:", d_sg)
+    for name, a, b, c in zip(("mlp0", "mlp1", "mlp2", "att0"), d_um, d_fp, d_sg):
+        assert a <= 5e-5, (name, a, b, c)
