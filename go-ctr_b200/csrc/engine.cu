@@ -514,6 +514,11 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
     a.dbg = h->umma_dbg;
     static const int pf = getenv("CTR_UMMA_PF") ? atoi(getenv("CTR_UMMA_PF")) : 0;     // measured: no gain (profiles/r02/EXPERIMENTS.md)
     a.pf = std::max(0, std::min(pf, 64));
+    // kind::tf32 ignores the low 13 mantissa bits of an operand word, so the raw activation tile is A_hi as it lies: the
+    // converters only write A_lo (bit-identical scores, test_raw_tile_as_hi_operand_is_bit_identical).  CTR_UMMA_RAWHI=0
+    // writes the truncated copy in place as well.
+    static const int rawhi = getenv("CTR_UMMA_RAWHI") ? atoi(getenv("CTR_UMMA_RAWHI")) : 1;
+    a.rawhi = rawhi;
     static const bool epi_old = getenv("CTR_UMMA_EPI_OLD") != nullptr;
     a.staged_epi = epi_old ? 0 : 1;
     int rc = launch(h, name, [&] {
@@ -540,6 +545,8 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
 
 int umma_dw(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtensorMap& mB, umma::DwArgs a) {
     a.ks = h->um.dw_ks; a.terms = h->um.dw_terms;
+    static const int rawhi = getenv("CTR_UMMA_RAWHI") ? atoi(getenv("CTR_UMMA_RAWHI")) : 1;
+    a.rawhi = rawhi;
     const int total_kb = (a.K + a.ks - 1) / a.ks;
     const int grid = std::max(1, std::min(total_kb, h->num_sms));
     const size_t smem = (size_t)a.stages * dw_stage_bytes(h->um, a.nb) + 8 * (3 * a.stages + 2) + 16 + 1024;

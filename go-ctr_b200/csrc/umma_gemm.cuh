@@ -42,6 +42,7 @@ struct Args {
     float drop_p; uint32_t seed, stream;
     int stages;
     int staged_epi;             // 1: the epilogue goes through per-warp shared-memory staging (coalesced 128-byte row segments)
+    int rawhi;                  // 1: the MMA reads the raw fp32 tile as A_hi (the tensor core ignores the low 13 mantissa bits)
     int kbk;                    // K elements per shared-memory stage (32 or 16): selects the kernel instantiation and the maps' box
     int pf;                     // activation k-blocks requested into L2 ahead of the shared-memory ring (0 = off)
     unsigned long long* dbg;    // optional timeline of CTA 0 (globaltimer ns): [it*8 + event], tiles at [4096 + t*4 + e]
@@ -267,7 +268,9 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         h.y = __uint_as_float(__float_as_uint(x[i].y) & 0xFFFFE000u); l.y = x[i].y - h.y;
                         h.z = __uint_as_float(__float_as_uint(x[i].z) & 0xFFFFE000u); l.z = x[i].z - h.z;
                         h.w = __uint_as_float(__float_as_uint(x[i].w) & 0xFFFFE000u); l.w = x[i].w - h.w;
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pa + 16u * (c + 128 * i)), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                        // kind::tf32 reads the upper 19 bits of each 32-bit operand word, i.e. the raw tile already IS A_hi
+                        // (bit-identical results, tests/test_gpu_umma.py); a.rawhi = 0 writes the truncated copy anyway
+                        if (!a.rawhi) asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pa + 16u * (c + 128 * i)), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pl + 16u * (c + 128 * i)), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
                     }
                     fence_proxy_async();                            // generic-proxy writes → visible to tcgen05.mma
@@ -484,6 +487,7 @@ struct DwArgs {
     int M, N;                   // valid rows / cols of C
     float* C; long ldc;
     int stages;
+    int rawhi;                  // 3 terms: the raw tiles serve as the hi operands (no in-place truncation)
     int ks;                     // samples per k-block / TMA box: 32 or 16
     int terms;                  // 3 = error-compensated 3xTF32 (hi/lo split of both operands, fp32-grade), 1 = one TF32-RN product per term
     int pf;                     // k-blocks requested into L2 ahead of the ring (0 = off)
@@ -637,7 +641,7 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         hv.y = __uint_as_float(__float_as_uint(x[u].y) & 0xFFFFE000u); lv.y = x[u].y - hv.y;
                         hv.z = __uint_as_float(__float_as_uint(x[u].z) & 0xFFFFE000u); lv.z = x[u].z - hv.z;
                         hv.w = __uint_as_float(__float_as_uint(x[u].w) & 0xFFFFE000u); lv.w = x[u].w - hv.w;
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ad[u]), "f"(hv.x), "f"(hv.y), "f"(hv.z), "f"(hv.w) : "memory");
+                        if (!a.rawhi) asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ad[u]), "f"(hv.x), "f"(hv.y), "f"(hv.z), "f"(hv.w) : "memory");
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ad[u] + hiBytes), "f"(lv.x), "f"(lv.y), "f"(lv.z), "f"(lv.w) : "memory");
                     } else {
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ad[u]), "f"(tf32_rn(x[u].x)), "f"(tf32_rn(x[u].y)),

@@ -108,3 +108,26 @@ def test_adam_trajectory_of_the_3xtf32_engine_stays_close_to_float32():
     print("  CPU float32 blocked SGEMM:", d_sg)
     for name, a, b, c in zip(("mlp0", "mlp1", "mlp2", "att0"), d_um, d_fp, d_sg):
         assert a <= 5e-5, (name, a, b, c)
+
+
+_RAWHI_SCRIPT = """
+import sys, numpy as np
+import go_ctr_b200 as g
+from tests.test_gpu_parity import setup
+eng, cfg, ocfg, W, tabs, (ur, ir, hist, y) = setup(g.MODEL_DIN_COS, "ns", 2048, seed=2, U=500, I=4000, gemm=g.GEMM_TCGEN05_3XTF32)
+out = eng.debug_grads_idx(ur, ir, hist, y, training=False)
+sys.stdout.buffer.write(out["logit"].tobytes() + out["dIt"].tobytes())
+"""
+
+
+def test_raw_tile_as_hi_operand_is_bit_identical():
+    """The converter warps only write A_lo: the MMA reads the raw fp32 activation tile as A_hi because kind::tf32 ignores
+    the low 13 mantissa bits of an operand word.  Logits (fwd0, fwd1) and item-row gradients (through dZ0 and dX) are
+    bit-identical to a run that truncates the tile in place first (CTR_UMMA_RAWHI=0; the switch is read once per process)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("1", "0"):
+        env = dict(os.environ, CTR_UMMA_RAWHI=flag, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        outs.append(subprocess.run([sys.executable, "-c", _RAWHI_SCRIPT], cwd=root, env=env, check=True, capture_output=True, timeout=100).stdout)
+    assert len(outs[0]) == 2048 * 4 + 2048 * 64 * 4 and outs[0] == outs[1]
