@@ -158,7 +158,9 @@ struct ctr_handle {
         float *Wt0[2] = {}, *Wt1[2] = {}, *W1s[2] = {}, *W0s[2] = {};     // [hi, lo]
         CUtensorMap mA_X0, mA_H0d, mA_dZ1, mA_dZ0;
         CUtensorMap mB_Wt0[2], mB_Wt1[2], mB_W1s[2], mB_W0s[2];
-        CUtensorMap mK_X0, mK_H0d, mK_dZ0, mK_dZ1;      // {32 x 32} boxes over [batch, width] for the weight-gradient GEMMs
+        CUtensorMap mK_X0, mK_H0d, mK_dZ0, mK_dZ1;      // {32 x ks} boxes over [batch, width] for the weight-gradient GEMMs
+        CUtensorMap m3_X0, m3_H0d, m3_dZ0, m3_dZ1;      // the same operands as ONE {32, ks, width/32} box per k-block
+        int dw_tma = 0;                                 // producer mode of k_umma_dw (DwArgs.tma)
         int dw_stages0 = 0, dw_stages1 = 0;
         int dw_ks = 16, dw_terms = 3;                   // samples per k-block; products per term (3 = error-compensated, fp32-grade)
     } um;
@@ -421,6 +423,26 @@ int make_map(ctr_handle* h, CUtensorMap* m, const float* base, uint64_t rows, ui
     return CTR_OK;
 }
 
+// {32 fp32, rows, width/32} view of a row-major [rows, width] matrix: dim 2 walks the 32-column blocks (stride 128 bytes),
+// so ONE box {32, box_rows, nblocks} lands as nblocks consecutive [box_rows x 128 B] column blocks in shared memory
+int make_map_blocks(ctr_handle* h, CUtensorMap* m, const float* base, uint64_t rows, uint64_t width, uint64_t ld, uint32_t box_rows, uint32_t nblocks) {
+    typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                            CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static PFN fn = nullptr;
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q; void* p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return CTR_ECUDA;
+        fn = (PFN)p;
+    }
+    cuuint64_t gdim[3] = {32, rows, width / 32};
+    cuuint64_t gstr[2] = {ld * sizeof(float), 32 * sizeof(float)};
+    cuuint32_t box[3] = {32, box_rows, nblocks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CTR_OK : CTR_ECUDA;
+}
+
 constexpr size_t kUmmaEpiBytes = (size_t)umma::kEpiWarps * umma::kEpiStageBytes + 32;     // staged-epilogue tiles
 // K elements per shared-memory stage: 32 (128-byte swizzle rows) or 16 (64-byte rows: half-size stages, twice as many).
 // The main loop is bound by the L2→SM traffic of the weight tiles, not by the ring depth, so the choice
@@ -444,6 +466,7 @@ bool umma_supported(const ctr_handle* h) {
 }
 
 // shared memory of one k-block of the weight-gradient GEMM: 8 A blocks + nb B blocks of (ks samples x 128 bytes), twice with lo copies
+constexpr size_t kDwSlack = 4096;          // one 32-sample column block
 template <class U> size_t dw_stage_bytes(const U& u, int nb) { return (size_t)(8 + nb) * u.dw_ks * 128 * (u.dw_terms == 3 ? 2 : 1); }
 
 int umma_init(ctr_handle* h) {
@@ -477,8 +500,17 @@ int umma_init(ctr_handle* h) {
     RET(make_map(h, &u.mK_H0d, h->H0d, c.batch, h->H0p, h->H0p, u.dw_ks, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     RET(make_map(h, &u.mK_dZ0, h->dZ0, c.batch, h->H0p, h->H0p, u.dw_ks, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     RET(make_map(h, &u.mK_dZ1, h->dZ1, c.batch, h->H1p, h->H1p, u.dw_ks, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    u.dw_stages0 = (int)std::min<size_t>(6, ((size_t)227 * 1024 - 2048) / dw_stage_bytes(u, h->H0p / 32));
-    u.dw_stages1 = (int)std::min<size_t>(6, ((size_t)227 * 1024 - 2048) / dw_stage_bytes(u, h->H1p / 32));
+    // producer mode: one 3-D box per operand when the driver accepts the block view (CTR_DW_TMA = 0 | 1 | 2 overrides)
+    u.dw_tma = getenv("CTR_DW_TMA") ? atoi(getenv("CTR_DW_TMA")) : 2;
+    if (u.dw_tma == 2 && (make_map_blocks(h, &u.m3_X0, h->X0, c.batch, h->Kp, h->Kp, u.dw_ks, h->Kp / 32) != CTR_OK ||
+                          make_map_blocks(h, &u.m3_H0d, h->H0d, c.batch, h->H0p, h->H0p, u.dw_ks, h->H0p / 32) != CTR_OK ||
+                          make_map_blocks(h, &u.m3_dZ0, h->dZ0, c.batch, h->H0p, h->H0p, u.dw_ks, h->H0p / 32) != CTR_OK ||
+                          make_map_blocks(h, &u.m3_dZ1, h->dZ1, c.batch, h->H1p, h->H1p, u.dw_ks, h->H1p / 32) != CTR_OK))
+        u.dw_tma = 1;
+    // kDwSlack: an operand with fewer than four 32-column blocks is still read as 128 rows by the MMA — the surplus rows
+    // (never stored) come from whatever follows, which must lie inside the allocation
+    u.dw_stages0 = (int)std::min<size_t>(6, ((size_t)227 * 1024 - 2048 - kDwSlack) / dw_stage_bytes(u, h->H0p / 32));
+    u.dw_stages1 = (int)std::min<size_t>(6, ((size_t)227 * 1024 - 2048 - kDwSlack) / dw_stage_bytes(u, h->H1p / 32));
     CU(h, cudaFuncSetAttribute(umma::k_umma_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const size_t smax = (size_t)227 * 1024;
     CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
@@ -544,12 +576,16 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
 }
 
 int umma_dw(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtensorMap& mB, umma::DwArgs a) {
-    a.ks = h->um.dw_ks; a.terms = h->um.dw_terms;
+    a.ks = h->um.dw_ks; a.terms = h->um.dw_terms; a.tma = h->um.dw_tma;
+    // tcgen05 TF32 MMAs cover 8 samples each and take >= ~65 ns whatever their width: the 3-term main loop is bound by their
+    // COUNT.  When C has <= 128 columns but > 128 rows (dW1: 200 x 96), accumulating Cᵀ needs one MMA per term, not two.
+    static const bool noswap = getenv("CTR_DW_NO_SWAP") != nullptr;
+    a.swap = (!noswap && a.M > 128 && a.N <= 128) ? 1 : 0;
     static const int rawhi = getenv("CTR_UMMA_RAWHI") ? atoi(getenv("CTR_UMMA_RAWHI")) : 1;
     a.rawhi = rawhi;
     const int total_kb = (a.K + a.ks - 1) / a.ks;
     const int grid = std::max(1, std::min(total_kb, h->num_sms));
-    const size_t smem = (size_t)a.stages * dw_stage_bytes(h->um, a.nb) + 8 * (3 * a.stages + 2) + 16 + 1024;
+    const size_t smem = (size_t)a.stages * dw_stage_bytes(h->um, a.nb) + 8 * (3 * a.stages + 2) + 16 + 1024 + kDwSlack;
     static const int pf = getenv("CTR_UMMA_DW_PF") ? atoi(getenv("CTR_UMMA_DW_PF")) : 0;
     a.pf = std::max(0, std::min(pf, 16));
     static const bool norot = getenv("CTR_DW_NO_ROTATE") != nullptr;
@@ -557,16 +593,19 @@ int umma_dw(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtens
     a.tl = h->umma_dbg;
     int rc = launch(h, name, [&] { umma::k_umma_dw<<<grid, 448, smem, h->stream>>>(mA, mB, a); });
     if (rc == CTR_OK && h->umma_dbg) {
-        std::vector<unsigned long long> t(64);
+        std::vector<unsigned long long> t(1024);
         cudaStreamSynchronize(h->stream);
-        cudaMemcpy(t.data(), h->umma_dbg, 64 * 8, cudaMemcpyDeviceToHost);
-        cudaMemset(h->umma_dbg, 0, 64 * 8);
+        cudaMemcpy(t.data(), h->umma_dbg, 1024 * 8, cudaMemcpyDeviceToHost);
+        cudaMemset(h->umma_dbg, 0, 1024 * 8);
         FILE* f = fopen("gpurun_out/umma_timeline.txt", "a");
         if (f) {
             fprintf(f, "# %s K=%d na=%d nb=%d ks=%d terms=%d stages=%d pf=%d grid=%d\n", name, a.K, a.na, a.nb, a.ks, a.terms, a.stages, a.pf, grid);
             fprintf(f, "first_box_landed %llu accumulators_done %llu kernel_end %llu  mma_batches:", t[1] - t[0], t[2] - t[0], t[3] - t[0]);
             for (int i = 8; i < 64 && t[i]; i++) fprintf(f, " %llu", t[i] - t[0]);
             fprintf(f, "\n");
+            for (int it = 0; it < 24 && t[128 + it * 4]; it++)
+                fprintf(f, "it %d tma_issue %llu conv_saw_full %llu conv_arrived %llu mma_saw_conv %llu\n", it, t[128 + it * 4] - t[0], t[128 + it * 4 + 1] - t[0],
+                        t[128 + it * 4 + 2] - t[0], t[128 + it * 4 + 3] - t[0]);
             fclose(f);
         }
     }
@@ -721,7 +760,8 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
     if (umdw) {   // dW1 += h0dᵀ · dZ1   (tcgen05, MN-major operands, split-K over the grid)
         umma::DwArgs a{}; a.K = B; a.na = h->H0p / 32; a.nb = h->H1p / 32; a.M = c.H0; a.N = h->H1p; a.C = h->G[1]; a.ldc = h->H1p;
         a.stages = h->um.dw_stages1;
-        RET(umma_dw(h, "umma_dW1_splitk", h->um.mK_H0d, h->um.mK_dZ1, a));
+        const bool t3 = h->um.dw_tma == 2;
+        RET(umma_dw(h, "umma_dW1_splitk", t3 ? h->um.m3_H0d : h->um.mK_H0d, t3 ? h->um.m3_dZ1 : h->um.mK_dZ1, a));
     } else {   // dW1 += h0dᵀ · dZ1
         GemmArgs g{}; g.A = h->H0d; g.lda = h->H0p; g.B = h->dZ1; g.ldb = h->H1p; g.C = h->G[1]; g.ldc = h->H1p;
         g.M = c.H0; g.N = c.H1; g.K = B;
@@ -739,7 +779,8 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
     if (umdw) {   // dW0 += x0ᵀ · dZ0
         umma::DwArgs a{}; a.K = B; a.na = h->Kp / 32; a.nb = h->H0p / 32; a.M = h->in; a.N = h->H0p; a.C = h->G[0]; a.ldc = h->H0p;
         a.stages = h->um.dw_stages0;
-        RET(umma_dw(h, "umma_dW0_splitk", h->um.mK_X0, h->um.mK_dZ0, a));
+        const bool t3 = h->um.dw_tma == 2;
+        RET(umma_dw(h, "umma_dW0_splitk", t3 ? h->um.m3_X0 : h->um.mK_X0, t3 ? h->um.m3_dZ0 : h->um.mK_dZ0, a));
     } else {   // dW0 += x0ᵀ · dZ0
         GemmArgs g{}; g.A = h->X0; g.lda = h->Kp; g.B = h->dZ0; g.ldb = h->H0p; g.C = h->G[0]; g.ldc = h->H0p;
         g.M = h->in; g.N = c.H0; g.K = B;

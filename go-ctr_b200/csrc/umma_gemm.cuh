@@ -83,9 +83,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // L2 prefetch of a box (no shared-memory destination, no barrier): the later tma_load_2d of the same box is an L2 hit
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" :: "l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
@@ -488,6 +495,8 @@ struct DwArgs {
     float* C; long ldc;
     int stages;
     int rawhi;                  // 3 terms: the raw tiles serve as the hi operands (no in-place truncation)
+    int swap;                   // 1: accumulate Cᵀ — needs N (cols of C) <= 128; halves the MMA count when M > 128 >= N
+    int tma;                    // producer: 0 = 2-D boxes from one thread, 1 = one lane per 2-D box, 2 = one 3-D box per operand (3-D maps)
     int ks;                     // samples per k-block / TMA box: 32 or 16
     int terms;                  // 3 = error-compensated 3xTF32 (hi/lo split of both operands, fp32-grade), 1 = one TF32-RN product per term
     int pf;                     // k-blocks requested into L2 ahead of the ring (0 = off)
@@ -548,7 +557,7 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-#define DWDBG(idx) do { if (a.tl && blockIdx.x == 0 && (idx) < 64) a.tl[(idx)] = gtimer(); } while (0)
+#define DWDBG(idx) do { if (a.tl && blockIdx.x == 0 && (idx) < 1024) a.tl[(idx)] = gtimer(); } while (0)
     if (threadIdx.x == 0) DWDBG(0);
     // this CTA's slice of the batch, in ks-sample k-blocks
     const int total_kb = (a.K + a.ks - 1) / a.ks;
@@ -558,10 +567,25 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const bool two_halves = a.M > 128;
 
     if (warp == 0) {
-        if (lane == 0) {
+        // TMA producer.  A k-block is na + nb column blocks of {32 fp32, ks samples}.  Issued as 2-D boxes by ONE thread the
+        // main loop ran at ~12 boxes/µs whatever their size — the issue rate of the producer thread — so (a.tma == 2)
+        // each operand comes as ONE 3-D box {32, ks, blocks} over a [32 | batch | width/32] view of the matrix, or
+        // (a.tma == 1) every lane of the producer warp issues one of the 2-D boxes.
+        if (a.tma == 1) {
+            for (int it = 0; it < nkb; it++) {
+                const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
+                mbar_wait(empty(s), ph ^ 1u);
+                if (lane == 0) mbar_expect_tx(full(s), aBytes + bBytes);
+                __syncwarp();
+                const int row = (kb0 + it) * a.ks;
+                if (lane < a.na) tma_load_2d(sA(s) + blk * lane, &tmA, full(s), 32 * lane, row);
+                else if (lane < a.na + a.nb) tma_load_2d(sB(s) + blk * (lane - a.na), &tmB, full(s), 32 * (lane - a.na), row);
+            }
+        } else if (lane == 0) {
             auto prefetch_ab = [&](int j) {
                 if (j >= nkb) return;
                 const int prow = (kb0 + j) * a.ks;
+                if (a.tma == 2) { tma_prefetch_3d(&tmA, 0, prow, 0); tma_prefetch_3d(&tmB, 0, prow, 0); return; }
                 for (int q = 0; q < a.na; q++) tma_prefetch_2d(&tmA, 32 * q, prow);
                 for (int q = 0; q < a.nb; q++) tma_prefetch_2d(&tmB, 32 * q, prow);
             };
@@ -570,20 +594,28 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
                 if (a.pf) prefetch_ab(it + stages + a.pf);
                 mbar_wait(empty(s), ph ^ 1u);
+                DWDBG(128 + it * 4 + 0);
                 mbar_expect_tx(full(s), aBytes + bBytes);
                 const int row = (kb0 + it) * a.ks;
-                for (int j = 0; j < a.na; j++) tma_load_2d(sA(s) + blk * j, &tmA, full(s), 32 * j, row);
-                for (int j = 0; j < a.nb; j++) tma_load_2d(sB(s) + blk * j, &tmB, full(s), 32 * j, row);
+                if (a.tma == 2) {
+                    tma_load_3d(sA(s), &tmA, full(s), 0, row, 0);
+                    tma_load_3d(sB(s), &tmB, full(s), 0, row, 0);
+                } else {
+                    for (int j = 0; j < a.na; j++) tma_load_2d(sA(s) + blk * j, &tmA, full(s), 32 * j, row);
+                    for (int j = 0; j < a.nb; j++) tma_load_2d(sB(s) + blk * j, &tmB, full(s), 32 * j, row);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = a.dbg == 2 ? idesc_tf32(kBlockM, bn) : idesc_tf32_mn(kBlockM, bn);
             const int ksteps = a.ks / 8;
+            const uint32_t idesc_sw = idesc_tf32_mn(kBlockM, a.na * 32);
             const uint64_t lo_off = (uint64_t)(hiBytes >> 4);            // hi → lo copy of the same operand, in descriptor address units
             for (int it = 0; it < nkb; it++) {
                 const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
                 mbar_wait(conv(s), ph);
+                DWDBG(128 + it * 4 + 3);
                 tc_fence_after();
                 uint64_t dA0 = desc_mn_sw128(sA(s), blk), dA1 = desc_mn_sw128(sA(s) + 4u * blk, blk), dB = desc_mn_sw128(sB(s), blk);
                 if (a.dbg == 2) { dA0 = desc_k_sw128(sA(s)); dA1 = desc_k_sw128(sA(s) + 4u * 4096u); dB = desc_k_sw128(sB(s)); }
@@ -594,6 +626,14 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 for (int k = 0; k < ksteps; k++) {                  // 8 samples per k-step = +1024 bytes = +64 in the address field
                     const uint64_t ko = (uint64_t)(k * 64);
                     const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+                    if (a.swap) {       // Cᵀ: the narrow operand supplies the 128 accumulator rows, the wide one all N columns — one MMA per term
+                        umma_tf32(tmem_base, dB + ko, dA0 + ko, idesc_sw, acc);
+                        if (split) {
+                            umma_tf32(tmem_base, dB + lo_off + ko, dA0 + ko, idesc_sw, 1u);
+                            umma_tf32(tmem_base, dB + ko, dA0 + lo_off + ko, idesc_sw, 1u);
+                        }
+                        continue;
+                    }
                     umma_tf32(tmem_base, dA0 + ko, dB + ko, idesc, acc);
                     if (split) {                                    // + A_lo·B_hi + A_hi·B_lo (A_lo·B_lo is below fp32 resolution)
                         umma_tf32(tmem_base, dA0 + lo_off + ko, dB + ko, idesc, 1u);
@@ -622,6 +662,7 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int s = it % stages; const uint32_t ph = (it / stages) & 1u;
             mbar_wait(full(s), ph);
             if (c == 0 && it == 0) DWDBG(1);
+            if (c == 0) DWDBG(128 + it * 4 + 1);
             const uint32_t pa = sA(s), pb = sB(s);
             const int na16 = (int)(aBytes / 16u);
             for (int i0 = c; i0 < n16; i0 += 384 * 4) {
@@ -651,12 +692,34 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             fence_proxy_async();
             mbar_arrive(conv(s));
+            if (c == 0) DWDBG(128 + it * 4 + 2);
         }
         if (warp >= 6 && nkb > 0) {                                 // epilogue warps 6..13: C += accumulators
             const int q = warp & 3, half = (warp - 6) >> 2;
             mbar_wait(tdone, 0);
             if (threadIdx.x == 192) DWDBG(2);
             tc_fence_after();
+            if (a.swap) {
+                // accumulator rows = columns of C (lane m = q*32 + lane), accumulator columns = rows of C: a warp's red.add of
+                // one accumulator column covers 32 consecutive floats of one row of C
+                const int m = q * 32 + lane;
+                const int nck = a.na * 2;                                    // 16-column chunks of the accumulator
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+                const int mine = (nck - half + 1) / 2;
+                const int rot = a.rotate ? (int)blockIdx.x : 0;
+                if (q * 32 < a.N)
+                    for (int kk = 0; kk < mine; kk++) {
+                        const int ci = half + 2 * ((kk + rot) % mine);
+                        uint32_t r[16];
+                        tmem_ld16_async(trow + (uint32_t)(ci * 16), r);
+                        tmem_ld_wait();
+                        if (m < a.N) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                if (ci * 16 + j < a.M) atomicAdd(a.C + (long)(ci * 16 + j) * a.ldc + m, __uint_as_float(r[j]));
+                        }
+                    }
+            } else {
             const int nchunks = bn / 16;
             // every CTA adds the same [M, N] block: walking it in the same order would put all 148 CTAs on the same
             // addresses at the same moment (same-address red ops serialise in L2), so each CTA starts at its own chunk
@@ -680,6 +743,7 @@ k_umma_dw(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                 red_add4(crow + j, a.dbg == 1 ? make_float4(1.f, 1.f, 1.f, 1.f) : make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
                     }
                 }
+            }
             }
         }
     }
