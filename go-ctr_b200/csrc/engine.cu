@@ -158,6 +158,9 @@ struct ctr_handle {
         float *Wt0[2] = {}, *Wt1[2] = {}, *W1s[2] = {}, *W0s[2] = {};     // [hi, lo]
         CUtensorMap mA_X0, mA_H0d, mA_dZ1, mA_dZ0;
         CUtensorMap mB_Wt0[2], mB_Wt1[2], mB_W1s[2], mB_W0s[2];
+        // transposed accumulation (k_umma_gemm<.., TR>) for the GEMMs whose weight tile is <= 128 rows: 256-row activation boxes
+        CUtensorMap mA_dZ0_tr, mB_W0s_tr[2];
+        int stages_dx_tr = 0;
         CUtensorMap mK_X0, mK_H0d, mK_dZ0, mK_dZ1;      // {32 x ks} boxes over [batch, width] for the weight-gradient GEMMs
         CUtensorMap m3_X0, m3_H0d, m3_dZ0, m3_dZ1;      // the same operands as ONE {32, ks, width/32} box per k-block
         int dw_tma = 0;                                 // producer mode of k_umma_dw (DwArgs.tma)
@@ -460,6 +463,18 @@ int umma_stages(int bn, int kbk) {
 size_t umma_smem(int bn, int stages, int kbk) {
     return (size_t)stages * umma_stage_bytes(bn, kbk) + 8 * (3 * stages + 4) + 16 + 1024 + kUmmaEpiBytes;
 }
+// transposed accumulation (dX): 256 activation rows per stage, 16 K-elements, no epilogue staging tiles; kTrSlack covers the 128-row
+// read of a weight tile with fewer rows (the surplus accumulator rows are never stored)
+constexpr int kTrKbk = 16;
+constexpr size_t kTrSlack = 4096;
+size_t umma_stage_bytes_tr(int bn) { return ((size_t)256 + (size_t)bn) * kTrKbk * 4 * 2; }
+int umma_stages_tr(int bn) { return (int)std::min<size_t>(6, ((size_t)227 * 1024 - 2048 - kTrSlack) / umma_stage_bytes_tr(bn)); }
+size_t umma_smem_tr(int bn, int stages) { return (size_t)stages * umma_stage_bytes_tr(bn) + 8 * (3 * stages + 4) + 16 + 1024 + kTrSlack; }
+// worth it once the 256-row tiles still fill the machine; CTR_UMMA_NO_TR=1 keeps every GEMM on 128-row tiles
+bool umma_use_tr(const ctr_handle* h, int M, int bn) {
+    static const bool off = getenv("CTR_UMMA_NO_TR") != nullptr;
+    return !off && bn <= 128 && (M + 255) / 256 >= h->num_sms;
+}
 
 bool umma_supported(const ctr_handle* h) {
     return h->H0p <= 256 && h->H1p <= 256 && round_up(2 * h->cfg.D, 16) <= 256 && h->H0p % 16 == 0 && h->H1p % 16 == 0;
@@ -487,6 +502,11 @@ int umma_init(ctr_handle* h) {
         RET(make_map(h, &u.mB_W1s[i], u.W1s[i], h->H0p, h->H1p, h->H1p, u.bn_fwd0, ksw(u.kbk_dz0), u.kbk_dz0));
         RET(make_map(h, &u.mB_W0s[i], u.W0s[i], u.bn_dx, h->H0p, h->H0p, u.bn_dx, ksw(u.kbk_dx), u.kbk_dx));
     }
+    if (u.bn_dx <= 128) {
+        RET(make_map(h, &u.mA_dZ0_tr, h->dZ0, h->Bmax, h->H0p, h->H0p, 256, ksw(kTrKbk), kTrKbk));
+        for (int i = 0; i < 2; i++) RET(make_map(h, &u.mB_W0s_tr[i], u.W0s[i], u.bn_dx, h->H0p, h->H0p, u.bn_dx, ksw(kTrKbk), kTrKbk));
+        u.stages_dx_tr = umma_stages_tr(u.bn_dx);
+    }
     RET(make_map(h, &u.mA_X0, h->X0, h->Bmax, h->Kp, h->Kp, umma::kBlockM, ksw(u.kbk_fwd0), u.kbk_fwd0));
     RET(make_map(h, &u.mA_H0d, h->H0d, h->Bmax, h->H0p, h->H0p, umma::kBlockM, ksw(u.kbk_fwd1), u.kbk_fwd1));
     RET(make_map(h, &u.mA_dZ1, h->dZ1, h->Bmax, h->H1p, h->H1p, umma::kBlockM, ksw(u.kbk_dz0), u.kbk_dz0));
@@ -513,12 +533,13 @@ int umma_init(ctr_handle* h) {
     u.dw_stages1 = (int)std::min<size_t>(6, ((size_t)227 * 1024 - 2048 - kDwSlack) / dw_stage_bytes(u, h->H1p / 32));
     CU(h, cudaFuncSetAttribute(umma::k_umma_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const size_t smax = (size_t)227 * 1024;
-    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
-    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
-    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
-    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
-    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
-    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_SIGMOID_DROP, true, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_DSIGMOID, true, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    CU(h, cudaFuncSetAttribute(umma::k_umma_gemm<umma::UEPI_STORE, true, kTrKbk, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
     if (getenv("CTR_UMMA_TIMELINE")) RET(dalloc(h, &h->umma_dbg, 8192));
     u.ready = true; u.dirty = true;
     return CTR_OK;
@@ -540,9 +561,10 @@ int umma_split_weights(ctr_handle* h) {
 
 template <int EPI>
 int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtensorMap* mB, umma::Args a) {
-    const int tiles = (a.M + umma::kBlockM - 1) / umma::kBlockM;
+    const int tile_rows = a.tr ? 256 : umma::kBlockM;
+    const int tiles = (a.M + tile_rows - 1) / tile_rows;
     const int grid = std::min(tiles, h->num_sms);
-    const size_t smem = umma_smem(a.bn, a.stages, a.kbk);
+    const size_t smem = a.tr ? umma_smem_tr(a.bn, a.stages) : umma_smem(a.bn, a.stages, a.kbk);
     a.dbg = h->umma_dbg;
     static const int pf = getenv("CTR_UMMA_PF") ? atoi(getenv("CTR_UMMA_PF")) : 0;     // measured: no gain (profiles/r02/EXPERIMENTS.md)
     a.pf = std::max(0, std::min(pf, 64));
@@ -554,8 +576,11 @@ int umma_gemm(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUte
     static const bool epi_old = getenv("CTR_UMMA_EPI_OLD") != nullptr;
     a.staged_epi = epi_old ? 0 : 1;
     int rc = launch(h, name, [&] {
-        if (a.kbk == 16) umma::k_umma_gemm<EPI, true, 16><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a);
-        else                  umma::k_umma_gemm<EPI, true, 32><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a);
+        if constexpr (EPI == umma::UEPI_STORE) {
+            if (a.tr) { umma::k_umma_gemm<EPI, true, kTrKbk, true><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a); return; }
+        }
+        if (a.kbk == 16) umma::k_umma_gemm<EPI, true, 16, false><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a);
+        else             umma::k_umma_gemm<EPI, true, 32, false><<<grid, 448, smem, h->stream>>>(mA, mB[0], mB[1], a);
     });
     if (rc == CTR_OK && h->umma_dbg) {
         std::vector<unsigned long long> t(8192);
@@ -792,6 +817,10 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
         if (um) {
             umma::Args a{}; a.M = B; a.N = 2 * c.D; a.Nz = h->lddx; a.K = h->H0p; a.bn = h->um.bn_dx; a.C = h->dX; a.ldc = h->lddx;
             a.stages = h->um.stages_dx; a.kbk = h->um.kbk_dx;
+            if (umma_use_tr(h, B, a.bn) && h->um.stages_dx_tr >= 2) {
+                a.tr = 1; a.kbk = kTrKbk; a.stages = h->um.stages_dx_tr;
+                RET(umma_gemm<umma::UEPI_STORE>(h, "umma_dX", h->um.mA_dZ0_tr, h->um.mB_W0s_tr, a));
+            } else
             RET(umma_gemm<umma::UEPI_STORE>(h, "umma_dX", h->um.mA_dZ0, h->um.mB_W0s, a));
         } else {   // d concat[:, uP:uP+2D] = dZ0 · W0[uP:uP+2D, :]ᵀ
             GemmArgs g{}; g.A = h->dZ0; g.lda = h->H0p; g.B = h->W[0] + (long)c.uP * h->H0p; g.ldb = h->H0p;

@@ -42,6 +42,7 @@ struct Args {
     float drop_p; uint32_t seed, stream;
     int stages;
     int staged_epi;             // 1: the epilogue goes through per-warp shared-memory staging (coalesced 128-byte row segments)
+    int tr;                     // 1: transposed accumulation (template TR): 256-row tiles, weight tile as the MMA's M operand; needs bn <= 128
     int rawhi;                  // 1: the MMA reads the raw fp32 tile as A_hi (the tensor core ignores the low 13 mantissa bits)
     int kbk;                    // K elements per shared-memory stage (32 or 16): selects the kernel instantiation and the maps' box
     int pf;                     // activation k-blocks requested into L2 ahead of the shared-memory ring (0 = off)
@@ -155,7 +156,11 @@ __device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
 
 // KBK: fp32 elements of K per shared-memory stage — 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B:
 // half-size stages, twice as many of them in the same shared memory)
-template <int EPI, bool SPLIT3, int KBK>
+// TR (plain-store epilogue only: dX): the accumulator holds Cᵀ — the WEIGHT tile (bn <= 128 rows) is the MMA's M operand
+// and 256 batch rows are its N operand.  A TF32 MMA covers K = 8 and occupies the tensor pipe >= ~65 ns however narrow it
+// is, so one 128x256x8 MMA per term replaces two 128xbnx8 ones, and the epilogue stores coalesced rows without staging.
+// Measured: dX 35.2 → 31.5 µs; the same variant with the sigmoid epilogue made fwd1 slower (33.4 → 43.1 µs) and was dropped.
+template <int EPI, bool SPLIT3, int KBK, bool TR>
 __global__ void __launch_bounds__(448, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
             const __grid_constant__ CUtensorMap tmBlo, Args a) {
@@ -163,7 +168,9 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int bn = a.bn, stages = a.stages;
-    constexpr uint32_t kABytes = (uint32_t)kBlockM * KBK * 4u;
+    static_assert(!TR || EPI == UEPI_STORE, "transposed accumulation is wired for the plain-store epilogue only");
+    constexpr int kTileRows = TR ? 256 : kBlockM;                     // batch rows per tile
+    constexpr uint32_t kABytes = (uint32_t)kTileRows * KBK * 4u;
     const uint32_t bBytes = (uint32_t)bn * (uint32_t)KBK * 4u;
     const uint32_t stBytes = kABytes * (SPLIT3 ? 2u : 1u) + bBytes * (SPLIT3 ? 2u : 1u);
     // stage s: [A | (Alo) | Bhi | (Blo)]
@@ -179,7 +186,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     auto tempty = [&](int i) { return bars + 8u * (3 * stages + 2 + i); };
     const uint32_t tmem_slot = bars + 8u * (3 * stages + 4);
     const uint32_t epi_base = (tmem_slot + 16u + 15u) & ~15u;          // kEpiWarps staging tiles (staged epilogue)
-    const int acc_stride = bn <= 128 ? 128 : 256;
+    const int acc_stride = TR ? 256 : (bn <= 128 ? 128 : 256);
     const uint32_t ncols = 2u * acc_stride;
 
     if (threadIdx.x == 0) {
@@ -195,7 +202,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     const int num_k = a.K / KBK;
-    const int num_tiles = (a.M + kBlockM - 1) / kBlockM;
+    const int num_tiles = (a.M + kTileRows - 1) / kTileRows;
 
     if (warp == 0) {
         if (lane == 0) {                                            // ---------------- TMA producer
@@ -204,7 +211,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
             const uint32_t total = (uint32_t)my_tiles * (uint32_t)num_k;
             auto prefetch_a = [&](uint32_t j) {
-                if (j < total) tma_prefetch_2d(&tmA, (int)(j % num_k) * KBK, ((int)blockIdx.x + (int)(j / num_k) * (int)gridDim.x) * kBlockM);
+                if (j < total) tma_prefetch_2d(&tmA, (int)(j % num_k) * KBK, ((int)blockIdx.x + (int)(j / num_k) * (int)gridDim.x) * kTileRows);
             };
             for (uint32_t j = stages; j < (uint32_t)(stages + a.pf); j++) prefetch_a(j);
             uint32_t it = 0;
@@ -215,7 +222,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(empty(s), ph ^ 1u);
                     mbar_expect_tx(full(s), kABytes + bBytes * (SPLIT3 ? 2u : 1u));
                     UDBG(it * 8 + 0);
-                    tma_load_2d(sA(s), &tmA, full(s), kb * KBK, tile * kBlockM);
+                    tma_load_2d(sA(s), &tmA, full(s), kb * KBK, tile * kTileRows);
                     tma_load_2d(sBhi(s), &tmBhi, full(s), kb * KBK, 0);
                     if (SPLIT3) tma_load_2d(sBlo(s), &tmBlo, full(s), kb * KBK, 0);
                 }
@@ -223,7 +230,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     } else if (warp == 1) {
         if (lane == 0) {                                            // ---------------- MMA issuer
-            const uint32_t idesc = idesc_tf32(kBlockM, bn);
+            const uint32_t idesc = TR ? idesc_tf32(kBlockM, 256) : idesc_tf32(kBlockM, bn);
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tcount++) {
                 const int acc = tcount & 1; const uint32_t aph = (tcount >> 1) & 1u;
@@ -240,10 +247,18 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int k = 0; k < KBK / 8; k++) {         // UMMA_K = 8 tf32 = 32 bytes = +2 in the address field
                         const uint64_t ko = (uint64_t)(k * 2);
-                        umma_tf32(d_tmem, dAhi + ko, dBhi + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        if (SPLIT3) {
-                            umma_tf32(d_tmem, dAhi + ko, dBlo + ko, idesc, 1u);
-                            umma_tf32(d_tmem, dAlo + ko, dBhi + ko, idesc, 1u);
+                        if (TR) {           // rows of D = weight rows, columns of D = the tile's 256 batch rows
+                            umma_tf32(d_tmem, dBhi + ko, dAhi + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            if (SPLIT3) {
+                                umma_tf32(d_tmem, dBlo + ko, dAhi + ko, idesc, 1u);
+                                umma_tf32(d_tmem, dBhi + ko, dAlo + ko, idesc, 1u);
+                            }
+                        } else {
+                            umma_tf32(d_tmem, dAhi + ko, dBhi + ko, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            if (SPLIT3) {
+                                umma_tf32(d_tmem, dAhi + ko, dBlo + ko, idesc, 1u);
+                                umma_tf32(d_tmem, dAlo + ko, dBhi + ko, idesc, 1u);
+                            }
                         }
                     }
                     umma_commit(empty(s));                          // smem stage reusable once these MMAs retire
@@ -262,23 +277,27 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(full(s), ph);
                     if (c == 0) UDBG(it * 8 + 1);
                     const uint32_t pa = sA(s), pl = sAlo(s);
-                    constexpr int NV = (int)(kABytes / 16u / 128u);     // float4 per thread: 128 threads x NV x 16 B = the A tile; all loads first
-                    float4 x[NV];
+                    constexpr int NV = (int)(kABytes / 16u / 128u);     // float4 per thread: 128 threads x NV x 16 B = the activation tile
+                    constexpr int NP = NV < 8 ? NV : 8;                  // handled NP at a time: all loads of a part first
 #pragma unroll
-                    for (int i = 0; i < NV; i++)
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
-                                     : "r"(pa + 16u * (c + 128 * i)));
+                    for (int p0 = 0; p0 < NV; p0 += NP) {
+                        float4 x[NP];
 #pragma unroll
-                    for (int i = 0; i < NV; i++) {
-                        float4 h, l;
-                        h.x = __uint_as_float(__float_as_uint(x[i].x) & 0xFFFFE000u); l.x = x[i].x - h.x;
-                        h.y = __uint_as_float(__float_as_uint(x[i].y) & 0xFFFFE000u); l.y = x[i].y - h.y;
-                        h.z = __uint_as_float(__float_as_uint(x[i].z) & 0xFFFFE000u); l.z = x[i].z - h.z;
-                        h.w = __uint_as_float(__float_as_uint(x[i].w) & 0xFFFFE000u); l.w = x[i].w - h.w;
-                        // kind::tf32 reads the upper 19 bits of each 32-bit operand word, i.e. the raw tile already IS A_hi
-                        // (bit-identical results, tests/test_gpu_umma.py); a.rawhi = 0 writes the truncated copy anyway
-                        if (!a.rawhi) asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pa + 16u * (c + 128 * i)), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pl + 16u * (c + 128 * i)), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                        for (int i = 0; i < NP; i++)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                                         : "r"(pa + 16u * (c + 128 * (p0 + i))));
+#pragma unroll
+                        for (int i = 0; i < NP; i++) {
+                            float4 h, l;
+                            h.x = __uint_as_float(__float_as_uint(x[i].x) & 0xFFFFE000u); l.x = x[i].x - h.x;
+                            h.y = __uint_as_float(__float_as_uint(x[i].y) & 0xFFFFE000u); l.y = x[i].y - h.y;
+                            h.z = __uint_as_float(__float_as_uint(x[i].z) & 0xFFFFE000u); l.z = x[i].z - h.z;
+                            h.w = __uint_as_float(__float_as_uint(x[i].w) & 0xFFFFE000u); l.w = x[i].w - h.w;
+                            // kind::tf32 reads the upper 19 bits of each 32-bit operand word, i.e. the raw tile already IS A_hi
+                            // (bit-identical results, tests/test_gpu_umma.py); a.rawhi = 0 writes the truncated copy anyway
+                            if (!a.rawhi) asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pa + 16u * (c + 128 * (p0 + i))), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(pl + 16u * (c + 128 * (p0 + i))), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                        }
                     }
                     fence_proxy_async();                            // generic-proxy writes → visible to tcgen05.mma
                     mbar_arrive(conv(s));
@@ -302,6 +321,29 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const long gm = (long)tile * kBlockM + row_in_tile;
             const uint32_t trow = tmem_base + (uint32_t)(acc * acc_stride) + ((uint32_t)(q * 32) << 16);
             const uint32_t ctr0 = (uint32_t)((uint64_t)gm * (uint64_t)a.N);
+            if (TR) {
+                // lane = output feature f (accumulator row), accumulator columns = the tile's 256 batch rows: the warp's store
+                // of one column is 32 consecutive floats of one row of C — coalesced without staging
+                const int f = q * 32 + lane;
+                const long tile_row0 = (long)tile * kTileRows;
+                if (q * 32 < a.Nz) {
+                    for (int ci = half; ci < kTileRows / 16; ci += 2) {
+                        uint32_t r[16];
+                        tmem_ld16_async(trow + (uint32_t)(ci * 16), r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const long grow = tile_row0 + ci * 16 + j;
+                            float v = __uint_as_float(r[j]);
+                            v = f < a.N ? v : 0.0f;
+                            if (grow < a.M && f < a.Nz) a.C[grow * a.ldc + f] = v;
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty(acc));
+                continue;
+            }
             if (a.staged_epi) {
                 // Staged epilogue.  tcgen05.ld hands every thread one ROW of the tile, so storing straight from registers
                 // writes 32 different rows per instruction (16 useful bytes of each 128-byte line).  Here a warp transposes
