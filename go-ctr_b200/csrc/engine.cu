@@ -900,7 +900,7 @@ int step_core(ctr_handle* h, const RowSrc& r, int B, const StepOpts& o) {
             a.sp[1][1] = SplitOut{u.W1s[0], u.W1s[1], (long)h->H1p, 0, 0, c.H0};                  // W1  [H0, H1]
             a.nsp[0] = a.nsp[1] = 2;
         }
-        RET(launch(h, "adam_dense", [&] { k_adam<<<h->num_sms, 256, 0, h->stream>>>(a); }));
+        RET(launch(h, "adam_dense", [&] { k_adam<<<h->num_sms * 2, 256, 0, h->stream>>>(a); }));
         h->um.dirty = !split_in_adam;
         h->step++;
     }

@@ -278,31 +278,44 @@ struct AdamArgs {
     float gscale;       // 1/world after the all-reduce(sum) of the ranks' local-mean gradients, else 1
 };
 
-__global__ void __launch_bounds__(256) k_adam(AdamArgs a) {
-    for (int ti = 0; ti < a.nt; ti++) {
-        const AdamTensor& t = a.t[ti];
-        long n = (long)t.rows * t.cols;
-        for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-            long off = (i / t.cols) * t.ld + (i % t.cols);
-            float w = t.w[off];
-            float g = t.g[off] * a.gscale;
-            if (a.l2 != 0.0f) g = g + a.l2 * w;
-            g = g * a.inv_batch;
-            float m = a.b1 * t.m[off] + (1.0f - a.b1) * g;
-            float v = a.b2 * t.v[off] + (1.0f - a.b2) * (g * g);
-            t.m[off] = m; t.v[off] = v;
-            const float wn = w - a.lr * (m / a.c1) / (sqrtf(v / a.c2) + a.eps);
-            t.w[off] = wn;
-            t.g[off] = 0.0f;
-            for (int k = 0; k < a.nsp[ti]; k++) {
-                const SplitOut& so = a.sp[ti][k];
-                const int r = (int)(i / t.cols) - so.r0, c = (int)(i % t.cols);
-                if (r < 0 || r >= so.nr) continue;
-                const float hi = __uint_as_float(__float_as_uint(wn) & 0xFFFFE000u);
-                const long o = so.transpose ? (long)c * so.old + r : (long)r * so.old + c;
-                so.hi[o] = hi; so.lo[o] = wn - hi;
-            }
-        }
+// element j of tensor TI (a compile-time index: the kernel parameters are read from the constant bank, not copied)
+template <int TI>
+__device__ __forceinline__ void adam_elem(const AdamArgs& a, int j) {
+    const AdamTensor& t = a.t[TI];
+    const int r = j / t.cols, c = j - r * t.cols;
+    const long off = (long)r * t.ld + c;
+    const float w = t.w[off];
+    float g = t.g[off] * a.gscale;
+    if (a.l2 != 0.0f) g = g + a.l2 * w;
+    g = g * a.inv_batch;
+    const float m = a.b1 * t.m[off] + (1.0f - a.b1) * g;
+    const float v = a.b2 * t.v[off] + (1.0f - a.b2) * (g * g);
+    t.m[off] = m; t.v[off] = v;
+    const float wn = w - a.lr * (m / a.c1) / (sqrtf(v / a.c2) + a.eps);
+    t.w[off] = wn;
+    t.g[off] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (k >= a.nsp[TI]) break;
+        const SplitOut& so = a.sp[TI][k];
+        const int rr = r - so.r0;
+        if (rr < 0 || rr >= so.nr) continue;
+        const float hi = __uint_as_float(__float_as_uint(wn) & 0xFFFFE000u);
+        const long o = so.transpose ? (long)c * so.old + rr : (long)rr * so.old + c;
+        so.hi[o] = hi; so.lo[o] = wn - hi;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_adam(const __grid_constant__ AdamArgs a) {
+    // one flat index space over the (up to four) tensors: a thread's elements are independent, so their loads are all in
+    // flight together — the tensors one after the other cost one dependent DRAM round trip each for 63 k parameters
+    const int p1 = a.t[0].rows * a.t[0].cols, p2 = p1 + a.t[1].rows * a.t[1].cols, p3 = p2 + a.t[2].rows * a.t[2].cols;
+    const int p4 = a.nt > 3 ? p3 + a.t[3].rows * a.t[3].cols : p3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p4; i += gridDim.x * blockDim.x) {
+        if (i < p1) adam_elem<0>(a, i);
+        else if (i < p2) adam_elem<1>(a, i - p1);
+        else if (i < p3) adam_elem<2>(a, i - p2);
+        else adam_elem<3>(a, i - p3);
     }
 }
 
