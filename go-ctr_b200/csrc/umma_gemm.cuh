@@ -356,8 +356,8 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const long tile_row0 = (long)tile * kBlockM + q * 32;
                 const int nch32 = (a.Nz + 31) / 32;
                 const float kp = a.drop_p > 0.0f ? 1.0f - a.drop_p : 1.0f;
-                // dsigmoid: the H tile of a chunk is fetched (coalesced) one chunk AHEAD, while the previous chunk's
-                // results drain to global memory — the epilogue of a K = 96 GEMM is otherwise a chain of dependent round trips
+                // dsigmoid: the H tile of a chunk is fetched (coalesced) one chunk AHEAD — issued as soon as the current chunk's H has
+                // moved from the registers to the staging tile — the epilogue of a K = 96 GEMM is otherwise a chain of dependent round trips
                 float4 hn[8];
                 auto fetch_h = [&](int c0n) {
 #pragma unroll
@@ -378,6 +378,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(stg + (uint32_t)(4 * j + sub) * kEpiRowBytes + (uint32_t)c4 * 4u),
                                          "f"(hn[j].x), "f"(hn[j].y), "f"(hn[j].z), "f"(hn[j].w) : "memory");
                         __syncwarp();
+                        if (cj + 2 < nch32) fetch_h((cj + 2) * 32);      // hn is free again: the next chunk's H is in flight under this chunk's math and stores
                     }
                     tmem_ld_wait();
                     float v[32];
@@ -413,7 +414,6 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     for (int j = 0; j < 32; j += 4)
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(my_row + (uint32_t)j * 4u), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
                     __syncwarp();
-                    if (EPI == UEPI_DSIGMOID && cj + 2 < nch32) fetch_h((cj + 2) * 32);   // in flight while this chunk drains
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const long gr = tile_row0 + 4 * j + sub;
