@@ -473,7 +473,8 @@ size_t umma_smem_tr(int bn, int stages) { return (size_t)stages * umma_stage_byt
 // worth it once the 256-row tiles still fill the machine; CTR_UMMA_NO_TR=1 keeps every GEMM on 128-row tiles
 bool umma_use_tr(const ctr_handle* h, int M, int bn) {
     static const bool off = getenv("CTR_UMMA_NO_TR") != nullptr;
-    return !off && bn <= 128 && (M + 255) / 256 >= h->num_sms;
+    // bn == 128 only: a narrower weight tile would still be read as 128 rows by the MMA, i.e. past its own buffer
+    return !off && bn == 128 && (M + 255) / 256 >= h->num_sms;
 }
 
 bool umma_supported(const ctr_handle* h) {
@@ -502,7 +503,7 @@ int umma_init(ctr_handle* h) {
         RET(make_map(h, &u.mB_W1s[i], u.W1s[i], h->H0p, h->H1p, h->H1p, u.bn_fwd0, ksw(u.kbk_dz0), u.kbk_dz0));
         RET(make_map(h, &u.mB_W0s[i], u.W0s[i], u.bn_dx, h->H0p, h->H0p, u.bn_dx, ksw(u.kbk_dx), u.kbk_dx));
     }
-    if (u.bn_dx <= 128) {
+    if (u.bn_dx == 128) {
         RET(make_map(h, &u.mA_dZ0_tr, h->dZ0, h->Bmax, h->H0p, h->H0p, 256, ksw(kTrKbk), kTrKbk));
         for (int i = 0; i < 2; i++) RET(make_map(h, &u.mB_W0s_tr[i], u.W0s[i], u.bn_dx, h->H0p, h->H0p, u.bn_dx, ksw(kTrKbk), kTrKbk));
         u.stages_dx_tr = umma_stages_tr(u.bn_dx);
@@ -605,7 +606,8 @@ int umma_dw(ctr_handle* h, const char* name, const CUtensorMap& mA, const CUtens
     // tcgen05 TF32 MMAs cover 8 samples each and take >= ~65 ns whatever their width: the 3-term main loop is bound by their
     // COUNT.  When C has <= 128 columns but > 128 rows (dW1: 200 x 96), accumulating Cᵀ needs one MMA per term, not two.
     static const bool noswap = getenv("CTR_DW_NO_SWAP") != nullptr;
-    a.swap = (!noswap && a.M > 128 && a.N <= 128) ? 1 : 0;
+    // nb >= 3: the 128-row read of the narrow operand then overruns its buffer by at most one block (kDwSlack)
+    a.swap = (!noswap && a.M > 128 && a.N <= 128 && a.nb >= 3) ? 1 : 0;
     static const int rawhi = getenv("CTR_UMMA_RAWHI") ? atoi(getenv("CTR_UMMA_RAWHI")) : 1;
     a.rawhi = rawhi;
     const int total_kb = (a.K + a.ks - 1) / a.ks;
